@@ -1,0 +1,143 @@
+/* rk_b200.h — C ABI of the B200-native repkiller grouping path (librk_b200.so).
+ *
+ * The reference has no FFI layer: its boundary for this path is the C++ surface called from
+ * execWithParams/main (/root/reference/src/repkiller.cpp:52,83-96).  Each entry point below names the
+ * reference interface it replaces.  Plain pointers and sizes only; no exceptions cross this boundary; every
+ * function returns an rk_status (0 = ok, negative = error, message via rk_last_error).  There is no CPU
+ * fallback: without a CUDA device rk_create fails.
+ */
+#ifndef RK_B200_H
+#define RK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RK_FRAG_BYTES 109u /* sizeof(struct FragFile) under #pragma pack(1), src/structs.h:2,12-51 */
+#define RK_NONE 0xFFFFFFFFu
+
+typedef enum {
+  RK_OK = 0,
+  RK_ERR_CUDA = -1,     /* a CUDA call failed (rk_last_error has the CUDA message) */
+  RK_ERR_ARG = -2,      /* bad argument (null, misaligned device pointer, non-positive ratio, ...) */
+  RK_ERR_RANGE = -3,    /* input the reference itself cannot process: xStart/10 >= vsize (out-of-bounds write at
+                           src/FragmentsDatabase.cpp:96-97), a center outside the occupation lists
+                           (src/SequenceOcupationList.cpp:16-18), or a coordinate >= 2^31 */
+  RK_ERR_STATE = -4,    /* call order: rk_group before rk_load_aos, ... */
+  RK_ERR_NOMEM = -5,
+  RK_ERR_INTERNAL = -6  /* an internal invariant failed (bounded spin expired, worklist overflow) */
+} rk_status;
+
+/* rk_group / rk_load_aos flags */
+#define RK_F_HOST_RESULT 1u /* copy order/gid/repval/identity to library-owned pinned host arrays */
+#define RK_F_NO_SORT 2u     /* stop after generate_fragment_groups: members stay in push_back (rank) order */
+#define RK_F_TIMING 4u      /* record per-stage CUDA-event times into rk_result / rk_load_stats */
+
+enum { /* stage indices of ms_stage[] */
+  RK_ST_H2D = 0,     /* host -> device copy of the records (0 when the input was a device pointer) */
+  RK_ST_DECODE,      /* K1  AoS -> SoA decode + validity + link bits                                  */
+  RK_ST_RANKSORT,    /* K2a stable LSD radix sort by xStart/10                                        */
+  RK_ST_KEYS,        /* K2  rank-order SoA gather + super-bucket keys                                  */
+  RK_ST_XSORT,       /* K2b stable sort by (strand class, X super-bucket)                              */
+  RK_ST_YSORT,       /* K2c stable sort by (strand class, Y super-bucket)                              */
+  RK_ST_XMATCH,      /* K3  X pass of generate_fragment_groups                                         */
+  RK_ST_YMATCH,      /* K3  Y pass                                                                     */
+  RK_ST_FOREST,      /* K4  roots + group ids                                                          */
+  RK_ST_HKEY,        /* K5a generate_diagonal_func evaluated per fragment + sort key                   */
+  RK_ST_GSORT,       /* K5b stable sort by gid + per-group std::sort order                             */
+  RK_ST_FINAL,       /* K5c output order, repval, identity                                             */
+  RK_ST_D2H,         /* device -> host copy of the result (RK_F_HOST_RESULT)                           */
+  RK_NSTAGES
+};
+
+typedef struct rk_ctx rk_ctx;
+
+typedef struct {
+  uint64_t n_loaded;  /* records handed to rk_load_aos */
+  uint64_t n_kept;    /* records the reference iterates: xStart/10 < vsize-1 (FragmentsDatabase.h:29-31) */
+  uint64_t vsize;     /* FragmentsDatabase::getA(), src/FragmentsDatabase.cpp:84 */
+  float ms_stage[RK_NSTAGES];
+  float ms_device;    /* first kernel to last kernel on the context's stream */
+  uint64_t n_launches; /* kernels launched by this call */
+} rk_load_stats;
+
+typedef struct {
+  uint64_t n_kept;
+  uint64_t n_groups;  /* return value of generate_fragment_groups, src/commonFunctions.cpp:79 */
+  /* n_kept entries each, in output order: groups by id (creation order), members as sort_groups leaves them.
+   * Host pointers (pinned, owned by the context, valid until the next rk_group/rk_destroy) when
+   * RK_F_HOST_RESULT was given, else NULL. */
+  const uint32_t *order;    /* index of the record in the loaded array (file order) */
+  const uint32_t *gid;      /* the `block` column the writer prints, src/commonFunctions.cpp:102,127 */
+  const uint8_t *repval;    /* 0 singleton, 1 first of a group, 2 rest: src/commonFunctions.cpp:106-115 */
+  const float *identity;    /* (float)ident*100/(float)length, src/commonFunctions.cpp:103 */
+  /* the same four arrays on the device (always valid until the next rk_group/rk_destroy) */
+  const uint32_t *d_order;
+  const uint32_t *d_gid;
+  const uint8_t *d_repval;
+  const float *d_identity;
+  float ms_stage[RK_NSTAGES];
+  float ms_device;
+  uint64_t n_launches; /* kernels launched by this call */
+} rk_result;
+
+/* One context per GPU and per concurrent grouping (mirrors one FragmentsDatabase + the per-call
+ * SequenceOcupationLists, src/repkiller.cpp:52, src/commonFunctions.cpp:45-48).  Returns NULL on failure;
+ * rk_create_error() then has the reason. */
+rk_ctx *rk_create(int device);
+const char *rk_create_error(void);
+void rk_destroy(rk_ctx *ctx);
+const char *rk_last_error(const rk_ctx *ctx);
+
+/* Use `cuda_stream` (a cudaStream_t) for all work of this context instead of its own stream. */
+int rk_set_stream(rk_ctx *ctx, void *cuda_stream);
+
+/* Replaces FragmentsDatabase::FragmentsDatabase after text parsing (src/FragmentsDatabase.cpp:84-100):
+ * takes n records in the struct FragFile layout, file order, from host or device memory (a device pointer
+ * must be 16-byte aligned), and builds the processing order (the xStart/10 bucket array) and the
+ * occupation-list buckets on the device.  seqx_len/seqy_len are the LOADED lengths (header value + 1,
+ * src/FragmentsDatabase.cpp:62,65).  Synchronous. */
+int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags,
+                rk_load_stats *stats);
+
+/* Replaces generate_fragment_groups + generate_diagonal_func + sort_groups
+ * (src/commonFunctions.cpp:41-80,161-177,148-159; call sites src/repkiller.cpp:84-91) for one
+ * (len_ratio, pos_ratio) pair.  Both ratios must be > 0 (src/commonFunctions.cpp:26-27).  Synchronous. */
+int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk_result *out);
+
+/* Replaces generate_diagonal_func (src/commonFunctions.cpp:161-177): fills diag_func[0 .. vsize-2] (host
+ * memory, vsize = FragmentsDatabase::getA()) including the carry-forward over empty buckets. */
+int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func);
+
+/* Test/diagnostic access to intermediate device arrays of the last load/group, copied to `host` (capacity
+ * `bytes`).  Names: "rank_fidx", "parent", "gid_rank", "hkey".  Returns the number of bytes the array has, or
+ * a negative rk_status. */
+int64_t rk_debug_fetch(rk_ctx *ctx, const char *name, void *host, uint64_t bytes);
+
+/* Per-kernel device time: when enabled, every kernel launch of later calls on this context is bracketed by a
+ * CUDA-event pair on the context's stream.  rk_profile_read fills up to `cap` entries (one per kernel that
+ * ran; consecutive launches of the 3-kernel scan are one entry) and returns how many; reset != 0 clears. */
+typedef struct {
+  const char *name;
+  uint64_t launches;
+  double ms_total;
+} rk_kernel_time;
+int rk_profile_enable(rk_ctx *ctx, int on);
+int rk_profile_read(rk_ctx *ctx, rk_kernel_time *out, int cap, int reset);
+
+/* Stand-alone stable LSD radix sort of (u32 key, u32 value) pairs on the device (kernel K2), exported for
+ * tests and the multi-GPU driver.  All pointers are device pointers; values_in may be NULL (values = 0..n-1).
+ * `work` needs rk_sort_pairs_work_bytes(n) bytes.  The result is in keys_out/values_out. */
+uint64_t rk_sort_pairs_work_bytes(uint64_t n);
+int rk_sort_pairs(rk_ctx *ctx, const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out,
+                  uint32_t *values_out, uint32_t *keys_tmp, uint32_t *values_tmp, uint64_t n, int key_bits, void *work);
+
+const char *rk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

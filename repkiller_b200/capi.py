@@ -1,0 +1,211 @@
+"""ctypes binding of librk_b200.so (include/rk_b200.h).
+
+This is plumbing: the product is the CUDA library behind the C ABI.  There is no CPU path — importing works
+anywhere (so the symbol table can be checked), but creating a Context without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librk_b200.so")
+
+RK_NONE = 0xFFFFFFFF
+F_HOST_RESULT, F_NO_SORT, F_TIMING = 1, 2, 4
+STAGES = ["h2d", "decode", "ranksort", "keys", "xsort", "ysort", "xmatch", "ymatch", "forest", "hkey", "gsort",
+          "final", "d2h"]
+NSTAGES = len(STAGES)
+
+# every symbol include/rk_b200.h declares
+SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_group",
+           "rk_diagonal_func", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version"]
+
+
+class RkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rk status {code}: {msg}")
+        self.code = code
+
+
+class _LoadStats(C.Structure):
+    _fields_ = [("n_loaded", C.c_uint64), ("n_kept", C.c_uint64), ("vsize", C.c_uint64),
+                ("ms_stage", C.c_float * NSTAGES), ("ms_device", C.c_float), ("n_launches", C.c_uint64)]
+
+
+class _KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("ms_total", C.c_double)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_kept", C.c_uint64), ("n_groups", C.c_uint64),
+                ("order", C.POINTER(C.c_uint32)), ("gid", C.POINTER(C.c_uint32)), ("repval", C.POINTER(C.c_uint8)),
+                ("identity", C.POINTER(C.c_float)),
+                ("d_order", C.c_void_p), ("d_gid", C.c_void_p), ("d_repval", C.c_void_p), ("d_identity", C.c_void_p),
+                ("ms_stage", C.c_float * NSTAGES), ("ms_device", C.c_float), ("n_launches", C.c_uint64)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library (building it is __graft_entry__.build()'s job; fail loudly if it is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RkError(-1, f"{LIB_PATH} is missing: run `python -m repkiller_b200.build` (there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    L.rk_create.argtypes = [C.c_int]
+    L.rk_create.restype = C.c_void_p
+    L.rk_create_error.restype = C.c_char_p
+    L.rk_destroy.argtypes = [C.c_void_p]
+    L.rk_last_error.argtypes = [C.c_void_p]
+    L.rk_last_error.restype = C.c_char_p
+    L.rk_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.rk_load_aos.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(_LoadStats)]
+    L.rk_group.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint, C.POINTER(_Result)]
+    L.rk_diagonal_func.argtypes = [C.c_void_p, C.c_void_p]
+    L.rk_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64]
+    L.rk_debug_fetch.restype = C.c_int64
+    L.rk_sort_pairs_work_bytes.argtypes = [C.c_uint64]
+    L.rk_sort_pairs_work_bytes.restype = C.c_uint64
+    L.rk_sort_pairs.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_uint64, C.c_int, C.c_void_p]
+    L.rk_version.restype = C.c_char_p
+    L.rk_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.rk_profile_read.argtypes = [C.c_void_p, C.POINTER(_KernelTime), C.c_int, C.c_int]
+    _lib = L
+    return L
+
+
+@dataclass
+class LoadStats:
+    n_loaded: int
+    n_kept: int
+    vsize: int
+    ms_stage: dict
+    ms_device: float
+    n_launches: int = 0
+
+
+@dataclass
+class Groups:
+    """Result of one (len_ratio, pos_ratio) grouping, in the reference's output order."""
+    n_kept: int
+    n_groups: int
+    order: np.ndarray | None      # file index of each output line
+    gid: np.ndarray | None        # the `block` column
+    repval: np.ndarray | None
+    identity: np.ndarray | None
+    d_ptrs: dict = field(default_factory=dict)
+    ms_stage: dict = field(default_factory=dict)
+    ms_device: float = 0.0
+    n_launches: int = 0
+
+
+class Context:
+    """One GPU-resident fragment database + grouping workspace (FragmentsDatabase's role on the device)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        self._h = self._L.rk_create(device)
+        if not self._h:
+            raise RkError(-1, self._L.rk_create_error().decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RkError(rc, self._L.rk_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._L.rk_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def load(self, records, seqx_len: int, seqy_len: int, n: int | None = None, timing: bool = True) -> LoadStats:
+        """records: numpy array of 109-byte FragFile records (host), or an int device/host pointer with n given.
+        seqx_len/seqy_len are the LOADED lengths (header value + 1)."""
+        if isinstance(records, np.ndarray):
+            rec = np.ascontiguousarray(records)
+            assert rec.dtype.itemsize == 109 or rec.dtype == np.uint8
+            n = rec.nbytes // 109
+            ptr = rec.ctypes.data
+            self._keep = rec
+        else:
+            ptr = int(records)
+            assert n is not None
+        st = _LoadStats()
+        self._check(self._L.rk_load_aos(self._h, C.c_void_p(ptr), n, seqx_len, seqy_len, F_TIMING if timing else 0, C.byref(st)))
+        return LoadStats(st.n_loaded, st.n_kept, st.vsize, {STAGES[i]: st.ms_stage[i] for i in range(NSTAGES)}, st.ms_device,
+                         st.n_launches)
+
+    def group(self, len_ratio: float, pos_ratio: float, host_result: bool = True, sort: bool = True, timing: bool = True) -> Groups:
+        flags = (F_HOST_RESULT if host_result else 0) | (0 if sort else F_NO_SORT) | (F_TIMING if timing else 0)
+        r = _Result()
+        self._check(self._L.rk_group(self._h, len_ratio, pos_ratio, flags, C.byref(r)))
+        m = r.n_kept
+
+        def arr(p, dt):
+            if not host_result:
+                return None
+            if m == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(p, shape=(m,)).copy()
+
+        return Groups(m, r.n_groups, arr(r.order, np.uint32), arr(r.gid, np.uint32), arr(r.repval, np.uint8),
+                      arr(r.identity, np.float32),
+                      {"order": r.d_order, "gid": r.d_gid, "repval": r.d_repval, "identity": r.d_identity},
+                      {STAGES[i]: r.ms_stage[i] for i in range(NSTAGES)}, r.ms_device, r.n_launches)
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.rk_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kernel name: (launches, total ms)} accumulated since the last reset."""
+        buf = (_KernelTime * 32)()
+        k = self._L.rk_profile_read(self._h, buf, 32, int(reset))
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].ms_total)) for i in range(k)}
+
+    def diagonal_func(self, vsize: int) -> np.ndarray:
+        out = np.zeros(max(vsize - 1, 0), dtype=np.uint64)
+        if out.size:
+            self._check(self._L.rk_diagonal_func(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def debug_fetch(self, name: str) -> np.ndarray:
+        sz = self._L.rk_debug_fetch(self._h, name.encode(), None, 0)
+        if sz < 0:
+            self._check(int(sz))
+        out = np.zeros(sz // 4, dtype=np.uint32)
+        if sz:
+            got = self._L.rk_debug_fetch(self._h, name.encode(), C.c_void_p(out.ctypes.data), out.nbytes)
+            if got < 0:
+                self._check(int(got))
+        return out
+
+    def sort_pairs_device(self, keys_in: int, values_in: int | None, keys_out: int, values_out: int, keys_tmp: int,
+                          values_tmp: int, n: int, key_bits: int, work: int):
+        self._check(self._L.rk_sort_pairs(self._h, C.c_void_p(keys_in), C.c_void_p(values_in) if values_in else None,
+                                          C.c_void_p(keys_out), C.c_void_p(values_out), C.c_void_p(keys_tmp),
+                                          C.c_void_p(values_tmp), n, key_bits, C.c_void_p(work)))
+
+    def sort_pairs_work_bytes(self, n: int) -> int:
+        return int(self._L.rk_sort_pairs_work_bytes(n))

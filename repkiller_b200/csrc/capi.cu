@@ -1,0 +1,576 @@
+// C ABI of librk_b200.so (include/rk_b200.h): context, device workspace, and the launch sequences that stand
+// in for FragmentsDatabase's constructor (rk_load_aos) and for generate_fragment_groups +
+// generate_diagonal_func + sort_groups (rk_group).  Reference call sites: /root/reference/src/repkiller.cpp:52,84-91.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rk_b200.h"
+#include "rk_common.cuh"
+
+using namespace rk;
+
+namespace {
+
+std::string g_create_error;
+
+inline u64 align_up(u64 x, u64 a) { return (x + a - 1) / a * a; }
+inline int ceil_log2(u64 x) {  // bits needed to represent values 0 .. x-1
+  int b = 0;
+  while (b < 63 && (1ull << b) < x) ++b;
+  return b;
+}
+
+const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan", "k_radix_scatter", "k_keys", "k_match_small",
+                                             "k_match_long", "k_chase", "k_hkey", "k_pack", "k_groupsort_small",
+                                             "k_groupsort_large", "k_finalize", "k_diag_table"};
+
+// CUDA-event pair around every launch group; folded into per-kernel totals after each synchronisation
+struct Profiler {
+  bool on = false;
+  struct Rec { int kid; cudaEvent_t a, b; };
+  std::vector<Rec> open_recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[KID_COUNT] = {0};
+  u64 launches[KID_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void fold() {  // call after the stream was synchronised
+    for (auto &r : open_recs) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; launches[r.kid] += 1; }
+      else cudaGetLastError();
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    open_recs.clear();
+  }
+};
+thread_local Profiler *tl_prof = nullptr;
+
+struct Counters {  // small device block, mirrored in pinned host memory
+  u32 n_dropped;
+  u32 err;
+  u32 n_groups;
+  u32 pad;
+  u32 work_x[2];
+  u32 work_y[2];
+  u32 work_g[2];
+};
+
+}  // namespace
+
+struct rk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // device workspace (one allocation, carved by carve())
+  void *arena = nullptr;
+  u64 arena_bytes = 0;
+  u64 cap_n = 0;  // records the workspace was carved for
+
+  // pinned host result buffers
+  void *h_res = nullptr;
+  u64 h_res_cap = 0;
+  Counters *h_cnt = nullptr;
+
+  cudaEvent_t ev[RK_NSTAGES + 2];
+  Profiler prof;
+
+  bool loaded = false;
+  u64 n = 0;
+  u32 m = 0;
+  Geometry g{};
+  int bits_rank = 1, bits_x = 1, bits_y = 1;
+  bool have_group = false;
+
+  // carved pointers
+  u8 *d_aos = nullptr;
+  u32 *xs = nullptr, *ys = nullptr, *len = nullptr, *key0 = nullptr;
+  u8 *flags = nullptr;
+  float *identity_f = nullptr;
+  u32 *link_x = nullptr, *link_y = nullptr;
+  u64 link_x_words = 0, link_y_words = 0;
+  Counters *d_cnt = nullptr;
+  u32 *k0_r = nullptr, *fidx_r = nullptr;
+  u32 *tmp_k = nullptr, *tmp_v = nullptr;
+  u32 *cx_r = nullptr, *cy_r = nullptr, *len_r = nullptr, *ys_r = nullptr, *kx = nullptr, *ky = nullptr;
+  u32 *skx = nullptr, *rx = nullptr, *sky = nullptr, *ry = nullptr;
+  void *sort_work = nullptr;
+  u32 *parent = nullptr, *gid_rank = nullptr, *h = nullptr, *sgid = nullptr, *srank = nullptr;
+  void *forest_work = nullptr;
+  u64 *packed = nullptr;
+  u32 *worklist = nullptr;
+  u32 work_cap = 0;
+  u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr;
+  u32 *out_order = nullptr, *out_gid = nullptr;
+  u8 *out_repval = nullptr;
+  float *out_identity = nullptr;
+};
+
+namespace {
+
+int fail(rk_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(ctx, RK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));    \
+  } while (0)
+
+// carve the workspace for n records; returns bytes needed.  With base == nullptr only sizes are computed.
+u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
+  u64 off = 0;
+  auto take = [&](u64 bytes) -> u8 * {
+    u8 *p = base ? base + off : nullptr;
+    off += align_up(bytes ? bytes : 16, 256);
+    return p;
+  };
+  const u64 n1 = n ? n : 1;
+  c->d_cnt = (Counters *)take(sizeof(Counters));
+  c->d_aos = need_aos ? take(align_up(n1 * RK_FRAG_BYTES, 16) + 16) : nullptr;
+  c->xs = (u32 *)take(n1 * 4);
+  c->ys = (u32 *)take(n1 * 4);
+  c->len = (u32 *)take(n1 * 4);
+  c->key0 = (u32 *)take(n1 * 4);
+  c->flags = take(n1);
+  c->identity_f = (float *)take(n1 * 4);
+  c->link_x = (u32 *)take(lxw * 4);
+  c->link_y = (u32 *)take(lyw * 4);
+  c->k0_r = (u32 *)take(n1 * 4);
+  c->fidx_r = (u32 *)take(n1 * 4);
+  c->tmp_k = (u32 *)take(n1 * 4);
+  c->tmp_v = (u32 *)take(n1 * 4);
+  c->cx_r = (u32 *)take(n1 * 4);
+  c->cy_r = (u32 *)take(n1 * 4);
+  c->len_r = (u32 *)take(n1 * 4);
+  c->ys_r = (u32 *)take(n1 * 4);
+  c->kx = (u32 *)take(n1 * 4);
+  c->ky = (u32 *)take(n1 * 4);
+  c->skx = (u32 *)take(n1 * 4);
+  c->rx = (u32 *)take(n1 * 4);
+  c->sky = (u32 *)take(n1 * 4);
+  c->ry = (u32 *)take(n1 * 4);
+  c->sort_work = take(sort_work_bytes(n1));
+  c->parent = (u32 *)take(n1 * 4);
+  c->gid_rank = (u32 *)take(n1 * 4);
+  c->h = (u32 *)take(n1 * 4);
+  c->sgid = (u32 *)take(n1 * 4);
+  c->srank = (u32 *)take(n1 * 4);
+  c->forest_work = take(forest_work_bytes((u32)n1));
+  c->packed = (u64 *)take(n1 * 8);
+  c->work_cap = (u32)(n1 / 32 + 2);
+  c->worklist = (u32 *)take((u64)c->work_cap * 4);
+  c->ent_rank = (u32 *)take(n1 * 4);
+  c->ent_c = (u32 *)take(n1 * 4);
+  c->ent_len = (u32 *)take(n1 * 4);
+  c->out_order = (u32 *)take(n1 * 4);
+  c->out_gid = (u32 *)take(n1 * 4);
+  c->out_repval = take(n1);
+  c->out_identity = (float *)take(n1 * 4);
+  return off;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+const char *err_bits_text(u32 e) {
+  if (e & ERR_XBUCKET) return "a fragment has xStart/10 >= vsize (the reference writes out of bounds there)";
+  if (e & ERR_CENTER) return "a fragment center lies beyond its sequence's occupation list (xStart+length/2 > sequence length)";
+  if (e & ERR_COORD) return "a coordinate, length or center does not fit in 32 bits";
+  if (e & ERR_WORKLIST) return "internal: segment worklist overflow";
+  if (e & ERR_SPIN) return "internal: bounded wait expired";
+  return "unknown device error";
+}
+
+}  // namespace
+
+namespace rk {
+void prof_begin(int kid, cudaStream_t st) {
+  if (!tl_prof) return;
+  Profiler::Rec r{kid, tl_prof->get(), tl_prof->get()};
+  cudaEventRecord(r.a, st);
+  tl_prof->open_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!tl_prof) return;
+  cudaEventRecord(tl_prof->open_recs.back().b, st);
+}
+}  // namespace rk
+
+namespace {
+struct ProfGuard {  // routes the launchers' KScope events to this context for the duration of one API call
+  rk_ctx *c;
+  explicit ProfGuard(rk_ctx *ctx) : c(ctx) { tl_prof = ctx->prof.on ? &ctx->prof : nullptr; }
+  ~ProfGuard() {
+    if (tl_prof) {
+      cudaStreamSynchronize(c->stream);
+      tl_prof->fold();
+    }
+    tl_prof = nullptr;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+const char *rk_version(void) { return "repkiller-b200 0.1 (sm_100a)"; }
+const char *rk_create_error(void) { return g_create_error.c_str(); }
+
+rk_ctx *rk_create(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return nullptr;
+  }
+  rk_ctx *c = new rk_ctx;
+  c->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaHostAlloc((void **)&c->h_cnt, sizeof(Counters), cudaHostAllocDefault)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete c;
+    return nullptr;
+  }
+  c->own_stream = true;
+  for (auto &ev : c->ev) cudaEventCreate(&ev);
+  return c;
+}
+
+void rk_destroy(rk_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->arena) cudaFree(c->arena);
+  if (c->h_res) cudaFreeHost(c->h_res);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  for (auto &ev : c->ev) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *rk_last_error(const rk_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int rk_set_stream(rk_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return RK_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return RK_OK;
+}
+
+int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags,
+                rk_load_stats *stats) {
+  if (!ctx) return RK_ERR_ARG;
+  if (!frags && n) return fail(ctx, RK_ERR_ARG, "null record pointer");
+  if (n >= 0xFFFFFFF0ull) return fail(ctx, RK_ERR_ARG, "more than 2^32-16 records per context; partition the input");
+  if (seqx_len >= (1ull << 32) || seqy_len >= (1ull << 32))
+    return fail(ctx, RK_ERR_RANGE, "sequence length does not fit in 32 bits");
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  ctx->loaded = false;
+  ctx->have_group = false;
+
+  bool on_device = false;
+  if (n) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, frags) == cudaSuccess) on_device = pa.type == cudaMemoryTypeDevice;
+    else cudaGetLastError();
+  }
+  if (on_device && ((uintptr_t)frags & 15)) return fail(ctx, RK_ERR_ARG, "device record pointer must be 16-byte aligned");
+
+  Geometry g{};
+  g.lx = seqx_len;
+  g.ly = seqy_len;
+  g.vsize = (u32)(1 + seqx_len / XBUCKET);  // FragmentsDatabase.cpp:84
+  g.mx = (u32)(seqx_len / DIVISOR);         // SequenceOcupationList.cpp:4
+  g.my = (u32)(seqy_len / DIVISOR);
+  g.nbx = g.mx + 2;
+  g.nby = g.my + 2;
+  const u64 lxw = (2ull * g.nbx + 31) / 32 + 1, lyw = (2ull * g.nby + 31) / 32 + 1;
+
+  // (re)carve the workspace
+  const bool need_aos = !on_device;
+  const u64 need = carve(ctx, nullptr, n, need_aos, lxw, lyw);
+  if (need > ctx->arena_bytes) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->arena, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, RK_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)need, cudaGetErrorString(e));
+    }
+    ctx->arena_bytes = need;
+  }
+  carve(ctx, (u8 *)ctx->arena, n, need_aos, lxw, lyw);
+  ctx->link_x_words = lxw;
+  ctx->link_y_words = lyw;
+  ctx->n = n;
+  ctx->g = g;
+  ctx->bits_rank = ceil_log2(g.vsize);
+  ctx->bits_x = ceil_log2(2ull * g.nbx);
+  ctx->bits_y = ceil_log2(2ull * g.nby);
+
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t *ev = ctx->ev;
+  CK(cudaEventRecord(ev[0], st));
+  const u8 *aos = (const u8 *)frags;
+  if (!on_device && n) {
+    CK(cudaMemcpyAsync(ctx->d_aos, frags, n * RK_FRAG_BYTES, cudaMemcpyHostToDevice, st));
+    aos = ctx->d_aos;
+  }
+  CK(cudaEventRecord(ev[1], st));
+  CK(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), st));
+  CK(cudaMemsetAsync(ctx->link_x, 0, lxw * 4, st));
+  CK(cudaMemsetAsync(ctx->link_y, 0, lyw * 4, st));
+  u64 launches = 0;
+  launches += launch_decode(aos, n, g, ctx->xs, ctx->ys, ctx->len, ctx->flags, ctx->identity_f, ctx->key0, ctx->link_x, ctx->link_y,
+                &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st);
+  CK(cudaEventRecord(ev[2], st));
+  // the rank sort does not depend on the number of dropped records: they carry the largest key and sort last
+  launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st);
+  CK(cudaEventRecord(ev[3], st));
+  CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (ctx->h_cnt->err) return fail(ctx, (ctx->h_cnt->err & (ERR_WORKLIST | ERR_SPIN)) ? RK_ERR_INTERNAL : RK_ERR_RANGE, "%s",
+                                   err_bits_text(ctx->h_cnt->err));
+  const u32 m = (u32)(n - ctx->h_cnt->n_dropped);
+  ctx->m = m;
+
+  CK(cudaEventRecord(ev[4], st));
+  launches += launch_keys(ctx->fidx_r, m, g, ctx->xs, ctx->ys, ctx->len, ctx->flags, ctx->link_x, ctx->link_y, ctx->cx_r, ctx->cy_r,
+              ctx->len_r, ctx->ys_r, ctx->kx, ctx->ky, st);
+  CK(cudaEventRecord(ev[5], st));
+  launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st);
+  CK(cudaEventRecord(ev[6], st));
+  launches += launch_sort_pairs(ctx->ky, nullptr, ctx->sky, ctx->ry, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_y, ctx->sort_work, st);
+  CK(cudaEventRecord(ev[7], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  ctx->loaded = true;
+
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->n_loaded = n;
+    stats->n_kept = m;
+    stats->vsize = g.vsize;
+    stats->n_launches = launches;
+    if (flags & RK_F_TIMING) {
+      stats->ms_stage[RK_ST_H2D] = ev_ms(ev[0], ev[1]);
+      stats->ms_stage[RK_ST_DECODE] = ev_ms(ev[1], ev[2]);
+      stats->ms_stage[RK_ST_RANKSORT] = ev_ms(ev[2], ev[3]);
+      stats->ms_stage[RK_ST_KEYS] = ev_ms(ev[4], ev[5]);
+      stats->ms_stage[RK_ST_XSORT] = ev_ms(ev[5], ev[6]);
+      stats->ms_stage[RK_ST_YSORT] = ev_ms(ev[6], ev[7]);
+      stats->ms_device = ev_ms(ev[1], ev[3]) + ev_ms(ev[4], ev[7]);
+    }
+  }
+  return RK_OK;
+}
+
+int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk_result *out) {
+  if (!ctx || !out) return RK_ERR_ARG;
+  if (!ctx->loaded) return fail(ctx, RK_ERR_STATE, "rk_group before a successful rk_load_aos");
+  if (!(len_ratio > 0)) return fail(ctx, RK_ERR_ARG, "Ratio between length and position must be greater than zero");
+  if (!(pos_ratio > 0)) return fail(ctx, RK_ERR_ARG, "Position proximity must be greater than zero");
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  memset(out, 0, sizeof *out);
+  const u32 m = ctx->m;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t *ev = ctx->ev;
+  u64 launches = 0;
+
+  if ((flags & RK_F_HOST_RESULT) && m) {
+    const u64 need = (u64)m * 13 + 1024;
+    if (need > ctx->h_res_cap) {
+      if (ctx->h_res) cudaFreeHost(ctx->h_res);
+      ctx->h_res = nullptr;
+      ctx->h_res_cap = 0;
+      CK(cudaHostAlloc(&ctx->h_res, need, cudaHostAllocDefault));
+      ctx->h_res_cap = need;
+    }
+  }
+
+  CK(cudaEventRecord(ev[0], st));
+  MatchArgs mx{};
+  mx.skey = ctx->skx, mx.srank = ctx->rx, mx.c_r = ctx->cx_r, mx.len_r = ctx->len_r, mx.parent = ctx->parent;
+  mx.m = m, mx.max_index = ctx->g.mx, mx.len_ratio = len_ratio, mx.pos_ratio = pos_ratio, mx.is_y = 0;
+  mx.worklist = ctx->worklist, mx.work_count = ctx->d_cnt->work_x, mx.work_cap = ctx->work_cap;
+  mx.ent_rank = ctx->ent_rank, mx.ent_c = ctx->ent_c, mx.ent_len = ctx->ent_len, mx.err = &ctx->d_cnt->err;
+  launches += launch_match(mx, st);
+  CK(cudaEventRecord(ev[1], st));
+  MatchArgs my = mx;
+  my.skey = ctx->sky, my.srank = ctx->ry, my.c_r = ctx->cy_r, my.max_index = ctx->g.my, my.is_y = 1;
+  my.work_count = ctx->d_cnt->work_y;
+  launches += launch_match(my, st);
+  CK(cudaEventRecord(ev[2], st));
+  launches += launch_forest(ctx->parent, m, ctx->gid_rank, &ctx->d_cnt->n_groups, ctx->forest_work, st);
+  CK(cudaEventRecord(ev[3], st));
+  launches += launch_hkey(ctx->k0_r, ctx->ys_r, m, ctx->h, st);
+  CK(cudaEventRecord(ev[4], st));
+  // gids are < number of groups <= m; sorting by ceil_log2(m) bits avoids a host round trip for the count
+  launches += launch_sort_pairs(ctx->gid_rank, nullptr, ctx->sgid, ctx->srank, ctx->tmp_k, ctx->tmp_v, m, ceil_log2(m),
+                                ctx->sort_work, st);
+  OrderArgs oa{};
+  oa.sgid = ctx->sgid, oa.srank = ctx->srank, oa.h = ctx->h, oa.fidx_r = ctx->fidx_r, oa.identity_f = ctx->identity_f;
+  oa.packed = ctx->packed, oa.m = m, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1;
+  oa.worklist = ctx->worklist, oa.work_count = ctx->d_cnt->work_g, oa.work_cap = ctx->work_cap;
+  oa.out_order = ctx->out_order, oa.out_gid = ctx->out_gid, oa.out_repval = ctx->out_repval, oa.out_identity = ctx->out_identity;
+  oa.err = &ctx->d_cnt->err;
+  // K5b = gid sort + per-group order; K5c = finalize (timed together with K5b's tail inside launch_order)
+  launches += launch_order(oa, st);
+  CK(cudaEventRecord(ev[5], st));
+  CK(cudaEventRecord(ev[6], st));
+  u8 *hb = (u8 *)ctx->h_res;
+  u32 *h_order = nullptr, *h_gid = nullptr;
+  float *h_ident = nullptr;
+  u8 *h_rep = nullptr;
+  if ((flags & RK_F_HOST_RESULT) && m) {
+    h_order = (u32 *)hb;
+    h_gid = (u32 *)(hb + align_up((u64)m * 4, 256));
+    h_ident = (float *)(hb + 2 * align_up((u64)m * 4, 256));
+    h_rep = hb + 3 * align_up((u64)m * 4, 256);
+    CK(cudaMemcpyAsync(h_order, ctx->out_order, (u64)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_gid, ctx->out_gid, (u64)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_ident, ctx->out_identity, (u64)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_rep, ctx->out_repval, (u64)m, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(ev[7], st));
+  CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
+  ctx->have_group = true;
+
+  out->n_kept = m;
+  out->n_groups = ctx->h_cnt->n_groups;
+  out->order = h_order;
+  out->gid = h_gid;
+  out->repval = h_rep;
+  out->identity = h_ident;
+  out->d_order = ctx->out_order;
+  out->d_gid = ctx->out_gid;
+  out->d_repval = ctx->out_repval;
+  out->d_identity = ctx->out_identity;
+  out->n_launches = launches;
+  if (flags & RK_F_TIMING) {
+    out->ms_stage[RK_ST_XMATCH] = ev_ms(ev[0], ev[1]);
+    out->ms_stage[RK_ST_YMATCH] = ev_ms(ev[1], ev[2]);
+    out->ms_stage[RK_ST_FOREST] = ev_ms(ev[2], ev[3]);
+    out->ms_stage[RK_ST_HKEY] = ev_ms(ev[3], ev[4]);
+    out->ms_stage[RK_ST_GSORT] = ev_ms(ev[4], ev[5]);
+    out->ms_stage[RK_ST_D2H] = ev_ms(ev[6], ev[7]);
+    out->ms_device = ev_ms(ev[0], ev[5]);
+  }
+  return RK_OK;
+}
+
+int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func) {
+  if (!ctx || !diag_func) return RK_ERR_ARG;
+  if (!ctx->loaded) return fail(ctx, RK_ERR_STATE, "rk_diagonal_func before rk_load_aos");
+  CK(cudaSetDevice(ctx->device));
+  const u32 nb = ctx->g.vsize - 1;
+  if (nb == 0) return RK_OK;
+  u64 *d = nullptr;
+  CK(cudaMalloc(&d, (u64)nb * 8));
+  launch_diag_table(ctx->k0_r, ctx->ys_r, ctx->m, ctx->g.vsize, d, nullptr, ctx->stream);
+  cudaError_t e = cudaMemcpyAsync(diag_func, d, (u64)nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, RK_ERR_CUDA, "rk_diagonal_func: %s", cudaGetErrorString(e));
+  return RK_OK;
+}
+
+int64_t rk_debug_fetch(rk_ctx *ctx, const char *name, void *host, uint64_t bytes) {
+  if (!ctx || !name) return RK_ERR_ARG;
+  if (!ctx->loaded) return fail(ctx, RK_ERR_STATE, "nothing loaded");
+  const void *src = nullptr;
+  u64 sz = (u64)ctx->m * 4;
+  if (!strcmp(name, "rank_fidx")) src = ctx->fidx_r;
+  else if (!strcmp(name, "k0_r")) src = ctx->k0_r;
+  else if (!strcmp(name, "skx")) src = ctx->skx;
+  else if (!strcmp(name, "rx")) src = ctx->rx;
+  else if (!strcmp(name, "sky")) src = ctx->sky;
+  else if (!strcmp(name, "ry")) src = ctx->ry;
+  else if (!strcmp(name, "parent")) src = ctx->parent;
+  else if (!strcmp(name, "gid_rank")) src = ctx->gid_rank;
+  else if (!strcmp(name, "hkey")) src = ctx->h;
+  else return fail(ctx, RK_ERR_ARG, "unknown array %s", name);
+  if ((!strcmp(name, "parent") || !strcmp(name, "gid_rank") || !strcmp(name, "hkey")) && !ctx->have_group)
+    return fail(ctx, RK_ERR_STATE, "no rk_group result yet");
+  if (host && bytes >= sz && sz) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, src, sz, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return (int64_t)sz;
+}
+
+int rk_profile_enable(rk_ctx *ctx, int on) {
+  if (!ctx) return RK_ERR_ARG;
+  ctx->prof.on = on != 0;
+  return RK_OK;
+}
+
+int rk_profile_read(rk_ctx *ctx, rk_kernel_time *out, int cap, int reset) {
+  if (!ctx) return RK_ERR_ARG;
+  int k = 0;
+  for (int i = 0; i < KID_COUNT && out && k < cap; ++i) {
+    if (!ctx->prof.launches[i]) continue;
+    out[k].name = kKernelNames[i];
+    out[k].launches = ctx->prof.launches[i];
+    out[k].ms_total = ctx->prof.ms[i];
+    ++k;
+  }
+  if (reset) {
+    for (int i = 0; i < KID_COUNT; ++i) ctx->prof.ms[i] = 0, ctx->prof.launches[i] = 0;
+  }
+  return k;
+}
+
+uint64_t rk_sort_pairs_work_bytes(uint64_t n) { return sort_work_bytes(n ? n : 1); }
+
+int rk_sort_pairs(rk_ctx *ctx, const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
+                  uint32_t *keys_tmp, uint32_t *values_tmp, uint64_t n, int key_bits, void *work) {
+  if (!ctx || !keys_in || !keys_out || !values_out || !keys_tmp || !values_tmp || !work) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  launch_sort_pairs(keys_in, values_in, keys_out, values_out, keys_tmp, values_tmp, n, key_bits, work, ctx->stream);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return RK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// Shared device helpers and the launcher declarations of the grouping kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RK_NONE32 0xFFFFFFFFu
+
+namespace rk {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+// record layout: /root/reference/src/structs.h:12-51 under #pragma pack(1)
+constexpr int FRAG_BYTES = 109;
+constexpr int OFF_XSTART = 8;
+constexpr int OFF_YSTART = 16;
+constexpr int OFF_LENGTH = 40;
+constexpr int OFF_IDENT = 48;
+constexpr int OFF_STRAND = 92;
+
+// constants of the reference
+constexpr u32 XBUCKET = 10;   // FragmentsDatabase.cpp:84,96 ; commonFunctions.cpp:152,154
+constexpr u32 DIVISOR = 100;  // SequenceOcupationList.h:11
+
+// per-fragment flag bits
+constexpr u8 FL_REVERSE = 1;  // strand != 'f' (commonFunctions.cpp:52-53)
+constexpr u8 FL_DROPPED = 2;  // xStart/10 == vsize-1 (FragmentsDatabase.h:29-31)
+
+// error bits raised by kernels (device word, OR-ed)
+constexpr u32 ERR_COORD = 1;     // coordinate >= 2^31
+constexpr u32 ERR_XBUCKET = 2;   // xStart/10 >= vsize
+constexpr u32 ERR_CENTER = 4;    // center/100 beyond the occupation list
+constexpr u32 ERR_WORKLIST = 8;  // long-segment worklist overflow
+constexpr u32 ERR_SPIN = 16;     // bounded spin expired
+
+struct Geometry {
+  u64 lx, ly;      // loaded sequence lengths (header + 1)
+  u32 vsize;       // 1 + lx/10
+  u32 mx, my;      // max_index = len / 100 (SequenceOcupationList.cpp:4)
+  u32 nbx, nby;    // buckets per strand class on each axis (max_index + 2: one slack bucket for "next" links)
+};
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+  u32 m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// streaming loads/stores: data touched once should not displace the gather targets in L1
+__device__ __forceinline__ u32 ld_stream(const u32 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(u32 *p, u32 v) { __stcs(p, v); }
+
+// "next"-bucket probes of get_associated_group (SequenceOcupationList.cpp:58,80): center+1 is probed iff
+// center < max_index, center+2 iff center < max_index-1 in unsigned arithmetic (wraps when max_index == 0).
+__device__ __forceinline__ bool probes_next(u32 c, u32 max_index) {
+  const u32 r = c % DIVISOR;
+  if (r == 99) return c < max_index || max_index == 0;
+  if (r == 98) return max_index == 0 || c < max_index - 1;
+  return false;
+}
+// "previous"-bucket probes (:47,69): center-1 iff center > 0, center-2 iff center > 1.
+__device__ __forceinline__ bool probes_prev(u32 c) { return (c % DIVISOR) <= 1 && c >= DIVISOR; }
+
+__device__ __forceinline__ u32 absdiff(u32 a, u32 b) { return a > b ? a - b : b - a; }
+
+// ---- per-kernel timing (CUDA events around every launch; off unless rk_profile_enable) ---------------
+enum KernelId {
+  KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
+  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_COUNT
+};
+void prof_begin(int kid, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct KScope {
+  cudaStream_t st;
+  KScope(int kid, cudaStream_t s) : st(s) { prof_begin(kid, s); }
+  ~KScope() { prof_end(st); }
+};
+
+// ---- launchers (each returns the number of kernels it launched) -------------------------------------
+
+// K1: decode n packed records (device, 16-byte aligned) into file-order SoA, raise link bits.
+int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity,
+                  u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st);
+
+// K2: stable LSD radix sort of (key,value) pairs; result in keys_out/vals_out.
+u64 sort_work_bytes(u64 n);
+int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp,
+                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st);
+
+// K2 keys: rank-order SoA + super-bucket sort keys.
+int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *ys, const u32 *len, const u8 *flags,
+                const u32 *link_x, const u32 *link_y, u32 *cx_r, u32 *cy_r, u32 *len_r, u32 *ys_r, u32 *kx,
+                u32 *ky, cudaStream_t st);
+
+// K3: one axis pass of generate_fragment_groups.  is_y: fragments with parent != NONE insert unconditionally.
+struct MatchArgs {
+  const u32 *skey;   // sorted super-bucket keys
+  const u32 *srank;  // rank of the fragment at each sorted position
+  const u32 *c_r;    // centers on this axis, rank order
+  const u32 *len_r;  // lengths, rank order
+  u32 *parent;       // rank-indexed; X pass writes every entry, Y pass fills unmatched ones
+  u32 m;
+  u32 max_index;     // axis max_index
+  double len_ratio, pos_ratio;
+  int is_y;
+  u32 *worklist;     // long segments (start positions)
+  u32 *work_count;   // [0] number of long segments
+  u32 work_cap;
+  u32 *ent_rank, *ent_c, *ent_len;  // scratch of m entries each for long segments
+  u32 *err;
+};
+int launch_match(const MatchArgs &a, cudaStream_t st);
+
+// K4: roots, group ids.
+u64 forest_work_bytes(u32 m);
+int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st);
+
+// K5a: h = |yStart - yStart(last fragment of the same xStart/10 bucket)| per rank.
+int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st);
+
+// K5a': the full diag_func table with carry-forward (only for rk_diagonal_func).
+int launch_diag_table(const u32 *k0_r, const u32 *ys_r, u32 m, u32 vsize, u64 *diag, void *work, cudaStream_t st);
+
+// K5b/c: after the stable sort by gid: pack (h, rank), per-group libstdc++ std::sort order, outputs.
+struct OrderArgs {
+  const u32 *sgid;    // sorted gids
+  const u32 *srank;   // rank at each sorted position
+  const u32 *h;       // by rank
+  const u32 *fidx_r;  // file index by rank
+  const float *identity_f;  // by file index
+  u64 *packed;        // scratch m
+  u32 m;
+  int do_sort;
+  u32 *worklist, *work_count;
+  u32 work_cap;
+  u32 *out_order, *out_gid;
+  u8 *out_repval;
+  float *out_identity;
+  u32 *err;
+};
+int launch_order(const OrderArgs &a, cudaStream_t st);
+
+}  // namespace rk

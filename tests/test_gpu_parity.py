@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden outputs.
+Run on the B200 box: python -m pytest tests -m gpu"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from repkiller_b200 import capi, gen
+from repkiller_b200.frags import FRAG_DTYPE, make_header
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def first_diff(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return f"shape {a.shape} vs {b.shape}"
+    d = np.nonzero(a != b)[0]
+    if d.size == 0:
+        return None
+    i = int(d[0])
+    return f"{d.size} diffs, first at {i}: got {a[max(0, i - 2):i + 3]} want {b[max(0, i - 2):i + 3]}"
+
+
+def assert_same(name, got, want):
+    msg = first_diff(got, want)
+    assert msg is None, f"{name}: {msg}"
+
+
+def check_against_oracle(ctx, rec, lx1, ly1, lr, pr, stages=True):
+    st = ctx.load(rec, lx1, ly1)
+    g = O.group(rec, lx1, ly1, lr, pr)
+    assert st.n_kept == g.n_kept
+    assert st.vsize == g.vsize
+    if stages and g.n_kept:
+        assert_same("rank_fidx", ctx.debug_fetch("rank_fidx"), g.rank_fidx)
+    res = ctx.group(lr, pr)
+    if stages and g.n_kept:
+        assert_same("parent", ctx.debug_fetch("parent"), g.parent)
+        assert_same("gid_rank", ctx.debug_fetch("gid_rank"), g.gid)
+        assert_same("hkey", ctx.debug_fetch("hkey"), g.h.astype(np.uint32))
+    assert res.n_groups == g.n_groups
+    assert_same("out_gid", res.gid, g.out_gid)
+    assert_same("order", res.order, g.order)
+    assert_same("repval", res.repval, g.repval)
+    assert_same("identity(bits)", res.identity.view(np.uint32), g.identity.view(np.uint32))
+    return res, g
+
+
+def test_sort_pairs_matches_stable_sort(ctx):
+    import torch
+    dev = torch.device("cuda:0")
+    gen_ = torch.Generator(device="cpu").manual_seed(5)
+    for n, bits in [(1, 1), (33, 5), (4096, 8), (4097, 9), (100_003, 17), (1_000_000, 24), (300_000, 32), (70_000, 3)]:
+        keys = torch.randint(0, 2 ** bits, (n,), generator=gen_, dtype=torch.int64).to(torch.int32).to(dev) if bits < 32 else \
+            torch.randint(-2 ** 31, 2 ** 31, (n,), generator=gen_, dtype=torch.int64).to(torch.int32).to(dev)
+        ko, vo, kt, vt = (torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4))
+        work = torch.empty(ctx.sort_pairs_work_bytes(n), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctx.sort_pairs_device(keys.data_ptr(), None, ko.data_ptr(), vo.data_ptr(), kt.data_ptr(), vt.data_ptr(), n, bits,
+                              work.data_ptr())
+        ku = keys.cpu().numpy().view(np.uint32)
+        perm = np.argsort(ku, kind="stable")
+        assert_same(f"sorted keys n={n} bits={bits}", ko.cpu().numpy().view(np.uint32), ku[perm])
+        assert_same(f"sorted values n={n} bits={bits}", vo.cpu().numpy().view(np.uint32), perm.astype(np.uint32))
+
+
+def test_c1_every_stage(ctx):
+    w = gen.WORKLOADS["c1"]
+    rec = gen.generate(w)
+    check_against_oracle(ctx, rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
+
+
+def test_fuzz_golden_bytes(ctx, fuzz_cases, tmp_path):
+    """Tiny adversarial inputs: the CUDA result, written with the reference's line format, must reproduce the
+    bytes the reference itself produced (tests/golden/fuzz.json.gz)."""
+    for c in fuzz_cases:
+        inp = tmp_path / "in.csv"
+        inp.write_text(c["csv"], newline="")
+        rec, lx1, ly1, hdr = O.load_csv(str(inp))
+        res, g = check_against_oracle(ctx, rec, lx1, ly1, c["len_ratio"], c["pos_ratio"])
+        g.order, g.out_gid, g.repval, g.identity = res.order, res.gid, res.repval, res.identity
+        outp = tmp_path / "out.csv"
+        O.write_output(str(outp), hdr, rec, g)
+        assert outp.read_bytes() == c["ref_out"].encode("latin1"), f"fuzz seed {c['seed']}"
+
+
+@pytest.mark.parametrize("name", ["c1_loose", "c3_small", "dense", "c2_small"])
+def test_medium_golden_md5(ctx, medium_cases, tmp_path, name):
+    c = medium_cases[name]
+    w = gen.Workload(**c["workload"])
+    rec = gen.generate(w)
+    res, g = check_against_oracle(ctx, rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
+    g.order, g.out_gid, g.repval, g.identity = res.order, res.gid, res.repval, res.identity
+    outp = tmp_path / "out.csv"
+    O.write_output(str(outp), make_header(w.lx, w.ly, w.n).encode(), rec, g)
+    assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"]
+
+
+def test_edge_inputs(ctx):
+    # empty database
+    st = ctx.load(np.zeros(0, FRAG_DTYPE), 1001, 1001)
+    assert st.n_kept == 0
+    res = ctx.group(0.05, 0.05)
+    assert res.n_groups == 0 and res.n_kept == 0
+    # everything in the dropped last bucket (vsize-1 == xStart/10)
+    rec = np.zeros(5, FRAG_DTYPE)
+    rec["xStart"] = 1000
+    rec["length"] = 1
+    rec["strand"] = b"f"
+    st = ctx.load(rec, 1001, 1001)
+    assert st.n_kept == 0
+    assert ctx.group(0.5, 0.5).n_kept == 0
+    # one fragment; duplicates (exact ties: newest entry wins)
+    rec = np.zeros(7, FRAG_DTYPE)
+    rec["xStart"] = [10, 10, 10, 500, 10, 10, 10]
+    rec["yStart"] = [20, 20, 700, 20, 20, 20, 20]
+    rec["length"] = 30
+    rec["ident"] = 7
+    rec["strand"] = [b"f", b"f", b"f", b"f", b"r", b"x", b"f"]
+    check_against_oracle(ctx, rec[:1], 1001, 1001, 0.05, 0.05)
+    check_against_oracle(ctx, rec, 1001, 1001, 0.05, 0.05)
+    # no sort: members stay in processing order
+    res = ctx.group(0.05, 0.05, sort=False)
+    g = O.group(rec, 1001, 1001, 0.05, 0.05)
+    assert_same("gid multiset", np.sort(res.gid), np.sort(g.out_gid))
+
+
+def test_error_behaviour(ctx):
+    rec = np.zeros(3, FRAG_DTYPE)
+    rec["xStart"] = [5, 20000, 7]
+    rec["length"] = 10
+    with pytest.raises(capi.RkError) as e:
+        ctx.load(rec, 1001, 1001)           # xStart/10 >= vsize: the reference writes out of bounds
+    assert e.value.code == -3
+    with pytest.raises(capi.RkError) as e:
+        ctx.group(0.05, 0.05)               # nothing loaded after a failed load
+    assert e.value.code == -4
+    rec["xStart"] = [5, 6, 7]
+    ctx.load(rec, 1001, 1001)
+    for bad in [(0.0, 0.1), (0.1, -1.0)]:
+        with pytest.raises(capi.RkError) as e:
+            ctx.group(*bad)                 # init_args rejects non-positive ratios (commonFunctions.cpp:26-27)
+        assert e.value.code == -2
+    rec["length"] = [10, 5000, 10]          # center beyond the occupation list
+    with pytest.raises(capi.RkError) as e:
+        ctx.load(rec, 1001, 1001)
+    assert e.value.code == -3
+
+
+def test_device_pointer_input(ctx):
+    import torch
+    w = gen.scaled(gen.WORKLOADS["c2"], 200_000)
+    rec = gen.generate(w)
+    t = torch.from_numpy(rec.view(np.uint8).copy()).cuda()
+    torch.cuda.synchronize()
+    ctx.load(t.data_ptr(), w.lx + 1, w.ly + 1, n=w.n)
+    res = ctx.group(w.len_ratio, w.pos_ratio)
+    g = O.group(rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
+    assert_same("order", res.order, g.order)
+    assert_same("gid", res.gid, g.out_gid)
+
+
+def test_diagonal_func_table(ctx):
+    w = gen.scaled(gen.WORKLOADS["c1"], 20_000)
+    rec = gen.generate(w)
+    st = ctx.load(rec, w.lx + 1, w.ly + 1)
+    g = O.group(rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio, want_diag=True)
+    assert_same("diag_func", ctx.diagonal_func(st.vsize), g.diag_func)
+
+
+def test_ratio_sweep_reuses_loaded_database(ctx):
+    """One loaded database, several (len_ratio, pos_ratio) pairs (src/repkiller.cpp:60-72)."""
+    w = gen.scaled(gen.WORKLOADS["c1"], 50_000)
+    rec = gen.generate(w)
+    ctx.load(rec, w.lx + 1, w.ly + 1)
+    for lr, pr in [(0.05, 0.05), (0.5, 0.5), (1.0, 0.1), (2.5, 3.0)]:
+        res = ctx.group(lr, pr)
+        g = O.group(rec, w.lx + 1, w.ly + 1, lr, pr)
+        assert res.n_groups == g.n_groups
+        assert_same(f"order {lr},{pr}", res.order, g.order)
+        assert_same(f"gid {lr},{pr}", res.gid, g.out_gid)
