@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — fragments grouped per second on B200 (BASELINE.json metric), the reference's CPU path beside it.
+
+A "step" is one pass of the whole hot path over one synthetic comparison of the named workload shape:
+rk_load_aos (K1 decode, K2 processing-order and occupation-bucket sorts) + rk_group (K3 X/Y passes, K4 forest,
+K5 diag/sort/labels) for len_ratio = pos_ratio = 0.05.
+  value : records already resident in HBM, result left in HBM; CUDA events on the launching stream.
+  e2e   : the same step through the C ABI with HOST buffers: pinned records -> H2D -> kernels -> D2H of
+          order/gid/repval/identity into pinned host arrays.
+N > 1: one process per GPU (torchrun), each rank groups its own independent sequence-pair comparison of the
+same shape (weak scaling, no data-path collective; SURVEY.md §8c: one reference run per (seqX, seqY) pair).
+`--impl reference` times the reference's own CPU code (oracle/_ref, built from /root/reference) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from dataclasses import replace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fragments grouped/sec (device-timed)"
+UNIT = "fragments/s"
+CPU_SAMPLE_N = 1_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--n", type=int, default=0, help="override the fragment count (same shape, scaled); testing only")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", type=int, default=1, help="CUDA-event pairs around every kernel launch in the timed region")
+    return ap.parse_args()
+
+
+def workload(args, rank=0):
+    from repkiller_b200 import gen
+    w = gen.WORKLOADS[args.workload]
+    if args.n:
+        w = gen.scaled(w, args.n)
+    if rank:
+        w = replace(w, seed=w.seed + 1000 * rank)  # another sequence pair of the same shape
+    return w
+
+
+def workload_text(w):
+    return (f"{w.name}: {w.n:,} synthetic fragments, {w.lx / 1e6:g} Mbp x {w.ly / 1e6:g} Mbp, {int(w.p_rep * 100)}% repeat-family "
+            f"fragments in {w.families} families, len_ratio={w.len_ratio} pos_ratio={w.pos_ratio}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(w_sample, steps, warmup):
+    """Times generate_fragment_groups + generate_diagonal_func + sort_groups of the compiled reference
+    (oracle/_ref/repkiller_ref) — or of the oracle port when the reference binary is absent — on a bounded
+    sample.  Returns (fragments/s, kind, per-step ms list)."""
+    from repkiller_b200 import gen
+    from oracle import oracle as O
+    rec = gen.generate(w_sample)
+    times = []
+    if O.have_ref():
+        kind = "reference"
+        tmp = tempfile.mkdtemp(prefix="rkbench")
+        inp = os.path.join(tmp, "in.csv")
+        O.write_input_csv(inp, rec, w_sample.lx, w_sample.ly)
+        for i in range(warmup + steps):
+            info = O.run_ref(inp, os.path.join(tmp, "out.csv"), w_sample.len_ratio, w_sample.pos_ratio, nosave=True)
+            if i >= warmup:
+                times.append(info["group_ms"] + info["diag_ms"] + info["sort_ms"])
+        os.remove(inp)
+    else:
+        kind = "port"
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.group(rec, w_sample.lx + 1, w_sample.ly + 1, w_sample.len_ratio, w_sample.pos_ratio)
+            if i >= warmup:
+                times.append((time.perf_counter() - t0) * 1e3)
+    ms = sum(times) / len(times)
+    return w_sample.n / (ms / 1e3), kind, times
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from repkiller_b200 import gen
+    w = workload(args)
+    ws = gen.scaled(w, min(w.n, CPU_SAMPLE_N))
+    t0 = time.perf_counter()
+    value, kind, times = cpu_reference_run(ws, args.steps, args.warmup)
+    ms = sum(times) / len(times)
+    sample = (f"{ws.n:,}-fragment sample of the {w.name} shape ({ws.lx / 1e6:g} Mbp x {ws.ly / 1e6:g} Mbp, same density); "
+              f"generate_fragment_groups + generate_diagonal_func + sort_groups, CSV parse/format excluded")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64+u64", "data": "synthetic", "config": {"workload": workload_text(w), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        out, _ = self.p.communicate(timeout=10)
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n, m, bits_rank, bits_x, bits_y, bits_g):
+    """Algorithmic HBM bytes per step and kernel: what the kernel must read and write once."""
+    passes = lambda b: (max(b, 1) + 7) // 8
+    sorted_elems = n * passes(bits_rank) + m * (passes(bits_x) + passes(bits_y) + passes(bits_g))
+    return {
+        "k_decode": n * (109 + 21),
+        "k_radix_hist": 4 * sorted_elems,
+        "k_radix_scatter": 16 * sorted_elems,
+        "k_keys": m * (4 + 13 + 24),
+        "k_match_small": m * (20 + 24),
+        "k_chase": m * 12,
+        "k_scan": m * 12,
+        "k_hkey": m * 16,
+        "k_pack": m * 16,
+        "k_groupsort_small": m * 4,
+        "k_finalize": m * (8 + 4 + 4 + 4 + 13),
+    }
+
+
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from repkiller_b200 import capi, gen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = workload(args, rank)
+    rec = gen.generate(w)
+    n = w.n
+    host = torch.from_numpy(rec.view(np.uint8).reshape(-1)).pin_memory()
+    dev = host.cuda()
+    lx1, ly1 = w.lx + 1, w.ly + 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    stream = torch.cuda.Stream()
+    ctx = capi.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        st = ctx.load(dev.data_ptr(), lx1, ly1, n=n)
+        return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=False)
+
+    def step_e2e():
+        st = ctx.load(host.data_ptr(), lx1, ly1, n=n)
+        return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=True)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            last = None
+            for _ in range(k):
+                last = fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.profile_enable(bool(args.profile_kernels))
+    ctx.profile_read(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, (st, res) = timed(step_resident, args.steps)
+    prof = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e, (st_e, res_e) = timed(step_e2e, args.steps)
+
+    n_total = n * world
+    value = n_total * args.steps / (ms_total / 1e3)
+    e2e_value = n_total * args.steps / (ms_e2e / 1e3)
+    m = res.n_kept
+    ceil_log2 = lambda x: max(1, (max(int(x), 1) - 1).bit_length())
+    bits = (ceil_log2(st.vsize), ceil_log2(2 * (lx1 // 100 + 2)), ceil_log2(2 * (ly1 // 100 + 2)), ceil_log2(m))
+    alg = algorithmic_bytes(n, m, *bits)
+
+    line = None
+    if rank == 0:
+        kernels = {}
+        for name, (launches, ms) in prof.items():
+            per_step_ms = ms / args.steps
+            b = alg.get(name)
+            kernels[name] = {"launches_per_step": launches / args.steps, "ms_per_step": round(per_step_ms, 4),
+                             "alg_gbs": round(b / per_step_ms / 1e6, 1) if b and per_step_ms > 0 else None}
+        top = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+        roofline = None
+        if top:
+            launches, ms = prof[top]
+            b = alg.get(top, 0)
+            achieved = b * args.steps / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
+                        "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+                        "alg_bytes_per_launch": round(b * args.steps / max(launches, 1)),
+                        "avg_launch_ms": round(ms / max(launches, 1), 5), "share_of_kernel_time": round(ms / max(sum(v[1] for v in prof.values()), 1e-9), 3)}
+        total_alg = sum(alg.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32+f64", "data": "synthetic",
+            "config": {"workload": workload_text(w), "per_gpu_fragments": n, "kept": int(m), "groups": int(res.n_groups),
+                       "l2": "inputs larger than L2 (1.09 GB of records per step vs 126 MB)" if n * 109 > 200e6 else "inputs smaller than L2 (reduced --n run)",
+                       "multi_gpu": "independent sequence pairs per rank, no data-path collective" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(m * 13 + 40),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int((st.n_launches + res.n_launches) * args.steps),
+            "clocks": clocks,
+            "roofline": roofline,
+            "pipeline_alg_bytes_per_fragment": round(total_alg / n, 1),
+            "pipeline_hbm_frac": round(total_alg * args.steps / (ms_total / 1e3) / 1e9 / peak_gbs, 4),
+            "stage_ms": {k: round(v, 4) for k, v in {**st.ms_stage, **{k2: v2 for k2, v2 in res.ms_stage.items() if v2}}.items() if v},
+            "kernels": kernels,
+        }
+    if world > 1:
+        dist.barrier()
+    ctx.close()
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            ws = gen.scaled(workload(args), min(n, CPU_SAMPLE_N))
+            v, kind, times = cpu_reference_run(ws, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"{ws.n:,}-fragment sample of the {w.name} shape (same density): generate_fragment_groups + "
+                                              f"generate_diagonal_func + sort_groups of the compiled reference, CSV parse/format excluded; "
+                                              f"{sum(times) / len(times):.0f} ms per run"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()
