@@ -108,6 +108,14 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
  * (len_ratio, pos_ratio) pair.  Both ratios must be > 0 (src/commonFunctions.cpp:26-27).  Synchronous. */
 int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk_result *out);
 
+/* Replaces sort_groups (src/commonFunctions.cpp:148-159) when it is called as a separate step: after an
+ * rk_group with RK_F_NO_SORT, orders the members of every group on the device and returns the result again. */
+int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out);
+
+/* Pinned host memory for record arrays handed to rk_load_aos (full-speed H2D); NULL on failure. */
+void *rk_host_alloc(size_t bytes);
+void rk_host_free(void *p);
+
 /* Replaces generate_diagonal_func (src/commonFunctions.cpp:161-177): fills diag_func[0 .. vsize-2] (host
  * memory, vsize = FragmentsDatabase::getA()) including the carry-forward over empty buckets. */
 int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func);

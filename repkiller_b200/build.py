@@ -54,17 +54,20 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_host(force: bool = False) -> str | None:
-    """The drop-in repkiller CLI (host C++ over the C ABI)."""
-    srcs = sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp")))
-    if not srcs:
+    """Host C++ over the C ABI: the drop-in `repkiller` CLI and the rk_hostcheck test helper."""
+    common = sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp")))
+    mains = sorted(glob.glob(os.path.join(CSRC, "host", "main", "*.cpp")))
+    if not mains:
         return None
-    deps = srcs + glob.glob(os.path.join(CSRC, "host", "*.h")) + [LIB]
-    if not force and _newer(CLI, deps):
-        return CLI
+    deps = common + mains + glob.glob(os.path.join(CSRC, "host", "*.h")) + [LIB]
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(HERE, "..", "include"), *srcs, "-o", CLI,
-           "-L", HERE, "-lrk_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
-    subprocess.check_call(cmd)
+    for m in mains:
+        exe = os.path.join(os.path.dirname(CLI), os.path.basename(m)[:-4])
+        if not force and _newer(exe, deps):
+            continue
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(HERE, "..", "include"), *common, m, "-o", exe,
+               "-L", HERE, "-lrk_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+        subprocess.check_call(cmd)
     return CLI
 
 

@@ -21,7 +21,7 @@ STAGES = ["h2d", "decode", "ranksort", "keys", "xsort", "ysort", "xmatch", "ymat
 NSTAGES = len(STAGES)
 
 # every symbol include/rk_b200.h declares
-SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_group",
+SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_group", "rk_sort_groups", "rk_host_alloc", "rk_host_free",
            "rk_diagonal_func", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version"]
 
 

@@ -234,6 +234,80 @@ struct ProfGuard {  // routes the launchers' KScope events to this context for t
 };
 }  // namespace
 
+namespace {
+// K5b tail + K5c on the state the last rk_group left on the device
+u64 run_order(rk_ctx *ctx, unsigned flags) {
+  OrderArgs oa{};
+  oa.sgid = ctx->sgid, oa.srank = ctx->srank, oa.h = ctx->h, oa.fidx_r = ctx->fidx_r, oa.identity_f = ctx->identity_f;
+  oa.packed = ctx->packed, oa.m = ctx->m, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1;
+  oa.worklist = ctx->worklist, oa.work_count = ctx->d_cnt->work_g, oa.work_cap = ctx->work_cap;
+  oa.out_order = ctx->out_order, oa.out_gid = ctx->out_gid, oa.out_repval = ctx->out_repval, oa.out_identity = ctx->out_identity;
+  oa.err = &ctx->d_cnt->err;
+  return (u64)launch_order(oa, ctx->stream);
+}
+
+// optional D2H of the four output arrays, final synchronisation, error word, result struct (events 0..5 recorded)
+int finish_group(rk_ctx *ctx, unsigned flags, rk_result *out, u64 launches) {
+  const u32 m = ctx->m;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t *ev = ctx->ev;
+  if ((flags & RK_F_HOST_RESULT) && m) {
+    const u64 need = 3 * align_up((u64)m * 4, 256) + align_up((u64)m, 256);
+    if (need > ctx->h_res_cap) {
+      CK(cudaStreamSynchronize(st));
+      if (ctx->h_res) cudaFreeHost(ctx->h_res);
+      ctx->h_res = nullptr;
+      ctx->h_res_cap = 0;
+      CK(cudaHostAlloc(&ctx->h_res, need, cudaHostAllocDefault));
+      ctx->h_res_cap = need;
+    }
+  }
+  CK(cudaEventRecord(ev[6], st));
+  u8 *hb = (u8 *)ctx->h_res;
+  u32 *h_order = nullptr, *h_gid = nullptr;
+  float *h_ident = nullptr;
+  u8 *h_rep = nullptr;
+  if ((flags & RK_F_HOST_RESULT) && m) {
+    h_order = (u32 *)hb;
+    h_gid = (u32 *)(hb + align_up((u64)m * 4, 256));
+    h_ident = (float *)(hb + 2 * align_up((u64)m * 4, 256));
+    h_rep = hb + 3 * align_up((u64)m * 4, 256);
+    CK(cudaMemcpyAsync(h_order, ctx->out_order, (u64)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_gid, ctx->out_gid, (u64)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_ident, ctx->out_identity, (u64)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_rep, ctx->out_repval, (u64)m, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(ev[7], st));
+  CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
+  ctx->have_group = true;
+
+  out->n_kept = m;
+  out->n_groups = ctx->h_cnt->n_groups;
+  out->order = h_order;
+  out->gid = h_gid;
+  out->repval = h_rep;
+  out->identity = h_ident;
+  out->d_order = ctx->out_order;
+  out->d_gid = ctx->out_gid;
+  out->d_repval = ctx->out_repval;
+  out->d_identity = ctx->out_identity;
+  out->n_launches = launches;
+  if (flags & RK_F_TIMING) {
+    out->ms_stage[RK_ST_XMATCH] = ev_ms(ev[0], ev[1]);
+    out->ms_stage[RK_ST_YMATCH] = ev_ms(ev[1], ev[2]);
+    out->ms_stage[RK_ST_FOREST] = ev_ms(ev[2], ev[3]);
+    out->ms_stage[RK_ST_HKEY] = ev_ms(ev[3], ev[4]);
+    out->ms_stage[RK_ST_GSORT] = ev_ms(ev[4], ev[5]);
+    out->ms_stage[RK_ST_D2H] = ev_ms(ev[6], ev[7]);
+    out->ms_device = ev_ms(ev[0], ev[5]);
+  }
+  return RK_OK;
+}
+}  // namespace
+
 extern "C" {
 
 const char *rk_version(void) { return "repkiller-b200 0.1 (sm_100a)"; }
@@ -412,17 +486,6 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
   cudaEvent_t *ev = ctx->ev;
   u64 launches = 0;
 
-  if ((flags & RK_F_HOST_RESULT) && m) {
-    const u64 need = (u64)m * 13 + 1024;
-    if (need > ctx->h_res_cap) {
-      if (ctx->h_res) cudaFreeHost(ctx->h_res);
-      ctx->h_res = nullptr;
-      ctx->h_res_cap = 0;
-      CK(cudaHostAlloc(&ctx->h_res, need, cudaHostAllocDefault));
-      ctx->h_res_cap = need;
-    }
-  }
-
   CK(cudaEventRecord(ev[0], st));
   MatchArgs mx{};
   mx.skey = ctx->skx, mx.srank = ctx->rx, mx.c_r = ctx->cx_r, mx.len_r = ctx->len_r, mx.parent = ctx->parent;
@@ -443,58 +506,22 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
   // gids are < number of groups <= m; sorting by ceil_log2(m) bits avoids a host round trip for the count
   launches += launch_sort_pairs(ctx->gid_rank, nullptr, ctx->sgid, ctx->srank, ctx->tmp_k, ctx->tmp_v, m, ceil_log2(m),
                                 ctx->sort_work, st);
-  OrderArgs oa{};
-  oa.sgid = ctx->sgid, oa.srank = ctx->srank, oa.h = ctx->h, oa.fidx_r = ctx->fidx_r, oa.identity_f = ctx->identity_f;
-  oa.packed = ctx->packed, oa.m = m, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1;
-  oa.worklist = ctx->worklist, oa.work_count = ctx->d_cnt->work_g, oa.work_cap = ctx->work_cap;
-  oa.out_order = ctx->out_order, oa.out_gid = ctx->out_gid, oa.out_repval = ctx->out_repval, oa.out_identity = ctx->out_identity;
-  oa.err = &ctx->d_cnt->err;
-  // K5b = gid sort + per-group order; K5c = finalize (timed together with K5b's tail inside launch_order)
-  launches += launch_order(oa, st);
+  launches += run_order(ctx, flags);
   CK(cudaEventRecord(ev[5], st));
-  CK(cudaEventRecord(ev[6], st));
-  u8 *hb = (u8 *)ctx->h_res;
-  u32 *h_order = nullptr, *h_gid = nullptr;
-  float *h_ident = nullptr;
-  u8 *h_rep = nullptr;
-  if ((flags & RK_F_HOST_RESULT) && m) {
-    h_order = (u32 *)hb;
-    h_gid = (u32 *)(hb + align_up((u64)m * 4, 256));
-    h_ident = (float *)(hb + 2 * align_up((u64)m * 4, 256));
-    h_rep = hb + 3 * align_up((u64)m * 4, 256);
-    CK(cudaMemcpyAsync(h_order, ctx->out_order, (u64)m * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_gid, ctx->out_gid, (u64)m * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_ident, ctx->out_identity, (u64)m * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_rep, ctx->out_repval, (u64)m, cudaMemcpyDeviceToHost, st));
-  }
-  CK(cudaEventRecord(ev[7], st));
-  CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  CK(cudaGetLastError());
-  if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
-  ctx->have_group = true;
+  return finish_group(ctx, flags, out, launches);
+}
 
-  out->n_kept = m;
-  out->n_groups = ctx->h_cnt->n_groups;
-  out->order = h_order;
-  out->gid = h_gid;
-  out->repval = h_rep;
-  out->identity = h_ident;
-  out->d_order = ctx->out_order;
-  out->d_gid = ctx->out_gid;
-  out->d_repval = ctx->out_repval;
-  out->d_identity = ctx->out_identity;
-  out->n_launches = launches;
-  if (flags & RK_F_TIMING) {
-    out->ms_stage[RK_ST_XMATCH] = ev_ms(ev[0], ev[1]);
-    out->ms_stage[RK_ST_YMATCH] = ev_ms(ev[1], ev[2]);
-    out->ms_stage[RK_ST_FOREST] = ev_ms(ev[2], ev[3]);
-    out->ms_stage[RK_ST_HKEY] = ev_ms(ev[3], ev[4]);
-    out->ms_stage[RK_ST_GSORT] = ev_ms(ev[4], ev[5]);
-    out->ms_stage[RK_ST_D2H] = ev_ms(ev[6], ev[7]);
-    out->ms_device = ev_ms(ev[0], ev[5]);
-  }
-  return RK_OK;
+int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out) {
+  if (!ctx || !out) return RK_ERR_ARG;
+  if (!ctx->loaded || !ctx->have_group) return fail(ctx, RK_ERR_STATE, "rk_sort_groups before rk_group");
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  memset(out, 0, sizeof *out);
+  cudaEvent_t *ev = ctx->ev;
+  for (int i = 0; i < 5; ++i) CK(cudaEventRecord(ev[i], ctx->stream));
+  const u64 launches = run_order(ctx, flags & ~RK_F_NO_SORT);
+  CK(cudaEventRecord(ev[5], ctx->stream));
+  return finish_group(ctx, flags, out, launches);
 }
 
 int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func) {
@@ -558,6 +585,18 @@ int rk_profile_read(rk_ctx *ctx, rk_kernel_time *out, int cap, int reset) {
     for (int i = 0; i < KID_COUNT; ++i) ctx->prof.ms[i] = 0, ctx->prof.launches[i] = 0;
   }
   return k;
+}
+
+void *rk_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void rk_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 uint64_t rk_sort_pairs_work_bytes(uint64_t n) { return sort_work_bytes(n ? n : 1); }

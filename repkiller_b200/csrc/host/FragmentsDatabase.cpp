@@ -1,0 +1,128 @@
+#include "FragmentsDatabase.h"
+
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+// One CSV row -> record.  Semantics of the reference's readFragment (FragmentsDatabase.cpp:17-50), which
+// tokenises with 14 x getline(stream, buf, ','):
+//  * a token ends at ',' or at the end of the row; an EMPTY token rejects the row (:25);
+//  * once the row is exhausted the extraction fails and buf keeps the previous token, so a short row is
+//    padded with its last field ("Frag,5" loads with every numeric field 5 and strand '5');
+//  * a trailing ',' produces one empty token (row rejected);
+//  * field 0 must be "Frag" (:29); numeric fields through atoll; similarity AND ident from stof(field 10)
+//    (:39-40; field 9 is ignored); a row whose similarity does not parse is rejected (:46-48).
+bool readFragment(FragFile *frag, const char *line, size_t len) {
+  const char *tok[14];
+  size_t tlen[14];
+  size_t pos = 0;
+  bool exhausted = false;
+  const char *cur = nullptr;
+  size_t curlen = 0;
+  for (int i = 0; i < 14; ++i) {
+    if (!exhausted) {
+      const size_t s = pos;
+      while (pos < len && line[pos] != ',') ++pos;
+      cur = line + s;
+      curlen = pos - s;
+      if (pos < len) ++pos;
+      else exhausted = true;
+    }
+    if (curlen == 0) return false;
+    tok[i] = cur;
+    tlen[i] = curlen;
+  }
+  if (!(tlen[0] == 4 && memcmp(tok[0], "Frag", 4) == 0)) return false;
+  char buf[72];
+  auto cstr = [&](int i) -> const char * {
+    const size_t l = tlen[i] < 71 ? tlen[i] : 71;
+    memcpy(buf, tok[i], l);
+    buf[l] = 0;
+    return buf;
+  };
+  frag->xStart = (uint64_t)atoll(cstr(1));
+  frag->yStart = (uint64_t)atoll(cstr(2));
+  frag->diag = (int64_t)frag->xStart - (int64_t)frag->yStart;
+  frag->xEnd = (uint64_t)atoll(cstr(3));
+  frag->yEnd = (uint64_t)atoll(cstr(4));
+  frag->strand = tok[5][0];
+  frag->block = atoll(cstr(6));
+  frag->length = (uint64_t)atoll(cstr(7));
+  frag->score = (uint64_t)atoll(cstr(8));
+  const char *s = cstr(10);
+  char *endp = nullptr;
+  errno = 0;
+  const float sim = strtof(s, &endp);  // std::stof: invalid_argument when nothing converts, out_of_range on ERANGE
+  if (endp == s || errno == ERANGE) return false;
+  frag->ident = (uint64_t)sim;
+  frag->similarity = sim;
+  frag->seqX = 0;
+  frag->seqY = 1;
+  memset(frag->evalue, 0, sizeof frag->evalue);
+  return true;
+}
+
+namespace {
+long long value_after_colon(const std::string &line) {  // atoll(line.substr(line.find(':') + 1)), :62,65,72
+  const size_t p = line.find(':');
+  return atoll(line.c_str() + (p == std::string::npos ? 0 : p + 1));
+}
+}  // namespace
+
+FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device) {
+  // slurp the rest of the stream; lines are split on '\n' like std::getline
+  std::string data((std::istreambuf_iterator<char>(frags_file)), std::istreambuf_iterator<char>());
+  size_t pos = 0;
+  auto next_line = [&](std::string &out) {
+    const size_t s = pos;
+    while (pos < data.size() && data[pos] != '\n') ++pos;
+    out.assign(data, s, pos - s);
+    if (pos < data.size()) ++pos;
+  };
+  std::string line;
+  uint64_t total_frags = 0;
+  for (int ln = 1; ln <= 16; ++ln) {  // reference: :57-77
+    next_line(line);
+    header.append(line).append("\n");
+    if (ln == 7) seq_manager.sequences.emplace_back(0, (uint64_t)(value_after_colon(line) + 1));
+    if (ln == 8) seq_manager.sequences.emplace_back(1, (uint64_t)(value_after_colon(line) + 1));
+    if (ln == 13) total_frags = (uint64_t)value_after_colon(line);
+  }
+  seq_manager.read_header(header);
+  vsize = 1 + seq_manager.get_sequence_by_label(0).len / 10;  // :84
+
+  ctx_ = rk_create(device);
+  if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
+
+  // upper bound on rows: number of remaining lines
+  uint64_t lines = 1;
+  for (size_t i = pos; i < data.size(); ++i) lines += data[i] == '\n';
+  cap_ = lines;
+  records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16);
+  if (!records_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
+
+  bool eof = data.empty();
+  while (!eof) {  // :92-100; the final getline on an exhausted stream yields one empty line
+    const size_t s = pos;
+    while (pos < data.size() && data[pos] != '\n') ++pos;
+    const size_t l = pos - s;
+    if (pos < data.size()) ++pos;
+    else eof = true;
+    FragFile tmp;
+    memset(&tmp, 0, sizeof tmp);
+    if (!readFragment(&tmp, data.data() + s, l)) continue;
+    records_[count_++] = tmp;
+    if (count_ > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
+  }
+
+  const int rc = rk_load_aos(ctx_, records_, count_, seq_manager.get_sequence_by_label(0).len,
+                             seq_manager.get_sequence_by_label(1).len, RK_F_TIMING, &load_stats_);
+  if (rc != RK_OK) throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(ctx_));
+}
+
+FragmentsDatabase::~FragmentsDatabase() {
+  if (ctx_) rk_destroy(ctx_);
+  if (records_) rk_host_free(records_);
+}

@@ -1,0 +1,37 @@
+// Drop-in for the reference's FragmentsDatabase (/root/reference/src/FragmentsDatabase.h:15-35): same
+// constructor and accessors, but the per-bucket vector<FragFile>[] is replaced by the records in file order
+// (pinned host memory) plus the device-side processing order built by rk_load_aos.
+#pragma once
+
+#include <cstdint>
+#include <fstream>
+#include <string>
+
+#include "rk_b200.h"
+#include "structs.h"
+
+bool readFragment(FragFile *frag, const char *line, size_t len);  // reference: FragmentsDatabase.cpp:17-50
+
+class FragmentsDatabase {
+  FragFile *records_ = nullptr;  // file order, pinned
+  uint64_t count_ = 0, cap_ = 0;
+  size_t vsize = 0;
+  rk_ctx *ctx_ = nullptr;
+  std::string header;
+  rk_load_stats load_stats_{};
+
+ public:
+  // Parses the GECKO CSV exactly like the reference (16 header lines, Frag rows, readFragment's accept/pad
+  // rules), fills seq_manager, then hands the records to the GPU.  Throws std::runtime_error like the
+  // reference on "Unexpected number of fragments"; also on device errors (message from rk_last_error).
+  FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device = 0);
+  ~FragmentsDatabase();
+  FragmentsDatabase(const FragmentsDatabase &) = delete;
+  FragmentsDatabase &operator=(const FragmentsDatabase &) = delete;
+
+  size_t getA() const { return vsize; }                 // reference: FragmentsDatabase.h:23-25
+  uint64_t getTotalFrags() const { return count_; }      // reference: FragmentsDatabase.h:32-34
+  const FragFile *records() const { return records_; }   // replaces begin()/end(): file order, not buckets
+  rk_ctx *ctx() const { return ctx_; }
+  const rk_load_stats &load_stats() const { return load_stats_; }
+};

@@ -1,0 +1,181 @@
+#include "commonFunctions.h"
+
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+
+void print_help() {
+  std::cout << "Repkiller v0.9.b\n";
+  std::cout << "Usage: ./repkiller <input_file_path> <output_file_path> <length_ratio> <position_ratio>\n";
+  std::cout << std::flush;
+}
+
+void init_args(const std::vector<std::string> &args, std::ifstream &multifrags, std::string &out_file_base_path,
+               std::string &path_frags, std::queue<std::pair<double, double>> &params) {
+  out_file_base_path.clear();
+  path_frags.clear();
+  if (args.size() < 4) throw std::invalid_argument("Invalid number of arguments.");
+  path_frags = args.at(1);
+  multifrags.open(path_frags, std::ifstream::in | std::ifstream::binary);
+  if (!multifrags) throw std::runtime_error("Could not open input file " + path_frags + ".");
+  out_file_base_path = args.at(2);
+  if (out_file_base_path.empty()) throw std::runtime_error("Output file name is missing");
+  for (size_t i = 3; i < args.size(); i += 2) {
+    const double len_ratio = std::stod(args.at(i), nullptr);
+    const double pos_ratio = std::stod(args.at(i + 1), nullptr);  // odd count: at() throws out_of_range, as the reference
+    if (len_ratio <= 0) throw std::invalid_argument("Ratio between length and position must be greater than zero");
+    if (pos_ratio <= 0) throw std::invalid_argument("Position proximity must be greater than zero");
+    params.push(std::make_pair(len_ratio, pos_ratio));
+  }
+}
+
+namespace {
+
+// which database filled which list (sort_groups receives only the list)
+std::mutex g_reg_mtx;
+std::map<const FGList *, const FragmentsDatabase *> g_registry;
+
+void build_groups(const FragmentsDatabase &db, const rk_result &r, FGList &out) {
+  const FragFile *recs = db.records();
+  out.clear();
+  out.reserve(r.n_groups);
+  uint64_t j = 0;
+  while (j < r.n_kept) {
+    const uint32_t g = r.gid[j];
+    uint64_t e = j;
+    while (e < r.n_kept && r.gid[e] == g) ++e;
+    FragsGroup *fg = new FragsGroup();
+    fg->reserve(e - j);
+    for (uint64_t k = j; k < e; ++k) fg->push_back(recs + r.order[k]);
+    out.push_back(fg);
+    j = e;
+  }
+}
+
+void reorder_groups(const FragmentsDatabase &db, const rk_result &r, FGList &fgl) {
+  const FragFile *recs = db.records();
+  uint64_t j = 0;
+  for (FragsGroup *fg : fgl) {
+    for (size_t k = 0; k < fg->size(); ++k) (*fg)[k] = recs + r.order[j + k];
+    j += fg->size();
+  }
+}
+
+[[noreturn]] void device_error(const FragmentsDatabase &db) {
+  throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(db.ctx()));
+}
+
+}  // namespace
+
+size_t generate_fragment_groups(const FragmentsDatabase &frags_db, FGList &efrags_groups, const sequence_manager &,
+                                double lensim, double possim) {
+  rk_result r;
+  if (rk_group(frags_db.ctx(), lensim, possim, RK_F_HOST_RESULT | RK_F_NO_SORT, &r) != RK_OK) device_error(frags_db);
+  build_groups(frags_db, r, efrags_groups);
+  {
+    std::lock_guard<std::mutex> lk(g_reg_mtx);
+    g_registry[&efrags_groups] = &frags_db;
+  }
+  std::cout << std::flush;  // reference: commonFunctions.cpp:78
+  return efrags_groups.size();
+}
+
+void generate_diagonal_func(const FragmentsDatabase &fdb, size_t *diag_func) {
+  static_assert(sizeof(size_t) == sizeof(uint64_t), "64-bit host");
+  if (rk_diagonal_func(fdb.ctx(), reinterpret_cast<uint64_t *>(diag_func)) != RK_OK) device_error(fdb);
+}
+
+void sort_groups(FGList &fgl, const size_t *) {
+  const FragmentsDatabase *db = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_reg_mtx);
+    auto it = g_registry.find(&fgl);
+    if (it != g_registry.end()) db = it->second;
+  }
+  if (!db) throw std::runtime_error("sort_groups: this list was not produced by generate_fragment_groups");
+  rk_result r;
+  if (rk_sort_groups(db->ctx(), RK_F_HOST_RESULT, &r) != RK_OK) device_error(*db);
+  reorder_groups(*db, r, fgl);
+}
+
+FGList *group_and_sort(const FragmentsDatabase &frags_db, double len_ratio, double pos_ratio, rk_result *stats) {
+  rk_result r;
+  if (rk_group(frags_db.ctx(), len_ratio, pos_ratio, RK_F_HOST_RESULT | RK_F_TIMING, &r) != RK_OK) device_error(frags_db);
+  FGList *fgl = new FGList;
+  build_groups(frags_db, r, *fgl);
+  if (stats) *stats = r;
+  return fgl;
+}
+
+void free_groups(FGList *fgl) {
+  if (!fgl) return;
+  {
+    std::lock_guard<std::mutex> lk(g_reg_mtx);
+    g_registry.erase(fgl);
+  }
+  for (FragsGroup *g : *fgl) delete g;
+  delete fgl;
+}
+
+// ---- writer: byte-identical to commonFunctions.cpp:101-146 ---------------------------------------------
+namespace {
+inline char *put_u64(char *p, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+inline char *put_float(char *p, float f) {  // ostream << float, default format: %g with precision 6
+  return p + snprintf(p, 32, "%g", (double)f);
+}
+void store_frag(std::ostream &out, const FragFile *f, uint64_t gid, unsigned repval) {
+  char line[320];
+  char *p = line;
+  memcpy(p, "Frag,", 5), p += 5;
+  p = put_u64(p, f->xStart), *p++ = ',';
+  p = put_u64(p, f->yStart), *p++ = ',';
+  p = put_u64(p, f->xEnd), *p++ = ',';
+  p = put_u64(p, f->yEnd), *p++ = ',';
+  *p++ = f->strand, *p++ = ',';
+  p = put_u64(p, gid), *p++ = ',';
+  p = put_u64(p, f->length), *p++ = ',';
+  p = put_u64(p, f->score), *p++ = ',';
+  p = put_u64(p, f->ident), *p++ = ',';
+  p = put_float(p, f->similarity), *p++ = ',';
+  p = put_float(p, (float)f->ident * 100 / (float)f->length);  // reference: :103
+  memcpy(p, ",0,", 3), p += 3;
+  p = put_u64(p, repval), *p++ = '\n';
+  out.write(line, p - line);
+}
+}  // namespace
+
+void save_frags_from_group(std::ostream &out_file, FragsGroup &fg, uint64_t gid) {
+  if (fg.size() == 1) {
+    store_frag(out_file, fg.front(), gid, 0);
+  } else {
+    store_frag(out_file, fg.front(), gid, 1);
+    for (auto it = fg.begin() + 1; it != fg.end(); ++it) store_frag(out_file, *it, gid, 2);
+  }
+}
+
+void save_frag_pair(std::ostream &out_file, uint64_t, uint64_t, const sequence_manager &seq_mngr, const FGList &fgl) {
+  uint64_t gid = 0;
+  seq_mngr.write_header(out_file);
+  for (auto fg : fgl) save_frags_from_group(out_file, *fg, gid++);
+}
+
+void save_all_frag_pairs(const std::string &out_file_base_path, const sequence_manager &seq_manager, const FGList &fgl) {
+  const uint64_t n_seq = seq_manager.get_number_of_sequences();
+  std::ofstream out_file;
+  for (uint64_t i = 0; i < n_seq; i++)
+    for (uint64_t j = i + 1; j < n_seq; j++) {
+      out_file.open(out_file_base_path, std::ofstream::out);
+      if (!out_file) throw std::runtime_error("Could not open output directory " + out_file_base_path);
+      save_frag_pair(out_file, i, j, seq_manager, fgl);
+      out_file.close();
+    }
+}

@@ -1,0 +1,34 @@
+// Drop-in for the free functions of /root/reference/src/commonFunctions.h used on the grouping path.  Same
+// names, argument meaning and error behaviour; the work is done by librk_b200.so.
+#pragma once
+
+#include <queue>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "FragmentsDatabase.h"
+#include "structs.h"
+
+void print_help();  // reference: commonFunctions.cpp:3-7
+void init_args(const std::vector<std::string> &args, std::ifstream &multifrags, std::string &out_file_base_path,
+               std::string &path_frags, std::queue<std::pair<double, double>> &params);  // :9-30
+
+// reference: commonFunctions.cpp:41-80.  Fills efrags_groups (groups in creation order, members in processing
+// order, pointers into frags_db.records()) and returns the number of groups.  Runs K3+K4 on the device.
+size_t generate_fragment_groups(const FragmentsDatabase &frags_db, FGList &efrags_groups, const sequence_manager &seq_manager,
+                                double len_pos_ratio, double pos_ratio);
+// reference: commonFunctions.cpp:161-177; diag_func has frags_db.getA() entries, [0, getA()-2] are written.
+void generate_diagonal_func(const FragmentsDatabase &fdb, size_t *diag_func);
+// reference: commonFunctions.cpp:148-159.  fgl must be the list the last generate_fragment_groups filled for
+// that database: the member order is computed on the device (K5b) from the state that call left there.
+void sort_groups(FGList &fgl, const size_t *diag_func);
+// One call for the three above (what the CLI uses: no intermediate host lists).
+FGList *group_and_sort(const FragmentsDatabase &frags_db, double len_ratio, double pos_ratio, rk_result *stats = nullptr);
+
+// reference: commonFunctions.cpp:101-146 (the writer; byte-identical output)
+void save_frags_from_group(std::ostream &out_file, FragsGroup &fg, uint64_t gid);
+void save_frag_pair(std::ostream &out_file, uint64_t seq1_label, uint64_t seq2_label, const sequence_manager &seq_mngr,
+                    const FGList &fgl);
+void save_all_frag_pairs(const std::string &out_file_base_path, const sequence_manager &seq_manager, const FGList &fgl);
+void free_groups(FGList *fgl);

@@ -1,0 +1,69 @@
+// repkiller — same command line, stdout and output file as the reference CLI (/root/reference/src/repkiller.cpp),
+// with the grouping path on the GPU.
+//   repkiller <input_file_path> <output_file_path> <length_ratio> <position_ratio> [<length_ratio> <position_ratio>]...
+// Parameter pairs are processed in argv order on one device context while the writer thread saves the previous
+// result; every pair writes the same path (as in the reference, repkiller.cpp:95-96), so the last pair's file
+// remains ([survey choice]: the reference's 3-thread pool makes the survivor timing dependent).
+// RK_TIMING=1 prints per-stage device times on stderr; RK_DEVICE selects the GPU.
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <queue>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../FragmentsDatabase.h"
+#include "../SaverQueue.h"
+#include "../commonFunctions.h"
+#include "../structs.h"
+
+static void execWithParams(const FragmentsDatabase &frag_db, std::pair<double, double> param, const std::string &out_path,
+                           SaverQueue &sq, bool timing) {
+  rk_result st;
+  FGList *groups = group_and_sort(frag_db, param.first, param.second, &st);  // repkiller.cpp:83-91 in one device pass
+  if (timing)
+    std::cerr << "[rk] len_ratio=" << param.first << " pos_ratio=" << param.second << " groups=" << st.n_groups
+              << " device_ms=" << st.ms_device << " launches=" << st.n_launches << "\n";
+  sq.addRequest(out_path, groups);  // repkiller.cpp:95-96
+}
+
+int main(int argc, char *argv[]) {
+  std::string out_file_base_path, multifrags_path;
+  std::queue<std::pair<double, double>> params;
+  std::ifstream frags_file;
+  try {
+    std::vector<std::string> args(argv, argv + argc);
+    init_args(args, frags_file, out_file_base_path, multifrags_path, params);
+  } catch (const std::invalid_argument &e) {
+    std::cerr << e.what() << std::endl;
+    print_help();
+    exit(1);
+  }
+  std::cout << "--- Running REPKILLER v0.9.b ---\n"
+               "     Bitlab - Arquitectura de Computadores\n"
+               "           Universidad de M\xc3\xa1laga 2018\n"
+               "\n"
+            << std::flush;
+  const bool timing = getenv("RK_TIMING") != nullptr;
+  const int device = getenv("RK_DEVICE") ? atoi(getenv("RK_DEVICE")) : 0;
+
+  sequence_manager seq_manager;
+  FragmentsDatabase frag_db(frags_file, seq_manager, device);
+  frags_file.close();
+  if (timing) {
+    const rk_load_stats &ls = frag_db.load_stats();
+    std::cerr << "[rk] loaded=" << ls.n_loaded << " kept=" << ls.n_kept << " device_ms=" << ls.ms_device << "\n";
+  }
+
+  SaverQueue sq(seq_manager);
+  sq.start();
+  while (!params.empty()) {
+    auto param = params.front();
+    params.pop();
+    execWithParams(frag_db, param, out_file_base_path, sq, timing);
+  }
+  sq.stop();
+  std::cout << "Repkiller finished with no errors\n";
+  return 0;
+}

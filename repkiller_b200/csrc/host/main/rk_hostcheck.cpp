@@ -1,0 +1,80 @@
+// Test helper for the host side of the drop-in.
+//   rk_hostcheck parse <in.csv> <out.bin>     readFragment over every data row: accepted records, 109 B each (no GPU)
+//   rk_hostcheck write <in.csv> <out.csv>     writer format: parses, then writes every accepted record as its own
+//                                             singleton group in file order (no GPU)
+//   rk_hostcheck steps <in.csv> <out.csv> <len_ratio> <pos_ratio>
+//                                             the reference's call sequence (repkiller.cpp:83-96):
+//                                             generate_fragment_groups -> generate_diagonal_func -> sort_groups ->
+//                                             save_all_frag_pairs, each through its own facade (GPU)
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <string>
+#include <vector>
+
+#include "../FragmentsDatabase.h"
+#include "../commonFunctions.h"
+
+static std::vector<FragFile> parse_rows(const char *path, std::string *header) {
+  std::ifstream in(path, std::ifstream::in | std::ifstream::binary);
+  std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  size_t pos = 0;
+  for (int ln = 0; ln < 16; ++ln) {
+    const size_t s = pos;
+    while (pos < data.size() && data[pos] != '\n') ++pos;
+    if (header) header->append(data, s, pos - s).append("\n");
+    if (pos < data.size()) ++pos;
+  }
+  std::vector<FragFile> out;
+  bool eof = data.empty();
+  while (!eof) {
+    const size_t s = pos;
+    while (pos < data.size() && data[pos] != '\n') ++pos;
+    const size_t l = pos - s;
+    if (pos < data.size()) ++pos; else eof = true;
+    FragFile f;
+    memset(&f, 0, sizeof f);
+    if (readFragment(&f, data.data() + s, l)) out.push_back(f);
+  }
+  return out;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 4) return 2;
+  const std::string mode = argv[1];
+  if (mode == "parse") {
+    auto recs = parse_rows(argv[2], nullptr);
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 3;
+    if (!recs.empty()) fwrite(recs.data(), sizeof(FragFile), recs.size(), f);
+    fclose(f);
+    return 0;
+  }
+  if (mode == "write") {
+    std::string header;
+    auto recs = parse_rows(argv[2], &header);
+    sequence_manager sm;
+    sm.sequences.emplace_back(0, 0);
+    sm.sequences.emplace_back(1, 0);
+    sm.read_header(header);
+    FGList fgl;
+    for (auto &r : recs) fgl.push_back(new FragsGroup{&r});
+    save_all_frag_pairs(argv[3], sm, fgl);
+    return 0;
+  }
+  if (mode == "steps" && argc >= 6) {
+    std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+    sequence_manager sm;
+    FragmentsDatabase db(in, sm);
+    FGList groups;
+    generate_fragment_groups(db, groups, sm, std::stod(argv[4]), std::stod(argv[5]));
+    std::vector<size_t> diag(db.getA());
+    generate_diagonal_func(db, diag.data());
+    sort_groups(groups, diag.data());
+    save_all_frag_pairs(argv[3], sm, groups);
+    return 0;
+  }
+  return 2;
+}

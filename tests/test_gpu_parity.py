@@ -189,3 +189,52 @@ def test_ratio_sweep_reuses_loaded_database(ctx):
         assert res.n_groups == g.n_groups
         assert_same(f"order {lr},{pr}", res.order, g.order)
         assert_same(f"gid {lr},{pr}", res.gid, g.out_gid)
+
+
+# ---- the drop-in CLI and the reference-named facades (host C++ over the C ABI) ----------------------------
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "repkiller_b200", "bin", "repkiller")
+HOSTCHECK = os.path.join(ROOT, "repkiller_b200", "bin", "rk_hostcheck")
+BANNER = ("--- Running REPKILLER v0.9.b ---\n     Bitlab - Arquitectura de Computadores\n"
+          "           Universidad de Málaga 2018\n\nRepkiller finished with no errors\n").encode()
+
+
+def test_cli_bytes_equal_reference_on_fuzz(fuzz_cases, tmp_path):
+    import subprocess
+    for c in fuzz_cases[::3]:
+        inp = tmp_path / "in.csv"
+        inp.write_text(c["csv"], newline="")
+        outp = tmp_path / "out.csv"
+        p = subprocess.run([CLI, str(inp), str(outp), repr(c["len_ratio"]), repr(c["pos_ratio"])], capture_output=True)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout == BANNER
+        assert outp.read_bytes() == c["ref_out"].encode("latin1"), f"fuzz seed {c['seed']}"
+
+
+def test_cli_and_facade_steps_on_c1(medium_cases, tmp_path):
+    import subprocess
+    c = medium_cases["c1"]
+    w = gen.Workload(**c["workload"])
+    rec = gen.generate(w)
+    inp = tmp_path / "c1.csv"
+    O.write_input_csv(str(inp), rec, w.lx, w.ly)
+    # the reference's golden md5 was produced from this same CSV shape (tests/golden/make_golden.py)
+    for tool, args in [(CLI, []), (HOSTCHECK, ["steps"])]:
+        outp = tmp_path / "out.csv"
+        cmd = [tool, *args, str(inp), str(outp), "0.05", "0.05"]
+        p = subprocess.run(cmd, capture_output=True)
+        assert p.returncode == 0, p.stderr
+        assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"], tool
+        outp.unlink()
+
+
+def test_cli_unwritable_output_falls_back(tmp_path, fuzz_cases):
+    import subprocess
+    c = fuzz_cases[0]
+    inp = tmp_path / "in.csv"
+    inp.write_text(c["csv"], newline="")
+    p = subprocess.run([CLI, str(inp), "/nonexistent-dir/out.csv", repr(c["len_ratio"]), repr(c["pos_ratio"])],
+                       capture_output=True, cwd=tmp_path)
+    assert p.returncode == 0
+    assert b"Couldn't access /nonexistent-dir/out.csv, saving into represults-1.csv" in p.stderr
+    assert (tmp_path / "represults-1.csv").read_bytes() == c["ref_out"].encode("latin1")
