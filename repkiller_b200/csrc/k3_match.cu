@@ -13,8 +13,8 @@
 // the link bits raised by K1).  Fragments arrive here stably sorted by (strand class, first bucket of their
 // run): every run is a contiguous segment in processing order and segments are independent of one another.
 //
-//   tier 1: one thread per segment of <= 32 fragments (the typical segment holds 3); inserted entries are a
-//           32-bit mask over the segment, scanned newest first.
+//   tier 1: segments of <= 32 fragments (the typical segment holds 3): candidate masks for every fragment in
+//           parallel, then the head's thread replays the segment with bit operations (see k_match_small).
 //   tier 2: one warp per longer segment: 32 queries at a time are scored against the entry list (uniform
 //           loads, each lane its own query), then the insertions inside the chunk are replayed in order with
 //           ballots; work per query is O(entries), not O(segment).
@@ -88,56 +88,158 @@ __device__ __forceinline__ u32 neighbour_bucket(u32 c, u32 max_index) {
   return NO_BUCKET;
 }
 
-__global__ void __launch_bounds__(128) k_match_small(MatchArgs a) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.m) return;
-  const u32 key = a.skey[i];
-  if (i > 0 && a.skey[i - 1] == key) return;  // not the head of a segment
-  u32 n = 1;
-  while (n <= (u32)T1_MAX && i + n < a.m && a.skey[i + n] == key) ++n;
-  if (n > (u32)T1_MAX) {
+// ---- tier 1: candidate masks -------------------------------------------------------------------------------
+// Whether entry k is a candidate for query j (deviation(k, j) > 0) does not depend on what was inserted, only
+// on the two fragments.  So the sequential part of the greedy loop shrinks to bit operations:
+//   cand[j]  = { k < j in j's segment, bucket-compatible, deviation > 0 }     computed for all j in parallel
+//   in order: hit = cand[j] & inserted;  hit == 0 -> j is inserted;  one bit -> that entry is the owner;
+//             several bits (2 % of the queries) -> exact scores decide (greatest, own bucket first, newest first).
+// deviation > 0  <=>  q_len <= 1 and q_pos <= 1 and not both == 1, with q = fl(dif / fl(length*ratio)).  The
+// comparison of the correctly rounded quotient with 1 is decided without dividing whenever dif is not within
+// 2^-40 (relative) of the threshold; inside that band the division is done.
+
+constexpr double BAND_LO = 1.0 - 0x1p-40;
+constexpr double BAND_HI = 1.0 + 0x1p-40;
+
+// Integer thresholds of one similarity term for one query (t = fl(length*ratio) > 0):
+//   d <  pass  =>  fl(d/t) < 1  (term > 0)          pass = ceil(t*(1-2^-40)), clamped to u32
+//   d >  rej   =>  fl(d/t) > 1  (term < 0)          rej  = floor(t*(1+2^-40)), clamped to u32
+// anything in between is decided by the real division.  Clamping only widens the band.
+struct Thresh {
+  u32 pass, rej;
+  double t;
+};
+__device__ __forceinline__ Thresh make_thresh(u32 len, double ratio) {
+  Thresh th;
+  th.t = __dmul_rn((double)len, ratio);
+  th.pass = __double2uint_ru(fmin(th.t * BAND_LO, 4294967295.0));
+  th.rej = __double2uint_rd(fmin(th.t * BAND_HI, 4294967295.0));
+  return th;
+}
+// 0: fl(d/t) > 1 (similarity < 0) ; 1: fl(d/t) < 1 ; 2: fl(d/t) == 1 (similarity exactly 0)
+__device__ __forceinline__ int quotient_vs_one(u32 d, const Thresh &th) {
+  if (d < th.pass) return 1;
+  if (d > th.rej) return 0;
+  const double q = __ddiv_rn((double)d, th.t);
+  return q > 1.0 ? 0 : (q == 1.0 ? 2 : 1);
+}
+
+constexpr int MT_THREADS = 256;
+constexpr int MT_TILE = MT_THREADS + 32;  // heads live in the first 256 positions, their segments end before 288
+
+__global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
+  __shared__ u32 s_key[MT_TILE], s_c[MT_TILE], s_len[MT_TILE], s_rank[MT_TILE], s_bkt[MT_TILE], s_cand[MT_TILE];
+  __shared__ u8 s_xm[MT_TILE];
+  __shared__ u32 s_nz[MT_TILE];  // per head: positions of its segment that have candidates
+  __shared__ u32 s_prev_key;
+
+  const u32 tid = threadIdx.x;
+  const u32 bs = blockIdx.x * MT_THREADS;
+  const u32 count = min((u32)MT_TILE, a.m - bs);  // valid tile positions
+
+  for (u32 e = tid; e < (u32)MT_TILE; e += MT_THREADS) {
+    s_nz[e] = 0;
+    if (e < count) {
+      const u32 r = a.srank[bs + e];
+      const u32 c = a.c_r[r];
+      s_key[e] = a.skey[bs + e];
+      s_rank[e] = r;
+      s_c[e] = c;
+      s_len[e] = a.len_r[r];
+      s_bkt[e] = c / DIVISOR;
+      s_xm[e] = (a.is_y && a.parent[r] != RK_NONE32) ? 1 : 0;  // X-matched: Y-insert without a query (:59)
+    }
+  }
+  if (tid == 0) s_prev_key = bs ? a.skey[bs - 1] : 0;
+  __syncthreads();
+
+  // phase 1: candidate mask of every tile element over its predecessors in the segment (bit d-1: element e-d)
+  const bool foreign0 = bs != 0 && s_prev_key == s_key[0];
+  for (u32 e = tid; e < (u32)MT_TILE; e += MT_THREADS) {
+    u32 dist_mask = 0, pos = 0;
+    if (e < count) {
+      const u32 key = s_key[e];
+      const u32 c = s_c[e], len = s_len[e];
+      const bool query = !s_xm[e] && len != 0;  // length 0: every score is NaN or 0 -> never matches
+      const u32 b = s_bkt[e];
+      const u32 nbk = neighbour_bucket(c, a.max_index);
+      const Thresh tl = make_thresh(len, a.len_ratio), tp = make_thresh(len, a.pos_ratio);
+      for (u32 d = 1; d <= e && d <= 32; ++d) {
+        const u32 k = e - d;
+        if (s_key[k] != key) break;
+        pos = d;
+        if (!query) continue;
+        const u32 el = s_len[k], ec = s_c[k], bk = s_bkt[k];
+        const u32 dl = len > el ? len - el : el - len;
+        const u32 dc = c > ec ? c - ec : ec - c;
+        if (dl > tl.rej || dc > tp.rej || (bk != b && bk != nbk)) continue;
+        const int ql = quotient_vs_one(dl, tl);
+        if (ql == 0) continue;
+        const int qp = quotient_vs_one(dc, tp);
+        if (qp == 0 || (ql == 2 && qp == 2)) continue;
+        dist_mask |= 1u << (d - 1);
+      }
+    }
+    // position-based mask: bit p <-> element head+p, p = pos - d
+    const u32 cand = pos ? (__brev(dist_mask) >> (32 - pos)) : 0;
+    s_cand[e] = cand;
+    if (e < count) {
+      const u32 h = e - pos;
+      if (cand) {
+        if (pos < 32) atomicOr(&s_nz[h], 1u << pos);
+      } else if (!a.is_y && !(h == 0 && foreign0)) {
+        // no candidate at all: an X entry for sure.  (Continuations of the previous tile's segment are that
+        // CTA's; elements whose head lies beyond position 255 are written again, identically, by the next CTA.)
+        a.parent[s_rank[e]] = RK_NONE32;
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 2: the thread at a segment's head replays, in order, only the positions that have candidates; every
+  // other position (no candidate, or X-matched in the Y pass) is inserted from the start.
+  if (tid >= count) return;
+  const u32 key = s_key[tid];
+  const bool head = tid == 0 ? !foreign0 : s_key[tid - 1] != key;
+  if (!head) return;
+  if (tid + 32 < count && s_key[tid + 32] == key) {  // more than 32 fragments: the tile holds head+32, exact
     const u32 slot = atomicAdd(a.work_count, 1u);
-    if (slot < a.work_cap) a.worklist[slot] = i;
+    if (slot < a.work_cap) a.worklist[slot] = bs + tid;
     else atomicOr(a.err, ERR_WORKLIST);
     return;
   }
-  u32 ec[T1_MAX], el[T1_MAX];
-  u32 inserted = 0;
-  for (u32 j = 0; j < n; ++j) {
-    const u32 r = a.srank[i + j];
-    const u32 c = a.c_r[r], len = a.len_r[r];
-    ec[j] = c;
-    el[j] = len;
-    if (a.is_y && a.parent[r] != RK_NONE32) {  // X-matched: Y-insert without a query (commonFunctions.cpp:59)
-      inserted |= 1u << j;
-      continue;
-    }
-    const u32 b = c / DIVISOR;
-    const u32 nbk = neighbour_bucket(c, a.max_index);
-    const double t_len = __dmul_rn((double)len, a.len_ratio);
-    const double t_pos = __dmul_rn((double)len, a.pos_ratio);
-    double best_sc = 0.0;
-    int best = -1;
-    bool best_own = false;
-    // newest entry first; the own bucket is scanned before the neighbour, `>` is strict (:40)
-    for (u32 msk = inserted; msk;) {
-      const int k = 31 - __clz(msk);
-      msk &= ~(1u << k);
-      const u32 bk = ec[k] / DIVISOR;
-      const bool own = bk == b;
-      if (!own && bk != nbk) continue;
-      const double sc = deviation(ec[k], el[k], c, len, t_len, t_pos);
-      if (sc > best_sc || (sc == best_sc && best >= 0 && own && !best_own)) {
-        best_sc = sc;
-        best = k;
-        best_own = own;
-      }
-    }
-    if (best >= 0) {
-      a.parent[r] = a.srank[i + best];
+  u32 todo = s_nz[tid];
+  u32 inserted = ~todo;
+  while (todo) {
+    const u32 p = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const u32 e = tid + p;
+    const u32 hit = s_cand[e] & inserted;
+    if (!hit) {
+      inserted |= 1u << p;
+      if (!a.is_y) a.parent[s_rank[e]] = RK_NONE32;
+    } else if ((hit & (hit - 1)) == 0) {
+      a.parent[s_rank[e]] = s_rank[tid + __ffs(hit) - 1];
     } else {
-      inserted |= 1u << j;
-      if (!a.is_y) a.parent[r] = RK_NONE32;
+      // several inserted candidates: greatest score, own bucket before neighbour, newest first (:40 strict >)
+      const u32 c = s_c[e], len = s_len[e], b = s_bkt[e];
+      const double t_len = __dmul_rn((double)len, a.len_ratio);
+      const double t_pos = __dmul_rn((double)len, a.pos_ratio);
+      double best_sc = 0.0;
+      int best = -1;
+      bool best_own = false;
+      for (u32 msk = hit; msk;) {
+        const int k = 31 - __clz(msk);
+        msk &= ~(1u << k);
+        const bool own = s_bkt[tid + k] == b;
+        const double sc = deviation(s_c[tid + k], s_len[tid + k], c, len, t_len, t_pos);
+        if (sc > best_sc || (sc == best_sc && best >= 0 && own && !best_own)) {
+          best_sc = sc;
+          best = k;
+          best_own = own;
+        }
+      }
+      a.parent[s_rank[e]] = s_rank[tid + best];
     }
   }
 }
@@ -240,7 +342,7 @@ int launch_match(const MatchArgs &a, cudaStream_t st) {
   cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
   {
     KScope ks(KID_MATCH_SMALL, st);
-    k_match_small<<<(a.m + 127) / 128, 128, 0, st>>>(a);
+    k_match_small<<<(a.m + MT_THREADS - 1) / MT_THREADS, MT_THREADS, 0, st>>>(a);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
