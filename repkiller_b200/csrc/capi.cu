@@ -432,7 +432,7 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
                 &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st);
   CK(cudaEventRecord(ev[2], st));
   // the rank sort does not depend on the number of dropped records: they carry the largest key and sort last
-  launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st);
+  launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st, &ctx->d_cnt->err);
   CK(cudaEventRecord(ev[3], st));
   CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -446,9 +446,9 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   launches += launch_keys(ctx->fidx_r, m, g, ctx->xs, ctx->ys, ctx->len, ctx->flags, ctx->link_x, ctx->link_y, ctx->cx_r, ctx->cy_r,
               ctx->len_r, ctx->ys_r, ctx->kx, ctx->ky, st);
   CK(cudaEventRecord(ev[5], st));
-  launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st);
+  launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st, &ctx->d_cnt->err);
   CK(cudaEventRecord(ev[6], st));
-  launches += launch_sort_pairs(ctx->ky, nullptr, ctx->sky, ctx->ry, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_y, ctx->sort_work, st);
+  launches += launch_sort_pairs(ctx->ky, nullptr, ctx->sky, ctx->ry, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_y, ctx->sort_work, st, &ctx->d_cnt->err);
   CK(cudaEventRecord(ev[7], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
@@ -505,7 +505,7 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
   CK(cudaEventRecord(ev[4], st));
   // gids are < number of groups <= m; sorting by ceil_log2(m) bits avoids a host round trip for the count
   launches += launch_sort_pairs(ctx->gid_rank, nullptr, ctx->sgid, ctx->srank, ctx->tmp_k, ctx->tmp_v, m, ceil_log2(m),
-                                ctx->sort_work, st);
+                                ctx->sort_work, st, &ctx->d_cnt->err);
   launches += run_order(ctx, flags);
   CK(cudaEventRecord(ev[5], st));
   return finish_group(ctx, flags, out, launches);

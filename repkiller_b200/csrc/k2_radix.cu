@@ -128,20 +128,209 @@ __global__ void k_iota_copy(const u32 *__restrict__ kin, const u32 *__restrict__
   }
 }
 
+// ---- one-sweep path: one global histogram for all digit positions, then per pass a single kernel whose tiles
+// chain their per-digit counts with decoupled look-back (flag+value packed in one 32-bit word, tile ids handed
+// out by an atomic counter so that a tile only ever waits on tiles that are already running) ---------------
+
+constexpr u32 OS_AGG = 1u << 30;  // the tile's own digit count is published
+constexpr u32 OS_PFX = 2u << 30;  // the inclusive prefix over tiles 0..t is published
+constexpr u32 OS_VAL = (1u << 30) - 1;
+constexpr u64 OS_MAX_N = 1ull << 30;
+constexpr int OS_MAX_PASSES = 4;
+
+__global__ void __launch_bounds__(256) k_onesweep_hist(const u32 *__restrict__ keys, u64 n, int passes, int key_bits,
+                                                       u32 *__restrict__ ghist) {
+  __shared__ u32 h[OS_MAX_PASSES][RADIX];
+  for (int p = 0; p < OS_MAX_PASSES; ++p) h[p][threadIdx.x] = 0;
+  __syncthreads();
+  const u32 last_mask = (1u << (key_bits - 8 * (passes - 1))) - 1;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u32 k = keys[i];
+#pragma unroll
+    for (int p = 0; p < OS_MAX_PASSES; ++p)
+      if (p < passes) atomicAdd(&h[p][(k >> (8 * p)) & (p == passes - 1 ? last_mask : 0xFFu)], 1u);
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    const u32 c = h[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * RADIX + threadIdx.x], c);
+  }
+}
+
+// block p: exclusive scan of the 256 bins of pass p, in place
+__global__ void __launch_bounds__(RADIX) k_onesweep_bases(u32 *ghist) {
+  u32 *g = ghist + blockIdx.x * RADIX;
+  const u32 v = g[threadIdx.x];
+  g[threadIdx.x] = block_excl_scan<RADIX>(v, nullptr);
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+    k_onesweep_pass(const u32 *__restrict__ kin, const u32 *__restrict__ vin, u32 *__restrict__ kout, u32 *__restrict__ vout,
+                    u64 n, int shift, u32 mask, const u32 *__restrict__ digit_start, u32 *state, u32 *tile_counter, u32 *err) {
+  __shared__ u32 warp_cnt[RS_WARPS][RADIX];
+  __shared__ u32 digit_base[RADIX];
+  __shared__ u32 gbase[RADIX];
+  __shared__ u32 skeys[RS_TILE];
+  __shared__ u32 svals[RS_TILE];
+  __shared__ u32 s_tile;
+
+  const u32 tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) warp_cnt[q][tid] = 0;
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u64 tile_start = (u64)tile * RS_TILE;
+  const u32 nvalid = (u32)((n - tile_start < (u64)RS_TILE) ? (n - tile_start) : RS_TILE);
+
+  u32 key[RS_ITEMS], val[RS_ITEMS], rnk[RS_ITEMS];
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 local = w * RS_WARP_TILE + j * 32 + lane;
+    const u64 i = tile_start + local;
+    if (local < nvalid) {
+      key[j] = kin[i];
+      val[j] = vin ? vin[i] : (u32)i;
+    } else {
+      key[j] = 0xFFFFFFFFu;
+      val[j] = 0;
+    }
+  }
+
+  const u32 lt = lanemask_lt();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 d = (key[j] >> shift) & mask;
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    u32 old = 0;
+    if ((int)lane == leader) {
+      old = warp_cnt[w][d];
+      warp_cnt[w][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    rnk[j] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread tid = digit tid: count of VALID keys with this digit (padding sits in the top digit, after them)
+  u32 total = 0;
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) {
+    const u32 c = warp_cnt[q][tid];
+    warp_cnt[q][tid] = total;
+    total += c;
+  }
+  u32 valid_total = total;
+  if (tid == mask) valid_total -= (u32)RS_TILE - nvalid;
+
+  // publish, look back, publish the inclusive prefix
+  volatile u32 *my_state = state + (u64)tile * RADIX + tid;
+  u32 excl = 0;
+  if (tile == 0) {
+    *my_state = OS_PFX | valid_total;
+  } else {
+    *my_state = OS_AGG | valid_total;
+    u32 prev = tile - 1;
+    u32 spins = 0;
+    for (;;) {
+      const u32 sv = *(volatile u32 *)(state + (u64)prev * RADIX + tid);
+      const u32 flag = sv & ~OS_VAL;
+      if (flag == 0) {
+        if (++spins > (1u << 26)) {  // predecessors are always running; fail loudly rather than hang
+          atomicOr(err, ERR_SPIN);
+          break;
+        }
+        continue;
+      }
+      excl += sv & OS_VAL;
+      if (flag == OS_PFX) break;
+      --prev;  // tile 0 always publishes OS_PFX, so prev never underflows
+    }
+    *my_state = OS_PFX | (excl + valid_total);
+  }
+
+  const u32 dbase = block_excl_scan<RS_THREADS>(total, nullptr);
+  digit_base[tid] = dbase;
+  gbase[tid] = digit_start[tid] + excl - dbase;
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 d = (key[j] >> shift) & mask;
+    const u32 pos = digit_base[d] + warp_cnt[w][d] + rnk[j];
+    skeys[pos] = key[j];
+    svals[pos] = val[j];
+  }
+  __syncthreads();
+
+  for (u32 p = tid; p < nvalid; p += RS_THREADS) {
+    const u32 k = skeys[p];
+    const u32 dst = gbase[(k >> shift) & mask] + p;
+    kout[dst] = k;
+    vout[dst] = svals[p];
+  }
+}
+
 static inline u64 align_up(u64 x, u64 a) { return (x + a - 1) / a * a; }
+
+static inline u64 onesweep_state_words(u64 n) {
+  const u64 tiles = (n + RS_TILE - 1) / RS_TILE;
+  return OS_MAX_PASSES * RADIX + 64 + OS_MAX_PASSES * tiles * RADIX;
+}
 
 u64 sort_work_bytes(u64 n) {
   const u64 tiles = (n + RS_TILE - 1) / RS_TILE;
   const u64 counts = tiles * RADIX;
   const u64 nb = (counts + SCAN_CHUNK - 1) / SCAN_CHUNK;
-  return align_up(counts * 4, 256) + align_up((nb + 2) * 4, 256);
+  const u64 three_kernel = align_up(counts * 4, 256) + align_up((nb + 2) * 4, 256);
+  const u64 onesweep = align_up(onesweep_state_words(n) * 4, 256);
+  return three_kernel > onesweep ? three_kernel : onesweep;
+}
+
+static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp, u32 *vals_tmp,
+                           u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word) {
+  const int passes = (key_bits + 7) / 8;
+  const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+  u32 *ghist = reinterpret_cast<u32 *>(work);          // [4][256]
+  u32 *counters = ghist + OS_MAX_PASSES * RADIX;          // [4] tile counters, [4] = error word when none was set
+  u32 *state = counters + 64;                            // [passes][tiles][256]
+  cudaMemsetAsync(work, 0, (OS_MAX_PASSES * RADIX + 64 + (u64)passes * tiles * RADIX) * 4, st);
+  u32 *err = err_word ? err_word : counters + 8;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    KScope ks(KID_RADIX_HIST, st);
+    u64 blocks = (n + 256 * 16 - 1) / (256 * 16);
+    if (blocks > (u64)sms * 8) blocks = (u64)sms * 8;
+    k_onesweep_hist<<<(unsigned)blocks, 256, 0, st>>>(keys_in, n, passes, key_bits, ghist);
+    k_onesweep_bases<<<passes, RADIX, 0, st>>>(ghist);
+  }
+  const u32 *ksrc = keys_in, *vsrc = vals_in;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    const int bits = (key_bits - shift) < 8 ? (key_bits - shift) : 8;
+    const u32 mask = (1u << bits) - 1;
+    const bool to_out = ((passes - 1 - p) % 2) == 0;
+    u32 *kdst = to_out ? keys_out : keys_tmp;
+    u32 *vdst = to_out ? vals_out : vals_tmp;
+    KScope ks(KID_RADIX_SCATTER, st);
+    k_onesweep_pass<<<tiles, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask, ghist + p * RADIX,
+                                                  state + (u64)p * tiles * RADIX, counters + p, err);
+    ksrc = kdst;
+    vsrc = vdst;
+  }
+  return 2 + passes;
 }
 
 int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp,
-                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st) {
+                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word) {
   if (n == 0) return 0;
   if (key_bits < 1) key_bits = 1;
   if (key_bits > 32) key_bits = 32;
+  if (n < OS_MAX_N) return launch_onesweep(keys_in, vals_in, keys_out, vals_out, keys_tmp, vals_tmp, n, key_bits, work, st, err_word);
   const int passes = (key_bits + 7) / 8;
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
   u32 *counts = reinterpret_cast<u32 *>(work);

@@ -88,7 +88,7 @@ int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, 
 // K2: stable LSD radix sort of (key,value) pairs; result in keys_out/vals_out.
 u64 sort_work_bytes(u64 n);
 int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp,
-                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st);
+                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word = nullptr);
 
 // K2 keys: rank-order SoA + super-bucket sort keys.
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *ys, const u32 *len, const u8 *flags,
