@@ -11,11 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "librk_b200.so")
+LIB = os.path.join(HERE, "librk_b200%s.so" % os.environ.get("RK_LIB_SUFFIX", ""))
 CLI = os.path.join(HERE, "bin", "repkiller")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v"] + os.environ.get("RK_EXTRA_NVCC", "").split()
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -31,10 +31,11 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB, deps):
         return LIB
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    BUILD = os.path.join(HERE, "build" + os.environ.get("RK_LIB_SUFFIX", ""))
+    os.makedirs(BUILD, exist_ok=True)
     procs = []
     for src in cu:
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [NVCC, *ARCH, *NVCC_FLAGS, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -45,7 +46,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError(f"nvcc failed on {src}")
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+    with open(os.path.join(BUILD, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))

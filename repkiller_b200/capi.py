@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librk_b200.so")
+LIB_PATH = os.path.join(HERE, "librk_b200%s.so" % os.environ.get("RK_LIB_SUFFIX", ""))  # suffix: tuning variants only
 
 RK_NONE = 0xFFFFFFFF
 F_HOST_RESULT, F_NO_SORT, F_TIMING = 1, 2, 4

@@ -11,19 +11,39 @@
 // digit counters), reordered through shared memory so that each digit's run leaves as one contiguous,
 // coalesced store, and placed at the scanned global offset.  HBM traffic per pass and key: 4 B (histogram)
 // + 8 B read + 8 B written.
+#include <cstdlib>
+
 #include "rk_common.cuh"
 #include "rk_scan.cuh"
 
 namespace rk {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
+#ifndef RK_RS_ITEMS
+#define RK_RS_ITEMS 16
+#endif
+#ifndef RK_RS_MINBLOCKS
+#define RK_RS_MINBLOCKS 3
+#endif
+constexpr int RS_ITEMS = RK_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_WARP_TILE = 32 * RS_ITEMS;  // 512 consecutive keys per warp
 constexpr int RADIX = 256;
 
 // ---- radix passes -------------------------------------------------------------------------------------
+
+// lanes of the warp whose 8-bit digit equals this lane's
+__device__ __forceinline__ u32 digit_peers(u32 d) {
+  u32 peers = 0xFFFFFFFFu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const u32 bit = (d >> b) & 1u;
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, bit);
+    peers &= bal ^ (bit - 1u);  // bit ? bal : ~bal
+  }
+  return peers;
+}
 
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u32 *__restrict__ keys, u64 n, int shift, u32 mask,
                                                            u32 *__restrict__ counts, u32 num_tiles) {
@@ -72,11 +92,16 @@ __global__ void __launch_bounds__(RS_THREADS)
   }
   __syncthreads();
 
+  // stable rank of every key among the keys of its warp: first the peer masks of all 16 rounds (8 independent
+  // ballots per round pipeline; match.any is a long-latency instruction and would serialise the rounds), then the
+  // short dependent chain through the per-warp digit counters.
   const u32 lt = lanemask_lt();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) rnk[j] = digit_peers((key[j] >> shift) & mask);
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
     const u32 d = (key[j] >> shift) & mask;
-    const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+    const u32 peers = rnk[j];
     const int leader = __ffs(peers) - 1;
     u32 old = 0;
     if ((int)lane == leader) {
@@ -129,8 +154,10 @@ __global__ void k_iota_copy(const u32 *__restrict__ kin, const u32 *__restrict__
 }
 
 // ---- one-sweep path: one global histogram for all digit positions, then per pass a single kernel whose tiles
-// chain their per-digit counts with decoupled look-back (flag+value packed in one 32-bit word, tile ids handed
-// out by an atomic counter so that a tile only ever waits on tiles that are already running) ---------------
+// chain their per-digit counts with decoupled look-back (flag+value packed in one 32-bit word; tile ids come from
+// an atomic ticket counter, so a tile only ever waits on tiles that are already running).  Measured alternatives
+// (B200, 10M pairs, one pass): serial look-back 100 us, batched x16 86 us, a dedicated scan-agent CTA 194 us,
+// histogram+scan+scatter as three kernels 28+21+62 us ---------------------------------------------------------
 
 constexpr u32 OS_AGG = 1u << 30;  // the tile's own digit count is published
 constexpr u32 OS_PFX = 2u << 30;  // the inclusive prefix over tiles 0..t is published
@@ -164,7 +191,7 @@ __global__ void __launch_bounds__(RADIX) k_onesweep_bases(u32 *ghist) {
   g[threadIdx.x] = block_excl_scan<RADIX>(v, nullptr);
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RK_RS_MINBLOCKS)
     k_onesweep_pass(const u32 *__restrict__ kin, const u32 *__restrict__ vin, u32 *__restrict__ kout, u32 *__restrict__ vout,
                     u64 n, int shift, u32 mask, const u32 *__restrict__ digit_start, u32 *state, u32 *tile_counter, u32 *err) {
   __shared__ u32 warp_cnt[RS_WARPS][RADIX];
@@ -197,11 +224,16 @@ __global__ void __launch_bounds__(RS_THREADS)
     }
   }
 
+  // stable rank of every key among the keys of its warp: first the peer masks of all 16 rounds (8 independent
+  // ballots per round pipeline; match.any is a long-latency instruction and would serialise the rounds), then the
+  // short dependent chain through the per-warp digit counters.
   const u32 lt = lanemask_lt();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) rnk[j] = digit_peers((key[j] >> shift) & mask);
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
     const u32 d = (key[j] >> shift) & mask;
-    const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+    const u32 peers = rnk[j];
     const int leader = __ffs(peers) - 1;
     u32 old = 0;
     if ((int)lane == leader) {
@@ -225,28 +257,42 @@ __global__ void __launch_bounds__(RS_THREADS)
   u32 valid_total = total;
   if (tid == mask) valid_total -= (u32)RS_TILE - nvalid;
 
-  // publish, look back, publish the inclusive prefix
+  // publish this tile's counts, look back over the predecessors, publish the inclusive prefix
   volatile u32 *my_state = state + (u64)tile * RADIX + tid;
   u32 excl = 0;
   if (tile == 0) {
     *my_state = OS_PFX | valid_total;
   } else {
     *my_state = OS_AGG | valid_total;
-    u32 prev = tile - 1;
+    // Batches of LB independent loads: the tiles of one wave start together and all sit in the AGG state, so the
+    // walk back to the last published prefix is as long as the wave; one load in flight would cost an L2 round
+    // trip per predecessor.
+    constexpr int LB = 16;
+    u32 next = tile;  // predecessors next-1, next-2, ... are still to be added
     u32 spins = 0;
-    for (;;) {
-      const u32 sv = *(volatile u32 *)(state + (u64)prev * RADIX + tid);
-      const u32 flag = sv & ~OS_VAL;
-      if (flag == 0) {
-        if (++spins > (1u << 26)) {  // predecessors are always running; fail loudly rather than hang
-          atomicOr(err, ERR_SPIN);
-          break;
+    bool done = false;
+    while (!done) {
+      u32 v[LB];
+#pragma unroll
+      for (int j = 0; j < LB; ++j)
+        v[j] = ((u32)j < next) ? *(volatile u32 *)(state + (u64)(next - 1 - j) * RADIX + tid) : (2u << 30) /* OS_PFX | 0 */;
+      u32 used = 0;
+#pragma unroll
+      for (int j = 0; j < LB; ++j) {
+        if (!done && used == (u32)j) {
+          const u32 flag = v[j] & ~OS_VAL;
+          if (flag != 0) {
+            excl += v[j] & OS_VAL;
+            ++used;
+            if (flag == OS_PFX) done = true;  // tile 0 always publishes OS_PFX; past it the filler is OS_PFX|0
+          }
         }
-        continue;
       }
-      excl += sv & OS_VAL;
-      if (flag == OS_PFX) break;
-      --prev;  // tile 0 always publishes OS_PFX, so prev never underflows
+      next -= used < next ? used : next;
+      if (!done && used == 0 && ++spins > (1u << 24)) {  // predecessors are always running: fail loudly, never hang
+        atomicOr(err, ERR_SPIN);
+        break;
+      }
     }
     *my_state = OS_PFX | (excl + valid_total);
   }
@@ -330,7 +376,8 @@ int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32
   if (n == 0) return 0;
   if (key_bits < 1) key_bits = 1;
   if (key_bits > 32) key_bits = 32;
-  if (n < OS_MAX_N) return launch_onesweep(keys_in, vals_in, keys_out, vals_out, keys_tmp, vals_tmp, n, key_bits, work, st, err_word);
+  static const bool force_3k = getenv("RK_SORT_3K") != nullptr;  // tuning switch: histogram + scan + scatter per pass
+  if (n < OS_MAX_N && !force_3k) return launch_onesweep(keys_in, vals_in, keys_out, vals_out, keys_tmp, vals_tmp, n, key_bits, work, st, err_word);
   const int passes = (key_bits + 7) / 8;
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
   u32 *counts = reinterpret_cast<u32 *>(work);
