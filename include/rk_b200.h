@@ -143,6 +143,35 @@ uint64_t rk_sort_pairs_work_bytes(uint64_t n);
 int rk_sort_pairs(rk_ctx *ctx, const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out,
                   uint32_t *values_out, uint32_t *keys_tmp, uint32_t *values_tmp, uint64_t n, int key_bits, void *work);
 
+/* ---- multi-GPU stage entry points -----------------------------------------------------------------------------
+ * The kernels of rk_load_aos / rk_group on caller-owned DEVICE arrays, for the range-partitioned single
+ * comparison (repkiller_b200/dist.py): fragments are exchanged between ranks (NCCL) between these calls, so every
+ * array is already in the order the kernel consumes ("direct" layout).  Work is queued on the context's stream. */
+uint64_t rk_st_link_words(uint64_t seq_len); /* u32 words of one link bitmap (axis length = loaded length) */
+/* K1 on this rank's slice of the file; link_x/link_y (rk_st_link_words words each) are this rank's contribution
+ * and must be OR-ed over the ranks (rk_st_or_words) before rk_st_keys.  Synchronises; *n_dropped = fragments of the
+ * never-visited last X bucket. */
+int rk_st_decode(rk_ctx *ctx, const void *aos, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, uint32_t *xs, uint32_t *ys,
+                 uint32_t *len, uint8_t *flags, float *identity, uint32_t *key0, uint32_t *link_x, uint32_t *link_y,
+                 uint64_t *n_dropped);
+int rk_st_or_words(rk_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n_words);
+/* centers and super-bucket sort keys of m fragments given in processing order */
+int rk_st_keys(rk_ctx *ctx, uint64_t m, uint64_t seqx_len, uint64_t seqy_len, const uint32_t *xs_r, const uint32_t *ys_r,
+               const uint32_t *len_r, const uint8_t *flags_r, const uint32_t *link_x, const uint32_t *link_y, uint32_t *cx,
+               uint32_t *cy, uint32_t *kx, uint32_t *ky);
+/* one axis pass (K3) over m fragments stably sorted by skey: sid = global processing rank, sc = center, slen = length,
+ * sxm = NULL for the X pass, else 1 where the fragment already has an X owner (Y pass).  owner[i] = global rank of
+ * the matched entry's fragment or RK_NONE.  seq_len = loaded length of this axis. */
+int rk_st_match(rk_ctx *ctx, uint64_t m, const uint32_t *skey, const uint32_t *sid, const uint32_t *sc, const uint32_t *slen,
+                const uint8_t *sxm, uint64_t seq_len, double len_ratio, double pos_ratio, uint32_t *owner);
+/* K4 on the all-gathered parent array (m_total global ranks): group ids of ranks [lo, lo+cnt).  Synchronises. */
+int rk_st_forest(rk_ctx *ctx, const uint32_t *parent, uint64_t m_total, uint64_t lo, uint64_t cnt, uint32_t *gid_out,
+                 uint64_t *n_groups);
+int rk_st_hkey(rk_ctx *ctx, const uint32_t *k0_r, const uint32_t *ys_r, uint64_t m, uint32_t *h);
+/* K5b/c over m fragments stably sorted by group id (processing order inside a group).  Synchronises. */
+int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *sh, const uint32_t *sfidx, const float *sident,
+                int do_sort, uint32_t *out_order, uint32_t *out_gid, uint8_t *out_repval, float *out_identity);
+
 const char *rk_version(void);
 
 #ifdef __cplusplus

@@ -58,6 +58,7 @@ def lib():
         L.rko_write_input_csv.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
         L.rko_write_input_csv.restype = C.c_int
         L.rko_free.argtypes = [C.c_void_p]
+        L.rko_std_sort_by_key.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -149,6 +150,14 @@ def write_input_csv(path: str, records: np.ndarray, lx_header: int, ly_header: i
     rec = np.ascontiguousarray(records)
     if lib().rko_write_input_csv(path.encode(), rec.ctypes.data, rec.shape[0], lx_header, ly_header):
         raise OSError(f"cannot write {path}")
+
+
+def std_sort_by_key(idx: np.ndarray, h: np.ndarray) -> np.ndarray:
+    """libstdc++ std::sort order of idx under comp(a, b) = h[a] < h[b]."""
+    out = np.ascontiguousarray(idx, dtype=np.uint32).copy()
+    hh = np.ascontiguousarray(h, dtype=np.uint64)
+    lib().rko_std_sort_by_key(out.ctypes.data, out.shape[0], hh.ctypes.data)
+    return out
 
 
 def have_ref() -> bool:

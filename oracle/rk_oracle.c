@@ -345,6 +345,12 @@ static void std_sort(uint32_t *first, uint32_t *last, const cmp_t *cm) {
   } else insertion_sort(first, last, cm);
 }
 
+/* std::sort of ranks by h[rank] (exported for tests that re-state single stages) */
+void rko_std_sort_by_key(uint32_t *idx, uint64_t n, const uint64_t *h) {
+  cmp_t cm = {h};
+  std_sort(idx, idx + n, &cm);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 void rko_result_free(rko_result *r) {
   free(r->rank_fidx); free(r->xowner); free(r->yowner); free(r->parent); free(r->gid); free(r->h);

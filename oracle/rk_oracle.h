@@ -73,6 +73,9 @@ int rko_write_output(const char *path, const char *header, const rko_frag *recs,
 /* Input-CSV writer for generated workloads (tooling, no reference counterpart). */
 int rko_write_input_csv(const char *path, const rko_frag *recs, uint64_t n, uint64_t lx_header, uint64_t ly_header);
 
+/* libstdc++ std::sort order of idx[0..n) under comp(a,b) = h[a] < h[b] (sort_groups, commonFunctions.cpp:158) */
+void rko_std_sort_by_key(uint32_t *idx, uint64_t n, const uint64_t *h);
+
 void rko_free(void *p);
 
 #ifdef __cplusplus

@@ -85,6 +85,11 @@ struct rk_ctx {
   cudaEvent_t ev[RK_NSTAGES + 2];
   Profiler prof;
 
+  // multi-GPU stage calls (rk_st_*): own counters and a grow-only scratch area
+  Counters *st_cnt = nullptr;
+  void *st_scratch = nullptr;
+  u64 st_scratch_bytes = 0;
+
   bool loaded = false;
   u64 n = 0;
   u32 m = 0;
@@ -185,6 +190,18 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   c->out_repval = take(n1);
   c->out_identity = (float *)take(n1 * 4);
   return off;
+}
+
+Geometry make_geometry(u64 seqx_len, u64 seqy_len) {
+  Geometry g{};
+  g.lx = seqx_len;
+  g.ly = seqy_len;
+  g.vsize = (u32)(1 + seqx_len / XBUCKET);  // FragmentsDatabase.cpp:84
+  g.mx = (u32)(seqx_len / DIVISOR);         // SequenceOcupationList.cpp:4
+  g.my = (u32)(seqy_len / DIVISOR);
+  g.nbx = g.mx + 2;
+  g.nby = g.my + 2;
+  return g;
 }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
@@ -335,6 +352,7 @@ rk_ctx *rk_create(int device) {
   }
   c->own_stream = true;
   for (auto &ev : c->ev) cudaEventCreate(&ev);
+  if (cudaMalloc((void **)&c->st_cnt, sizeof(Counters)) != cudaSuccess) c->st_cnt = nullptr;
   return c;
 }
 
@@ -343,6 +361,8 @@ void rk_destroy(rk_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->arena) cudaFree(c->arena);
+  if (c->st_cnt) cudaFree(c->st_cnt);
+  if (c->st_scratch) cudaFree(c->st_scratch);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -381,14 +401,7 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   }
   if (on_device && ((uintptr_t)frags & 15)) return fail(ctx, RK_ERR_ARG, "device record pointer must be 16-byte aligned");
 
-  Geometry g{};
-  g.lx = seqx_len;
-  g.ly = seqy_len;
-  g.vsize = (u32)(1 + seqx_len / XBUCKET);  // FragmentsDatabase.cpp:84
-  g.mx = (u32)(seqx_len / DIVISOR);         // SequenceOcupationList.cpp:4
-  g.my = (u32)(seqy_len / DIVISOR);
-  g.nbx = g.mx + 2;
-  g.nby = g.my + 2;
+  const Geometry g = make_geometry(seqx_len, seqy_len);
   const u64 lxw = (2ull * g.nbx + 31) / 32 + 1, lyw = (2ull * g.nby + 31) / 32 + 1;
 
   // (re)carve the workspace
@@ -610,6 +623,142 @@ int rk_sort_pairs(rk_ctx *ctx, const uint32_t *keys_in, const uint32_t *values_i
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   return RK_OK;
+}
+
+// ---- multi-GPU stage entry points: the same kernels on caller-owned device arrays ("direct" layout) ----------
+// All pointers are device pointers.  Work is queued on the context's stream (set it to the caller's stream with
+// rk_set_stream); only the calls that return a host value synchronise.
+
+static int st_scratch(rk_ctx *ctx, u64 bytes, void **out) {
+  if (bytes > ctx->st_scratch_bytes) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->st_scratch) cudaFree(ctx->st_scratch);
+    ctx->st_scratch = nullptr;
+    ctx->st_scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->st_scratch, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, RK_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    ctx->st_scratch_bytes = bytes;
+  }
+  *out = ctx->st_scratch;
+  return RK_OK;
+}
+
+static int st_check_errors(rk_ctx *ctx, bool range_errors) {
+  CK(cudaMemcpyAsync(ctx->h_cnt, ctx->st_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  const u32 e = ctx->h_cnt->err;
+  if (e) {
+    cudaMemsetAsync(&ctx->st_cnt->err, 0, sizeof(u32), ctx->stream);
+    return fail(ctx, (range_errors && !(e & (ERR_WORKLIST | ERR_SPIN))) ? RK_ERR_RANGE : RK_ERR_INTERNAL, "%s", err_bits_text(e));
+  }
+  return RK_OK;
+}
+
+uint64_t rk_st_link_words(uint64_t seq_len) { return (2ull * (seq_len / DIVISOR + 2) + 31) / 32 + 1; }
+
+int rk_st_decode(rk_ctx *ctx, const void *aos, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, uint32_t *xs, uint32_t *ys,
+                 uint32_t *len, uint8_t *flags, float *identity, uint32_t *key0, uint32_t *link_x, uint32_t *link_y,
+                 uint64_t *n_dropped) {
+  if (!ctx || !ctx->st_cnt || (n && !aos)) return RK_ERR_ARG;
+  if ((uintptr_t)aos & 15) return fail(ctx, RK_ERR_ARG, "device record pointer must be 16-byte aligned");
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  const Geometry g = make_geometry(seqx_len, seqy_len);
+  CK(cudaMemsetAsync(ctx->st_cnt, 0, sizeof(Counters), ctx->stream));
+  CK(cudaMemsetAsync(link_x, 0, rk_st_link_words(seqx_len) * 4, ctx->stream));
+  CK(cudaMemsetAsync(link_y, 0, rk_st_link_words(seqy_len) * 4, ctx->stream));
+  launch_decode((const u8 *)aos, n, g, xs, ys, len, flags, identity, key0, link_x, link_y, &ctx->st_cnt->n_dropped,
+                &ctx->st_cnt->err, ctx->stream);
+  const int rc = st_check_errors(ctx, true);
+  if (rc != RK_OK) return rc;
+  if (n_dropped) *n_dropped = ctx->h_cnt->n_dropped;
+  return RK_OK;
+}
+
+int rk_st_or_words(rk_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n_words) {
+  if (!ctx) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  launch_or_words(dst, src, n_words, ctx->stream);
+  return RK_OK;
+}
+
+int rk_st_keys(rk_ctx *ctx, uint64_t m, uint64_t seqx_len, uint64_t seqy_len, const uint32_t *xs_r, const uint32_t *ys_r,
+               const uint32_t *len_r, const uint8_t *flags_r, const uint32_t *link_x, const uint32_t *link_y, uint32_t *cx,
+               uint32_t *cy, uint32_t *kx, uint32_t *ky) {
+  if (!ctx) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  launch_keys_direct((u32)m, make_geometry(seqx_len, seqy_len), xs_r, ys_r, len_r, flags_r, link_x, link_y, cx, cy, kx, ky,
+                     ctx->stream);
+  return RK_OK;
+}
+
+int rk_st_match(rk_ctx *ctx, uint64_t m, const uint32_t *skey, const uint32_t *sid, const uint32_t *sc, const uint32_t *slen,
+                const uint8_t *sxm, uint64_t seq_len, double len_ratio, double pos_ratio, uint32_t *owner) {
+  if (!ctx || !ctx->st_cnt) return RK_ERR_ARG;
+  if (!(len_ratio > 0) || !(pos_ratio > 0)) return fail(ctx, RK_ERR_ARG, "ratios must be greater than zero");
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  const u64 m1 = m ? m : 1;
+  const u32 cap = (u32)(m1 / 32 + 2);
+  void *scr = nullptr;
+  const int rc = st_scratch(ctx, (3 * m1 + cap) * 4 + 1024, &scr);
+  if (rc != RK_OK) return rc;
+  MatchArgs a{};
+  a.skey = skey, a.srank = sid, a.m = (u32)m, a.max_index = (u32)(seq_len / DIVISOR);
+  a.len_ratio = len_ratio, a.pos_ratio = pos_ratio, a.is_y = sxm ? 1 : 0;
+  a.ent_rank = (u32 *)scr, a.ent_c = a.ent_rank + m1, a.ent_len = a.ent_c + m1, a.worklist = a.ent_len + m1;
+  a.work_cap = cap, a.work_count = ctx->st_cnt->work_x, a.err = &ctx->st_cnt->err;
+  a.direct = 1, a.sc = sc, a.slen = slen, a.sxm = sxm, a.owner = owner;
+  launch_match(a, ctx->stream);
+  return RK_OK;
+}
+
+int rk_st_forest(rk_ctx *ctx, const uint32_t *parent, uint64_t m_total, uint64_t lo, uint64_t cnt, uint32_t *gid_out,
+                 uint64_t *n_groups) {
+  if (!ctx || !ctx->st_cnt) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  void *scr = nullptr;
+  const int rc = st_scratch(ctx, forest_work_bytes((u32)(m_total ? m_total : 1)), &scr);
+  if (rc != RK_OK) return rc;
+  launch_forest(parent, (u32)m_total, gid_out, &ctx->st_cnt->n_groups, scr, ctx->stream, (u32)lo, (u32)cnt);
+  const int rc2 = st_check_errors(ctx, false);
+  if (rc2 != RK_OK) return rc2;
+  if (n_groups) *n_groups = ctx->h_cnt->n_groups;
+  return RK_OK;
+}
+
+int rk_st_hkey(rk_ctx *ctx, const uint32_t *k0_r, const uint32_t *ys_r, uint64_t m, uint32_t *h) {
+  if (!ctx) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  launch_hkey(k0_r, ys_r, (u32)m, h, ctx->stream);
+  return RK_OK;
+}
+
+int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *sh, const uint32_t *sfidx, const float *sident,
+                int do_sort, uint32_t *out_order, uint32_t *out_gid, uint8_t *out_repval, float *out_identity) {
+  if (!ctx || !ctx->st_cnt) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  const u64 m1 = m ? m : 1;
+  const u32 cap = (u32)(m1 / 32 + 2);
+  void *scr = nullptr;
+  const int rc = st_scratch(ctx, m1 * 8 + (u64)cap * 4 + 1024, &scr);
+  if (rc != RK_OK) return rc;
+  OrderArgs oa{};
+  oa.sgid = sgid, oa.srank = nullptr, oa.h = sh, oa.fidx_r = sfidx, oa.identity_f = nullptr, oa.identity_r = sident;
+  oa.packed = (u64 *)scr, oa.m = (u32)m, oa.do_sort = do_sort;
+  oa.worklist = (u32 *)((u8 *)scr + m1 * 8), oa.work_count = ctx->st_cnt->work_g, oa.work_cap = cap;
+  oa.out_order = out_order, oa.out_gid = out_gid, oa.out_repval = out_repval, oa.out_identity = out_identity;
+  oa.err = &ctx->st_cnt->err;
+  launch_order(oa, ctx->stream);
+  return st_check_errors(ctx, false);
 }
 
 }  // extern "C"

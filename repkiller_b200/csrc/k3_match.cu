@@ -68,6 +68,40 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *
   return 1;
 }
 
+// multi-GPU stage: the fragments are already in processing order on this rank; the link maps are the OR over ranks
+__global__ void __launch_bounds__(256)
+    k_keys_direct(u32 m, Geometry g, const u32 *__restrict__ xs_r, const u32 *__restrict__ ys_r, const u32 *__restrict__ len_r,
+                  const u8 *__restrict__ flags_r, const u32 *__restrict__ link_x, const u32 *__restrict__ link_y,
+                  u32 *__restrict__ cx, u32 *__restrict__ cy, u32 *__restrict__ kx, u32 *__restrict__ ky) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const u32 l = len_r[i];
+  const u32 sc = flags_r[i] & FL_REVERSE;
+  const u32 x = xs_r[i] + l / 2, y = ys_r[i] + l / 2;
+  cx[i] = x;
+  cy[i] = y;
+  kx[i] = run_start(link_x, sc * g.nbx + x / DIVISOR);
+  ky[i] = run_start(link_y, sc * g.nby + y / DIVISOR);
+}
+
+int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
+                       const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st) {
+  if (m == 0) return 0;
+  KScope ks(KID_KEYS, st);
+  k_keys_direct<<<(m + 255) / 256, 256, 0, st>>>(m, g, xs_r, ys_r, len_r, flags_r, link_x, link_y, cx, cy, kx, ky);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256) k_or_words(u32 *__restrict__ dst, const u32 *__restrict__ src, u64 n) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] |= src[i];
+}
+int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_or_words<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, src, n);
+  return 1;
+}
+
 // SequenceOcupationList::deviation (SequenceOcupationList.cpp:20-31).  t_len = length*len_ratio and
 // t_pos = length*pos_ratio are the query's (the relation is asymmetric).
 __device__ __forceinline__ double deviation(u32 ec, u32 el, u32 c, u32 len, double t_len, double t_pos) {
@@ -124,6 +158,29 @@ __device__ __forceinline__ int quotient_vs_one(u32 d, const Thresh &th) {
   return q > 1.0 ? 0 : (q == 1.0 ? 2 : 1);
 }
 
+// Two data layouts.  Indirect (single GPU): srank[i] is the processing rank, centers/lengths are gathered from the
+// rank-ordered arrays and the owner is stored at parent[rank].  Direct (multi-GPU stages): sc/slen/sxm are already
+// in sorted order, srank[i] is the id to report (global rank) and the owner is stored at owner[i].
+__device__ __forceinline__ void load_elem(const MatchArgs &a, u32 pos, u32 &r, u32 &c, u32 &len, bool &xm) {
+  r = a.srank[pos];
+  if (a.direct) {
+    c = a.sc[pos];
+    len = a.slen[pos];
+    xm = a.sxm != nullptr && a.sxm[pos] != 0;
+  } else {
+    c = a.c_r[r];
+    len = a.len_r[r];
+    xm = a.is_y && a.parent[r] != RK_NONE32;  // X-matched: Y-insert without a query (commonFunctions.cpp:59)
+  }
+}
+__device__ __forceinline__ void store_owner(const MatchArgs &a, u32 pos, u32 r, u32 v) {
+  if (a.direct) a.owner[pos] = v;
+  else a.parent[r] = v;
+}
+// "no match" is stored by the X pass only: in the Y pass parent[] already holds the X result (indirect), and the
+// direct owner[] array is pre-filled with NONE by the launcher.
+__device__ __forceinline__ bool stores_none(const MatchArgs &a) { return !a.is_y && !a.direct; }
+
 constexpr int MT_THREADS = 256;
 constexpr int MT_TILE = MT_THREADS + 32;  // heads live in the first 256 positions, their segments end before 288
 
@@ -140,14 +197,15 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
   for (u32 e = tid; e < (u32)MT_TILE; e += MT_THREADS) {
     s_nz[e] = 0;
     if (e < count) {
-      const u32 r = a.srank[bs + e];
-      const u32 c = a.c_r[r];
+      u32 r, c, len;
+      bool xm;
+      load_elem(a, bs + e, r, c, len, xm);
       s_key[e] = a.skey[bs + e];
       s_rank[e] = r;
       s_c[e] = c;
-      s_len[e] = a.len_r[r];
+      s_len[e] = len;
       s_bkt[e] = c / DIVISOR;
-      s_xm[e] = (a.is_y && a.parent[r] != RK_NONE32) ? 1 : 0;  // X-matched: Y-insert without a query (:59)
+      s_xm[e] = xm ? 1 : 0;
     }
   }
   if (tid == 0) s_prev_key = bs ? a.skey[bs - 1] : 0;
@@ -187,10 +245,10 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
       const u32 h = e - pos;
       if (cand) {
         if (pos < 32) atomicOr(&s_nz[h], 1u << pos);
-      } else if (!a.is_y && !(h == 0 && foreign0)) {
+      } else if (stores_none(a) && !(h == 0 && foreign0)) {
         // no candidate at all: an X entry for sure.  (Continuations of the previous tile's segment are that
         // CTA's; elements whose head lies beyond position 255 are written again, identically, by the next CTA.)
-        a.parent[s_rank[e]] = RK_NONE32;
+        store_owner(a, bs + e, s_rank[e], RK_NONE32);
       }
     }
   }
@@ -217,9 +275,9 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
     const u32 hit = s_cand[e] & inserted;
     if (!hit) {
       inserted |= 1u << p;
-      if (!a.is_y) a.parent[s_rank[e]] = RK_NONE32;
+      if (stores_none(a)) store_owner(a, bs + e, s_rank[e], RK_NONE32);
     } else if ((hit & (hit - 1)) == 0) {
-      a.parent[s_rank[e]] = s_rank[tid + __ffs(hit) - 1];
+      store_owner(a, bs + e, s_rank[e], s_rank[tid + __ffs(hit) - 1]);
     } else {
       // several inserted candidates: greatest score, own bucket before neighbour, newest first (:40 strict >)
       const u32 c = s_c[e], len = s_len[e], b = s_bkt[e];
@@ -239,7 +297,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
           best_own = own;
         }
       }
-      a.parent[s_rank[e]] = s_rank[tid + best];
+      store_owner(a, bs + e, s_rank[e], s_rank[tid + best]);
     }
   }
 }
@@ -269,10 +327,7 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
       u32 r = 0, c = 0, len = 0;
       bool xm = false;
       if (valid) {
-        r = a.srank[q];
-        c = a.c_r[r];
-        len = a.len_r[r];
-        xm = a.is_y && a.parent[r] != RK_NONE32;
+        load_elem(a, q, r, c, len, xm);
       }
       const bool needq = valid && !xm;
       const u32 b = c / DIVISOR;
@@ -329,8 +384,8 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
         pending &= ~((2u << L) - 1u);  // lanes <= L are final
       }
       if (needq) {
-        if (best != RK_NONE32) a.parent[r] = best;
-        else if (!a.is_y) a.parent[r] = RK_NONE32;
+        if (best != RK_NONE32) store_owner(a, q, r, best);
+        else if (!a.is_y || a.direct) store_owner(a, q, r, RK_NONE32);  // also clears a tier-1 partial result
       }
       __syncwarp();  // entry stores of this chunk are read by every lane in the next one
     }
@@ -340,6 +395,7 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
 int launch_match(const MatchArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
   cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
+  if (a.direct) cudaMemsetAsync(a.owner, 0xFF, (size_t)a.m * sizeof(u32), st);
   {
     KScope ks(KID_MATCH_SMALL, st);
     k_match_small<<<(a.m + MT_THREADS - 1) / MT_THREADS, MT_THREADS, 0, st>>>(a);

@@ -18,22 +18,26 @@ struct LoadIsRoot {
 };
 
 __global__ void __launch_bounds__(256) k_chase(const u32 *__restrict__ parent, const u32 *__restrict__ gid_of_root, u32 m,
-                                               u32 *__restrict__ gid_rank, const u32 *__restrict__ total, u32 *n_groups) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *n_groups = *total;
-  if (i >= m) return;
+                                               u32 *__restrict__ gid_rank, const u32 *__restrict__ total, u32 *n_groups,
+                                               u32 lo) {
+  // ranks lo .. lo+m-1 are resolved (lo = 0, m = all on a single GPU; a rank's slice in the multi-GPU stages)
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) *n_groups = *total;
+  if (t >= m) return;
+  const u32 i = lo + t;
   u32 r = i;
   for (;;) {
     const u32 p = parent[r];
     if (p == RK_NONE32) break;
     r = p;  // p < r always: terminates
   }
-  gid_rank[i] = gid_of_root[r];
+  gid_rank[t] = gid_of_root[r];
 }
 
 u64 forest_work_bytes(u32 m) { return ((u64)m + scan_work_words(m)) * 4 + 256; }
 
-int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st) {
+int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st, u32 lo, u32 cnt) {
+  if (cnt == 0xFFFFFFFFu) cnt = m;
   if (m == 0) {
     cudaMemsetAsync(n_groups, 0, sizeof(u32), st);
     return 0;
@@ -43,7 +47,7 @@ int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *
   int launches = exclusive_scan_u32(LoadIsRoot{parent}, gid_of_root, m, bsum, st);
   const u32 nb = (u32)(((u64)m + SCAN_CHUNK - 1) / SCAN_CHUNK);
   KScope ks(KID_CHASE, st);
-  k_chase<<<(m + 255) / 256, 256, 0, st>>>(parent, gid_of_root, m, gid_rank, bsum + nb, n_groups);
+  k_chase<<<(cnt + 255) / 256 + (cnt == 0), 256, 0, st>>>(parent, gid_of_root, cnt, gid_rank, bsum + nb, n_groups, lo);
   return launches + 1;
 }
 

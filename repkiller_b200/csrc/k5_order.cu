@@ -227,7 +227,7 @@ constexpr int GS_SMEM_ELEMS = 6144;  // larger groups up to this size are sorted
 __global__ void __launch_bounds__(256) k_pack(OrderArgs a) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.m) return;
-  const u32 r = a.srank[j];
+  const u32 r = a.srank ? a.srank[j] : j;  // direct layout: h/fidx/identity are already in this order
   a.packed[j] = ((u64)a.h[r] << 32) | r;
 }
 
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) k_finalize(OrderArgs a) {
   a.out_order[j] = f;
   a.out_gid[j] = g;
   a.out_repval[j] = (head && last) ? 0 : (head ? 1 : 2);  // commonFunctions.cpp:106-115
-  a.out_identity[j] = a.identity_f[f];
+  a.out_identity[j] = a.identity_r ? a.identity_r[r] : a.identity_f[f];
 }
 
 int launch_order(const OrderArgs &a, cudaStream_t st) {

@@ -95,6 +95,10 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *
                 const u32 *link_x, const u32 *link_y, u32 *cx_r, u32 *cy_r, u32 *len_r, u32 *ys_r, u32 *kx,
                 u32 *ky, cudaStream_t st);
 
+int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
+                       const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
+int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st);
+
 // K3: one axis pass of generate_fragment_groups.  is_y: fragments with parent != NONE insert unconditionally.
 struct MatchArgs {
   const u32 *skey;   // sorted super-bucket keys
@@ -111,12 +115,19 @@ struct MatchArgs {
   u32 work_cap;
   u32 *ent_rank, *ent_c, *ent_len;  // scratch of m entries each for long segments
   u32 *err;
+  // direct layout (multi-GPU stages): inputs already in sorted order, result per sorted position
+  int direct;
+  const u32 *sc, *slen;
+  const u8 *sxm;
+  u32 *owner;
 };
 int launch_match(const MatchArgs &a, cudaStream_t st);
 
 // K4: roots, group ids.
 u64 forest_work_bytes(u32 m);
-int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st);
+// lo/cnt: resolve only ranks [lo, lo+cnt) of a parent array of m entries (multi-GPU: the rank's own slice)
+int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st, u32 lo = 0,
+                  u32 cnt = 0xFFFFFFFFu);
 
 // K5a: h = |yStart - yStart(last fragment of the same xStart/10 bucket)| per rank.
 int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st);
@@ -131,6 +142,7 @@ struct OrderArgs {
   const u32 *h;       // by rank
   const u32 *fidx_r;  // file index by rank
   const float *identity_f;  // by file index
+  const float *identity_r;  // direct layout: by the same index as h/fidx_r (srank == nullptr)
   u64 *packed;        // scratch m
   u32 m;
   int do_sort;
