@@ -7,8 +7,9 @@ K5 diag/sort/labels) for len_ratio = pos_ratio = 0.05.
   value : records already resident in HBM, result left in HBM; CUDA events on the launching stream.
   e2e   : the same step through the C ABI with HOST buffers: pinned records -> H2D -> kernels -> D2H of
           order/gid/repval/identity into pinned host arrays.
-N > 1: one process per GPU (torchrun), each rank groups its own independent sequence-pair comparison of the
-same shape (weak scaling, no data-path collective; SURVEY.md §8c: one reference run per (seqX, seqY) pair).
+N > 1: one process per GPU (torchrun).  Default: ONE comparison of N x the per-GPU size, range-partitioned over
+the GPUs with three all-to-all redistributions and a parent all-gather over NCCL (repkiller_b200/dist.py; weak
+scaling: per-GPU fragments fixed).  --multi independent: one independent sequence-pair comparison per GPU.
 `--impl reference` times the reference's own CPU code (oracle/_ref, built from /root/reference) on host cores.
 """
 from __future__ import annotations
@@ -29,6 +30,8 @@ sys.path.insert(0, ROOT)
 METRIC = "fragments grouped/sec (device-timed)"
 UNIT = "fragments/s"
 CPU_SAMPLE_N = 1_000_000
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {}
 
 
 def parse():
@@ -40,6 +43,8 @@ def parse():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--n", type=int, default=0, help="override the fragment count (same shape, scaled); testing only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="partitioned", choices=["partitioned", "independent"],
+                    help="N > 1: one comparison range-partitioned over the GPUs (default) or one independent comparison per GPU")
     ap.add_argument("--profile-kernels", type=int, default=1, help="CUDA-event pairs around every kernel launch in the timed region")
     return ap.parse_args()
 
@@ -155,23 +160,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(n, m, bits_rank, bits_x, bits_y, bits_g):
-    """Algorithmic HBM bytes per step and kernel: what the kernel must read and write once."""
-    passes = lambda b: (max(b, 1) + 7) // 8
-    sorted_elems = n * passes(bits_rank) + m * (passes(bits_x) + passes(bits_y) + passes(bits_g))
-    return {
-        "k_decode": n * (109 + 21),
-        "k_radix_hist": 4 * sorted_elems,
-        "k_radix_scatter": 16 * sorted_elems,
-        "k_keys": m * (4 + 13 + 24),
-        "k_match_small": m * (20 + 24),
-        "k_chase": m * 12,
-        "k_scan": m * 12,
-        "k_hkey": m * 16,
-        "k_pack": m * 16,
-        "k_groupsort_small": m * 4,
-        "k_finalize": m * (8 + 4 + 4 + 4 + 13),
-    }
+# Algorithmic HBM bytes per unit a kernel processes: what it must read and write once.
+ALG_BYTES_PER_UNIT = {
+    "k_decode": 109 + 21,        # record in; xs, ys, len, key0 u32 + flags u8 + identity f32 out
+    "k_radix_hist": 4,           # one read of the keys for all digit histograms of a sort
+    "k_radix_scatter": 16,       # (key, value) in, (key, value) out, per pass
+    "k_keys": 4 + 13 + 24,       # file index, gather of xs/ys/len/flags, rank-order SoA + two keys out
+    "k_match_small": 22,         # key, rank, center, length (+ X flag) in, owner out
+    "k_chase": 12,
+    "k_scan": 12,
+    "k_hkey": 16,
+    "k_pack": 16,
+    "k_groupsort_small": 4,
+    "k_finalize": 8 + 4 + 4 + 4 + 13,
+}
 
 
 def ours(args):
@@ -179,6 +181,7 @@ def ours(args):
     import torch
     import torch.distributed as dist
     from repkiller_b200 import capi, gen
+    from repkiller_b200.dist import Comm, CudaStages, group_partitioned
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,14 +189,26 @@ def ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=device)
+    partitioned = world > 1 and args.multi == "partitioned"
 
-    w = workload(args, rank)
-    rec = gen.generate(w)
-    n = w.n
+    base = workload(args)
+    if partitioned:
+        # ONE comparison of world x the per-GPU size (same density), range-partitioned over the GPUs
+        w = gen.scaled(base, base.n * world)
+        lo, hi = w.n * rank // world, w.n * (rank + 1) // world
+        lo, hi = lo - lo % 16, (hi - hi % 16 if rank + 1 < world else hi)   # slices start on a 16-record boundary
+        n_total = w.n
+    else:
+        w = workload(args, rank)   # rank r: its own sequence pair of the same shape
+        lo, hi = 0, w.n
+        n_total = w.n * world
+    n = hi - lo
+    rec = gen.generate(w, start=lo, count=n)
     host = torch.from_numpy(rec.view(np.uint8).reshape(-1)).pin_memory()
-    dev = host.cuda()
+    dev = host.to(device)
     lx1, ly1 = w.lx + 1, w.ly + 1
     peaks = {}
     try:
@@ -205,6 +220,9 @@ def ours(args):
     stream = torch.cuda.Stream()
     ctx = capi.Context(local)
     ctx.set_stream(stream.cuda_stream)
+    stages, comm = CudaStages(ctx, device), Comm()
+    dev2 = torch.empty_like(dev) if partitioned else None
+    pinned_out = {}
 
     def barrier():
         if world > 1:
@@ -212,10 +230,22 @@ def ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        if partitioned:
+            return group_partitioned(stages, comm, dev, n, lo, lx1, ly1, w.len_ratio, w.pos_ratio)
         st = ctx.load(dev.data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=False)
 
     def step_e2e():
+        if partitioned:
+            dev2.copy_(host, non_blocking=True)
+            r = group_partitioned(stages, comm, dev2, n, lo, lx1, ly1, w.len_ratio, w.pos_ratio)
+            for name in ("order", "gid", "repval", "identity"):
+                t = getattr(r, name)
+                if name not in pinned_out or pinned_out[name].numel() < t.numel():
+                    pinned_out[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype).pin_memory()
+                pinned_out[name][: t.numel()].copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return r
         st = ctx.load(host.data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=True)
 
@@ -231,69 +261,77 @@ def ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, last
 
-    for _ in range(args.warmup):
-        step_resident()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_resident()
     ctx.profile_enable(bool(args.profile_kernels))
     ctx.profile_read(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, (st, res) = timed(step_resident, args.steps)
+    ms_total, last = timed(step_resident, args.steps)
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    ms_e2e, (st_e, res_e) = timed(step_e2e, args.steps)
+    with torch.cuda.stream(stream):
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+    ms_e2e, last_e = timed(step_e2e, args.steps)
 
-    n_total = n * world
     value = n_total * args.steps / (ms_total / 1e3)
     e2e_value = n_total * args.steps / (ms_e2e / 1e3)
-    m = res.n_kept
-    ceil_log2 = lambda x: max(1, (max(int(x), 1) - 1).bit_length())
-    bits = (ceil_log2(st.vsize), ceil_log2(2 * (lx1 // 100 + 2)), ceil_log2(2 * (ly1 // 100 + 2)), ceil_log2(m))
-    alg = algorithmic_bytes(n, m, *bits)
+    if partitioned:
+        kept, groups, lines = last.n_kept, last.n_groups, last.n_local_lines
+        stage_ms = {}
+        exchanged = last.bytes_exchanged // max(1, args.warmup + args.steps)
+    else:
+        st, res = last
+        kept, groups, lines = res.n_kept, res.n_groups, res.n_kept
+        stage_ms = {k: round(v, 4) for k, v in {**st.ms_stage, **{k2: v2 for k2, v2 in res.ms_stage.items() if v2}}.items() if v}
+        exchanged = 0
 
     line = None
     if rank == 0:
-        kernels = {}
-        for name, (launches, ms) in prof.items():
-            per_step_ms = ms / args.steps
-            b = alg.get(name)
-            kernels[name] = {"launches_per_step": launches / args.steps, "ms_per_step": round(per_step_ms, 4),
-                             "alg_gbs": round(b / per_step_ms / 1e6, 1) if b and per_step_ms > 0 else None}
-        top = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+        kernels, total_alg, total_ms = {}, 0.0, 0.0
+        for name, (launches, ms, units) in prof.items():
+            b = ALG_BYTES_PER_UNIT.get(name, 0) * units
+            total_alg += b
+            total_ms += ms
+            kernels[name] = {"launches_per_step": launches / args.steps, "ms_per_step": round(ms / args.steps, 4),
+                             "alg_gbs": round(b / ms / 1e6, 1) if b and ms > 0 else None}
         roofline = None
-        if top:
-            launches, ms = prof[top]
-            b = alg.get(top, 0)
-            achieved = b * args.steps / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        if prof:
+            top = max(prof.items(), key=lambda kv: kv[1][1])[0]
+            launches, ms, units = prof[top]
+            b = ALG_BYTES_PER_UNIT.get(top, 0) * units
+            achieved = b / (ms / 1e3) / 1e9 if ms > 0 else 0.0
             roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
-                        "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
-                        "alg_bytes_per_launch": round(b * args.steps / max(launches, 1)),
-                        "avg_launch_ms": round(ms / max(launches, 1), 5), "share_of_kernel_time": round(ms / max(sum(v[1] for v in prof.values()), 1e-9), 3)}
-        total_alg = sum(alg.values())
+                        "frac": round(achieved / peak_gbs, 4), "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
+                        "alg_bytes_per_launch": round(b / max(launches, 1)), "avg_launch_ms": round(ms / max(launches, 1), 5),
+                        "share_of_kernel_time": round(ms / max(total_ms, 1e-9), 3)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32+f64", "data": "synthetic",
-            "config": {"workload": workload_text(w), "per_gpu_fragments": n, "kept": int(m), "groups": int(res.n_groups),
-                       "l2": "inputs larger than L2 (1.09 GB of records per step vs 126 MB)" if n * 109 > 200e6 else "inputs smaller than L2 (reduced --n run)",
-                       "multi_gpu": "independent sequence pairs per rank, no data-path collective" if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(m * 13 + 40),
+            "config": {"workload": workload_text(w), "per_gpu_fragments": n, "kept": int(kept), "groups": int(groups),
+                       "l2": "inputs larger than L2 (1.09 GB of records per GPU and step vs 126 MB)" if n * 109 > 200e6 else "inputs smaller than L2 (reduced --n run)",
+                       "multi_gpu": ("one comparison range-partitioned over the GPUs: 3 all-to-all redistributions + parent all-gather over NCCL, "
+                                     f"{exchanged / 1e6:.0f} MB sent per GPU and step" if partitioned else
+                                     "independent sequence pairs per rank, no data-path collective") if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(lines * 13 + 40),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int((st.n_launches + res.n_launches) * args.steps),
+            "gpu_launches": int(sum(v[0] for v in prof.values())) if prof else None,
             "clocks": clocks,
             "roofline": roofline,
-            "pipeline_alg_bytes_per_fragment": round(total_alg / n, 1),
-            "pipeline_hbm_frac": round(total_alg * args.steps / (ms_total / 1e3) / 1e9 / peak_gbs, 4),
-            "stage_ms": {k: round(v, 4) for k, v in {**st.ms_stage, **{k2: v2 for k2, v2 in res.ms_stage.items() if v2}}.items() if v},
+            "pipeline_alg_bytes_per_fragment": round(total_alg / args.steps / n, 1),
+            "pipeline_hbm_frac": round(total_alg / (ms_total / 1e3) / 1e9 / peak_gbs, 4),
+            "stage_ms": stage_ms,
             "kernels": kernels,
         }
     if world > 1:

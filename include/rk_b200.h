@@ -132,6 +132,7 @@ typedef struct {
   const char *name;
   uint64_t launches;
   double ms_total;
+  uint64_t units; /* fragments (or sort elements, buckets) the launches processed in total */
 } rk_kernel_time;
 int rk_profile_enable(rk_ctx *ctx, int on);
 int rk_profile_read(rk_ctx *ctx, rk_kernel_time *out, int cap, int reset);

@@ -40,7 +40,7 @@ class _LoadStats(C.Structure):
 
 
 class _KernelTime(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("ms_total", C.c_double)]
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("ms_total", C.c_double), ("units", C.c_uint64)]
 
 
 class _Result(C.Structure):
@@ -182,10 +182,10 @@ class Context:
         self._check(self._L.rk_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True) -> dict:
-        """{kernel name: (launches, total ms)} accumulated since the last reset."""
+        """{kernel name: (launches, total ms, units processed)} accumulated since the last reset."""
         buf = (_KernelTime * 32)()
         k = self._L.rk_profile_read(self._h, buf, 32, int(reset))
-        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].ms_total)) for i in range(k)}
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].ms_total), int(buf[i].units)) for i in range(k)}
 
     def diagonal_func(self, vsize: int) -> np.ndarray:
         out = np.zeros(max(vsize - 1, 0), dtype=np.uint64)

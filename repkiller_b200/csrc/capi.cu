@@ -30,11 +30,12 @@ const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan
 // CUDA-event pair around every launch group; folded into per-kernel totals after each synchronisation
 struct Profiler {
   bool on = false;
-  struct Rec { int kid; cudaEvent_t a, b; };
+  struct Rec { int kid; cudaEvent_t a, b; u64 units; };
   std::vector<Rec> open_recs;
   std::vector<cudaEvent_t> pool;
   double ms[KID_COUNT] = {0};
   u64 launches[KID_COUNT] = {0};
+  u64 units[KID_COUNT] = {0};
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
     cudaEvent_t e;
@@ -44,7 +45,7 @@ struct Profiler {
   void fold() {  // call after the stream was synchronised
     for (auto &r : open_recs) {
       float t = 0.f;
-      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; launches[r.kid] += 1; }
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; launches[r.kid] += 1; units[r.kid] += r.units; }
       else cudaGetLastError();
       pool.push_back(r.a);
       pool.push_back(r.b);
@@ -225,9 +226,9 @@ const char *err_bits_text(u32 e) {
 }  // namespace
 
 namespace rk {
-void prof_begin(int kid, cudaStream_t st) {
+void prof_begin(int kid, cudaStream_t st, unsigned long long units) {
   if (!tl_prof) return;
-  Profiler::Rec r{kid, tl_prof->get(), tl_prof->get()};
+  Profiler::Rec r{kid, tl_prof->get(), tl_prof->get(), (u64)units};
   cudaEventRecord(r.a, st);
   tl_prof->open_recs.push_back(r);
 }
@@ -592,10 +593,11 @@ int rk_profile_read(rk_ctx *ctx, rk_kernel_time *out, int cap, int reset) {
     out[k].name = kKernelNames[i];
     out[k].launches = ctx->prof.launches[i];
     out[k].ms_total = ctx->prof.ms[i];
+    out[k].units = ctx->prof.units[i];
     ++k;
   }
   if (reset) {
-    for (int i = 0; i < KID_COUNT; ++i) ctx->prof.ms[i] = 0, ctx->prof.launches[i] = 0;
+    for (int i = 0; i < KID_COUNT; ++i) ctx->prof.ms[i] = 0, ctx->prof.launches[i] = 0, ctx->prof.units[i] = 0;
   }
   return k;
 }

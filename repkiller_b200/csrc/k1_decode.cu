@@ -219,7 +219,7 @@ int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, 
   u64 grid = (u64)sms * 2;  // two CTAs (2 x 84 KB of staging) per SM, persistent over the tiles
   if (grid > full_tiles) grid = full_tiles ? full_tiles : 1;
   DecodeOut o{xs, ys, len, flags, identity, key0, link_x, link_y, n_dropped, err};
-  KScope ks(KID_DECODE, st);
+  KScope ks(KID_DECODE, st, n);
   k_decode<<<(unsigned)grid, DEC_THREADS, smem, st>>>(aos, n, g, o);
   return 1;
 }

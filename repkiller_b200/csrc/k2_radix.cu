@@ -348,7 +348,7 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   {
-    KScope ks(KID_RADIX_HIST, st);
+    KScope ks(KID_RADIX_HIST, st, n);
     u64 blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (blocks > (u64)sms * 8) blocks = (u64)sms * 8;
     k_onesweep_hist<<<(unsigned)blocks, 256, 0, st>>>(keys_in, n, passes, key_bits, ghist);
@@ -362,7 +362,7 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
     const bool to_out = ((passes - 1 - p) % 2) == 0;
     u32 *kdst = to_out ? keys_out : keys_tmp;
     u32 *vdst = to_out ? vals_out : vals_tmp;
-    KScope ks(KID_RADIX_SCATTER, st);
+    KScope ks(KID_RADIX_SCATTER, st, n);
     k_onesweep_pass<<<tiles, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask, ghist + p * RADIX,
                                                   state + (u64)p * tiles * RADIX, counters + p, err);
     ksrc = kdst;
@@ -392,12 +392,12 @@ int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32
     u32 *kdst = to_out ? keys_out : keys_tmp;
     u32 *vdst = to_out ? vals_out : vals_tmp;
     {
-      KScope ks(KID_RADIX_HIST, st);
+      KScope ks(KID_RADIX_HIST, st, n);
       k_radix_hist<<<tiles, RS_THREADS, 0, st>>>(ksrc, n, shift, mask, counts, tiles);
     }
     launches += 1 + exclusive_scan_u32(LoadU32{counts}, counts, (u64)tiles * RADIX, bsum, st);
     {
-      KScope ks(KID_RADIX_SCATTER, st);
+      KScope ks(KID_RADIX_SCATTER, st, n);
       k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask, counts, tiles);
     }
     launches += 1;

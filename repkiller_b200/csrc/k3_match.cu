@@ -63,7 +63,7 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *
                 const u32 *link_x, const u32 *link_y, u32 *cx_r, u32 *cy_r, u32 *len_r, u32 *ys_r, u32 *kx, u32 *ky,
                 cudaStream_t st) {
   if (m == 0) return 0;
-  KScope ks(KID_KEYS, st);
+  KScope ks(KID_KEYS, st, m);
   k_keys<<<(m + 255) / 256, 256, 0, st>>>(fidx_r, m, g, xs, ys, len, flags, link_x, link_y, cx_r, cy_r, len_r, ys_r, kx, ky);
   return 1;
 }
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256)
 int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
                        const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st) {
   if (m == 0) return 0;
-  KScope ks(KID_KEYS, st);
+  KScope ks(KID_KEYS, st, m);
   k_keys_direct<<<(m + 255) / 256, 256, 0, st>>>(m, g, xs_r, ys_r, len_r, flags_r, link_x, link_y, cx, cy, kx, ky);
   return 1;
 }
@@ -302,6 +302,16 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
   }
 }
 
+// ---- tier 2: one warp per segment of more than 32 fragments ------------------------------------------------------
+// 32 queries at a time are checked against the entry list (uniform loads; every lane its own query), then the
+// insertions inside the chunk are replayed in order with ballots.  Two exact reductions keep the work per query at
+// O(distinct entries) instead of O(segment):
+//  * the candidate test (deviation > 0) uses the integer thresholds of tier 1; the two divisions are only done for
+//    candidates, to rank them;
+//  * an entry with the same (center, length) as a newer entry can never win: its score is identical and the newer
+//    one is scanned first (`>` is strict, SequenceOcupationList.cpp:40).  Inserting therefore retires the older
+//    duplicate (tombstone: rank = NONE; the list is compacted, order preserved, when half of it is dead).  In a
+//    repeat family thousands of X-matched fragments Y-insert the same few (center, length) pairs.
 __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
   const u32 lane = threadIdx.x & 31;
   const u32 nseg = min(*a.work_count, a.work_cap);
@@ -320,34 +330,47 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
       end += __popc(bal);  // sorted keys: the matching lanes are a prefix
       if (bal != 0xFFFFFFFFu) break;
     }
-    u32 n_ent = 0;
+    u32 *const e_rank = a.ent_rank + start, *const e_c = a.ent_c + start, *const e_len = a.ent_len + start;
+    u32 n_ent = 0, n_dead = 0;
     for (u32 base = start; base < end; base += 32) {
       const u32 q = base + lane;
       const bool valid = q < end;
       u32 r = 0, c = 0, len = 0;
       bool xm = false;
-      if (valid) {
-        load_elem(a, q, r, c, len, xm);
-      }
-      const bool needq = valid && !xm;
+      if (valid) load_elem(a, q, r, c, len, xm);
+      const bool needq = valid && !xm && len != 0;  // length 0 never matches (every score is NaN or 0)
       const u32 b = c / DIVISOR;
       const u32 nbk = neighbour_bucket(c, a.max_index);
-      const double t_len = __dmul_rn((double)len, a.len_ratio);
-      const double t_pos = __dmul_rn((double)len, a.pos_ratio);
+      const Thresh tl = make_thresh(len, a.len_ratio), tp = make_thresh(len, a.pos_ratio);
       double best_sc = 0.0;
       u32 best = RK_NONE32;
       bool best_own = false;
+      // score of entry (ec, el) for this lane's query, 0 when it is not a candidate
+      auto score = [&](u32 ec, u32 el, bool &own) -> double {
+        const u32 bk = ec / DIVISOR;
+        own = bk == b;
+        if (!own && bk != nbk) return 0.0;
+        const u32 dl = len > el ? len - el : el - len;
+        const u32 dc = c > ec ? c - ec : ec - c;
+        if (dl > tl.rej || dc > tp.rej) return 0.0;
+        const int ql = quotient_vs_one(dl, tl);
+        if (ql == 0) return 0.0;
+        const int qp = quotient_vs_one(dc, tp);
+        if (qp == 0 || (ql == 2 && qp == 2)) return 0.0;
+        return deviation(ec, el, c, len, tl.t, tp.t);
+      };
       // phase A: entries inserted before this chunk, newest first (uniform loads)
-      for (u32 t = n_ent; t-- > 0;) {
-        const u32 e_c = a.ent_c[start + t], e_l = a.ent_len[start + t];
-        if (needq) {
-          const u32 bk = e_c / DIVISOR;
-          const bool own = bk == b;
-          if (own || bk == nbk) {
-            const double sc = deviation(e_c, e_l, c, len, t_len, t_pos);
+      if (__any_sync(0xFFFFFFFFu, needq)) {
+        for (u32 t = n_ent; t-- > 0;) {
+          const u32 er = e_rank[t];
+          if (er == RK_NONE32) continue;  // retired duplicate (uniform branch)
+          const u32 ec = e_c[t], el = e_len[t];
+          if (needq) {
+            bool own;
+            const double sc = score(ec, el, own);
             if (sc > best_sc || (sc == best_sc && best != RK_NONE32 && own && !best_own)) {
               best_sc = sc;
-              best = a.ent_rank[start + t];
+              best = er;
               best_own = own;
             }
           }
@@ -362,32 +385,66 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
         const u32 Lc = __shfl_sync(0xFFFFFFFFu, c, L);
         const u32 Ll = __shfl_sync(0xFFFFFFFFu, len, L);
         const u32 Lr = __shfl_sync(0xFFFFFFFFu, r, L);
+        // retire the live entry with the same (center, length), if any (at most one is live)
+        for (u32 t0 = 0; t0 < n_ent; t0 += 32) {
+          const u32 t = t0 + lane;
+          const bool dup = t < n_ent && e_c[t] == Lc && e_len[t] == Ll && e_rank[t] != RK_NONE32;
+          const u32 hit = __ballot_sync(0xFFFFFFFFu, dup);
+          if (hit) {
+            if (dup) e_rank[t] = RK_NONE32;
+            ++n_dead;
+            break;
+          }
+        }
         if ((int)lane == L) {
-          a.ent_rank[start + n_ent] = r;
-          a.ent_c[start + n_ent] = c;
-          a.ent_len[start + n_ent] = len;
+          e_rank[n_ent] = r;
+          e_c[n_ent] = c;
+          e_len[n_ent] = len;
         }
         ++n_ent;
         if ((int)lane > L && needq) {
           // the new entry is the newest: it is scanned before every older entry of its bucket class
-          const u32 bk = Lc / DIVISOR;
-          const bool own = bk == b;
-          if (own || bk == nbk) {
-            const double sc = deviation(Lc, Ll, c, len, t_len, t_pos);
-            if (sc > best_sc || (sc == best_sc && best != RK_NONE32 && (own || !best_own))) {
-              best_sc = sc;
-              best = Lr;
-              best_own = own;
-            }
+          bool own;
+          const double sc = score(Lc, Ll, own);
+          if (sc > best_sc || (sc == best_sc && sc > 0.0 && (own || !best_own))) {
+            best_sc = sc;
+            best = Lr;
+            best_own = own;
           }
         }
         pending &= ~((2u << L) - 1u);  // lanes <= L are final
+        __syncwarp();                  // the entry stores are read by the duplicate search of the next insertion
       }
-      if (needq) {
+      if (valid && !xm) {
         if (best != RK_NONE32) store_owner(a, q, r, best);
         else if (!a.is_y || a.direct) store_owner(a, q, r, RK_NONE32);  // also clears a tier-1 partial result
       }
       __syncwarp();  // entry stores of this chunk are read by every lane in the next one
+      // stable compaction once half of the list is dead
+      if (n_dead > 32 && 2 * n_dead > n_ent) {
+        u32 w = 0;
+        for (u32 t0 = 0; t0 < n_ent; t0 += 32) {
+          const u32 t = t0 + lane;
+          u32 er = RK_NONE32, ec = 0, el = 0;
+          if (t < n_ent) {
+            er = e_rank[t];
+            ec = e_c[t];
+            el = e_len[t];
+          }
+          const u32 live = __ballot_sync(0xFFFFFFFFu, er != RK_NONE32);
+          __syncwarp();           // every lane holds its entry before any lane stores into this batch's range
+          if (er != RK_NONE32) {  // destination index <= t: never overwrites an entry that is still to be read
+            const u32 dst = w + __popc(live & lanemask_lt());
+            e_rank[dst] = er;
+            e_c[dst] = ec;
+            e_len[dst] = el;
+          }
+          w += __popc(live);
+          __syncwarp();
+        }
+        n_ent = w;
+        n_dead = 0;
+      }
     }
   }
 }
@@ -397,13 +454,13 @@ int launch_match(const MatchArgs &a, cudaStream_t st) {
   cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
   if (a.direct) cudaMemsetAsync(a.owner, 0xFF, (size_t)a.m * sizeof(u32), st);
   {
-    KScope ks(KID_MATCH_SMALL, st);
+    KScope ks(KID_MATCH_SMALL, st, a.m);
     k_match_small<<<(a.m + MT_THREADS - 1) / MT_THREADS, MT_THREADS, 0, st>>>(a);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  KScope ks(KID_MATCH_LONG, st);
+  KScope ks(KID_MATCH_LONG, st, 0);
   k_match_long<<<sms * 4, 128, 0, st>>>(a);
   return 2;
 }

@@ -46,7 +46,7 @@ int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *
   u32 *bsum = gid_of_root + m;
   int launches = exclusive_scan_u32(LoadIsRoot{parent}, gid_of_root, m, bsum, st);
   const u32 nb = (u32)(((u64)m + SCAN_CHUNK - 1) / SCAN_CHUNK);
-  KScope ks(KID_CHASE, st);
+  KScope ks(KID_CHASE, st, cnt);
   k_chase<<<(cnt + 255) / 256 + (cnt == 0), 256, 0, st>>>(parent, gid_of_root, cnt, gid_rank, bsum + nb, n_groups, lo);
   return launches + 1;
 }

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_hkey(const u32 *__restrict__ k0_r, cons
 
 int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st) {
   if (m == 0) return 0;
-  KScope ks(KID_HKEY, st);
+  KScope ks(KID_HKEY, st, m);
   k_hkey<<<(m + 255) / 256, 256, 0, st>>>(k0_r, ys_r, m, h);
   return 1;
 }
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) k_diag_table(const u32 *__restrict__ k0_r
 int launch_diag_table(const u32 *k0_r, const u32 *ys_r, u32 m, u32 vsize, u64 *diag, void *, cudaStream_t st) {
   if (vsize <= 1) return 0;
   const u32 nb = vsize - 1;
-  KScope ks(KID_DIAG, st);
+  KScope ks(KID_DIAG, st, nb);
   k_diag_table<<<(nb + 255) / 256, 256, 0, st>>>(k0_r, ys_r, m, nb, diag);
   return 1;
 }
@@ -304,26 +304,26 @@ int launch_order(const OrderArgs &a, cudaStream_t st) {
   int launches = 0;
   const u32 m = a.m;
   {
-    KScope ks(KID_PACK, st);
+    KScope ks(KID_PACK, st, m);
     k_pack<<<(m + 255) / 256, 256, 0, st>>>(a);
   }
   ++launches;
   if (a.do_sort) {
     cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
     {
-      KScope ks(KID_GSORT_SMALL, st);
+      KScope ks(KID_GSORT_SMALL, st, m);
       k_groupsort_small<<<(m + 127) / 128, 128, 0, st>>>(a);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     {
-      KScope ks(KID_GSORT_LARGE, st);
+      KScope ks(KID_GSORT_LARGE, st, 0);
       k_groupsort_large<<<sms * 4, 32, 0, st>>>(a);
     }
     launches += 2;
   }
-  KScope ks(KID_FINALIZE, st);
+  KScope ks(KID_FINALIZE, st, m);
   k_finalize<<<(m + 255) / 256, 256, 0, st>>>(a);
   return launches + 1;
 }

@@ -71,11 +71,11 @@ enum KernelId {
   KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
   KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_COUNT
 };
-void prof_begin(int kid, cudaStream_t st);
+void prof_begin(int kid, cudaStream_t st, unsigned long long units);
 void prof_end(cudaStream_t st);
 struct KScope {
   cudaStream_t st;
-  KScope(int kid, cudaStream_t s) : st(s) { prof_begin(kid, s); }
+  KScope(int kid, cudaStream_t s, unsigned long long units) : st(s) { prof_begin(kid, s, units); }
   ~KScope() { prof_end(st); }
 };
 

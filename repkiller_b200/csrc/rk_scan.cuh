@@ -104,7 +104,7 @@ template <class Load>
 static int exclusive_scan_u32(Load in, u32 *out, u64 n, u32 *bsum, cudaStream_t st) {
   if (n == 0) return 0;
   const u32 nb = (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-  KScope ks(KID_SCAN, st);
+  KScope ks(KID_SCAN, st, n);
   k_scan_reduce<Load><<<nb, SCAN_THREADS, 0, st>>>(in, n, bsum);
   k_scan_blocksums<<<1, 1024, 0, st>>>(bsum, nb);
   k_scan_apply<Load><<<nb, SCAN_THREADS, 0, st>>>(in, out, n, bsum);

@@ -238,3 +238,18 @@ def test_cli_unwritable_output_falls_back(tmp_path, fuzz_cases):
     assert p.returncode == 0
     assert b"Couldn't access /nonexistent-dir/out.csv, saving into represults-1.csv" in p.stderr
     assert (tmp_path / "represults-1.csv").read_bytes() == c["ref_out"].encode("latin1")
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_full_size_workloads_match_oracle(ctx, name):
+    """BASELINE configs 2 and 3 at their full 10M fragments: every output array bit-exact vs the oracle, plus the
+    size-independent properties (each kept fragment exactly once, gids non-decreasing and dense, repval pattern)."""
+    w = gen.WORKLOADS[name]
+    rec = gen.generate(w)
+    res, g = check_against_oracle(ctx, rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio, stages=False)
+    assert np.array_equal(np.sort(res.order), np.sort(g.rank_fidx))
+    assert (np.diff(res.gid.astype(np.int64)) >= 0).all() and res.gid[-1] + 1 == res.n_groups
+    head = np.r_[True, res.gid[1:] != res.gid[:-1]]
+    size = np.bincount(res.gid)[res.gid]
+    assert np.array_equal(res.repval, np.where(size == 1, 0, np.where(head, 1, 2)).astype(np.uint8))
+    print(name, "groups", res.n_groups, "max group", int(size.max()), "device ms", res.ms_device)

@@ -21,7 +21,7 @@ for _ in range(reps):
     ctx.sort_pairs_device(*args)
 prof = ctx.profile_read()
 passes = (bits + 7) // 8
-for k, (l, ms) in prof.items():
+for k, (l, ms, _u) in prof.items():
     print(f"{os.environ.get('RK_LIB_SUFFIX','')} {k}: {ms / reps * 1e3:.1f} us per sort, {ms / l * 1e3:.1f} us per launch")
 sc = prof["k_radix_scatter"][1] / reps / passes
 print(f"pass: {sc * 1e3:.1f} us -> {16 * n / sc / 1e6:.0f} GB/s algorithmic")
