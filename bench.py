@@ -170,9 +170,7 @@ ALG_BYTES_PER_UNIT = {
     "k_chase": 12,
     "k_scan": 12,
     "k_hkey": 16,
-    "k_pack": 16,
-    "k_groupsort_small": 4,
-    "k_finalize": 8 + 4 + 4 + 4 + 13,
+    "k_order_tile": 8 + 4 + 4 + 4 + 4 + 13,   # gid, rank, h, file index, identity in; four output arrays out
 }
 
 

@@ -24,7 +24,7 @@ inline int ceil_log2(u64 x) {  // bits needed to represent values 0 .. x-1
 }
 
 const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan", "k_radix_scatter", "k_keys", "k_match_small",
-                                             "k_match_long", "k_chase", "k_hkey", "k_pack", "k_groupsort_small",
+                                             "k_match_long", "k_chase", "k_hkey", "k_pack", "k_order_tile",
                                              "k_groupsort_large", "k_finalize", "k_diag_table"};
 
 // CUDA-event pair around every launch group; folded into per-kernel totals after each synchronisation
@@ -100,15 +100,16 @@ struct rk_ctx {
 
   // carved pointers
   u8 *d_aos = nullptr;
-  u32 *xs = nullptr, *ys = nullptr, *len = nullptr, *key0 = nullptr;
-  u8 *flags = nullptr;
+  uint4 *rec4 = nullptr;  // file order {xStart, yStart, length, flags}
+  u32 *key0 = nullptr;
   float *identity_f = nullptr;
   u32 *link_x = nullptr, *link_y = nullptr;
   u64 link_x_words = 0, link_y_words = 0;
   Counters *d_cnt = nullptr;
   u32 *k0_r = nullptr, *fidx_r = nullptr;
   u32 *tmp_k = nullptr, *tmp_v = nullptr;
-  u32 *cx_r = nullptr, *cy_r = nullptr, *len_r = nullptr, *ys_r = nullptr, *kx = nullptr, *ky = nullptr;
+  uint2 *xl_r = nullptr, *yl_r = nullptr;  // rank order {center, length} per axis
+  u32 *ys_r = nullptr, *kx = nullptr, *ky = nullptr;
   u32 *skx = nullptr, *rx = nullptr, *sky = nullptr, *ry = nullptr;
   void *sort_work = nullptr;
   u32 *parent = nullptr, *gid_rank = nullptr, *h = nullptr, *sgid = nullptr, *srank = nullptr;
@@ -151,11 +152,8 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   const u64 n1 = n ? n : 1;
   c->d_cnt = (Counters *)take(sizeof(Counters));
   c->d_aos = need_aos ? take(align_up(n1 * RK_FRAG_BYTES, 16) + 16) : nullptr;
-  c->xs = (u32 *)take(n1 * 4);
-  c->ys = (u32 *)take(n1 * 4);
-  c->len = (u32 *)take(n1 * 4);
+  c->rec4 = (uint4 *)take(n1 * 16);
   c->key0 = (u32 *)take(n1 * 4);
-  c->flags = take(n1);
   c->identity_f = (float *)take(n1 * 4);
   c->link_x = (u32 *)take(lxw * 4);
   c->link_y = (u32 *)take(lyw * 4);
@@ -163,9 +161,8 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   c->fidx_r = (u32 *)take(n1 * 4);
   c->tmp_k = (u32 *)take(n1 * 4);
   c->tmp_v = (u32 *)take(n1 * 4);
-  c->cx_r = (u32 *)take(n1 * 4);
-  c->cy_r = (u32 *)take(n1 * 4);
-  c->len_r = (u32 *)take(n1 * 4);
+  c->xl_r = (uint2 *)take(n1 * 8);
+  c->yl_r = (uint2 *)take(n1 * 8);
   c->ys_r = (u32 *)take(n1 * 4);
   c->kx = (u32 *)take(n1 * 4);
   c->ky = (u32 *)take(n1 * 4);
@@ -442,8 +439,8 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   CK(cudaMemsetAsync(ctx->link_x, 0, lxw * 4, st));
   CK(cudaMemsetAsync(ctx->link_y, 0, lyw * 4, st));
   u64 launches = 0;
-  launches += launch_decode(aos, n, g, ctx->xs, ctx->ys, ctx->len, ctx->flags, ctx->identity_f, ctx->key0, ctx->link_x, ctx->link_y,
-                &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st);
+  launches += launch_decode(aos, n, g, nullptr, nullptr, nullptr, nullptr, ctx->identity_f, ctx->key0, ctx->link_x, ctx->link_y,
+                            &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st, ctx->rec4);
   CK(cudaEventRecord(ev[2], st));
   // the rank sort does not depend on the number of dropped records: they carry the largest key and sort last
   launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st, &ctx->d_cnt->err);
@@ -457,8 +454,7 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   ctx->m = m;
 
   CK(cudaEventRecord(ev[4], st));
-  launches += launch_keys(ctx->fidx_r, m, g, ctx->xs, ctx->ys, ctx->len, ctx->flags, ctx->link_x, ctx->link_y, ctx->cx_r, ctx->cy_r,
-              ctx->len_r, ctx->ys_r, ctx->kx, ctx->ky, st);
+  launches += launch_keys(ctx->fidx_r, m, g, ctx->rec4, ctx->link_x, ctx->link_y, ctx->xl_r, ctx->yl_r, ctx->ys_r, ctx->kx, ctx->ky, st);
   CK(cudaEventRecord(ev[5], st));
   launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st, &ctx->d_cnt->err);
   CK(cudaEventRecord(ev[6], st));
@@ -502,14 +498,14 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
 
   CK(cudaEventRecord(ev[0], st));
   MatchArgs mx{};
-  mx.skey = ctx->skx, mx.srank = ctx->rx, mx.c_r = ctx->cx_r, mx.len_r = ctx->len_r, mx.parent = ctx->parent;
+  mx.skey = ctx->skx, mx.srank = ctx->rx, mx.cl_r = ctx->xl_r, mx.parent = ctx->parent;
   mx.m = m, mx.max_index = ctx->g.mx, mx.len_ratio = len_ratio, mx.pos_ratio = pos_ratio, mx.is_y = 0;
   mx.worklist = ctx->worklist, mx.work_count = ctx->d_cnt->work_x, mx.work_cap = ctx->work_cap;
   mx.ent_rank = ctx->ent_rank, mx.ent_c = ctx->ent_c, mx.ent_len = ctx->ent_len, mx.err = &ctx->d_cnt->err;
   launches += launch_match(mx, st);
   CK(cudaEventRecord(ev[1], st));
   MatchArgs my = mx;
-  my.skey = ctx->sky, my.srank = ctx->ry, my.c_r = ctx->cy_r, my.max_index = ctx->g.my, my.is_y = 1;
+  my.skey = ctx->sky, my.srank = ctx->ry, my.cl_r = ctx->yl_r, my.max_index = ctx->g.my, my.is_y = 1;
   my.work_count = ctx->d_cnt->work_y;
   launches += launch_match(my, st);
   CK(cudaEventRecord(ev[2], st));

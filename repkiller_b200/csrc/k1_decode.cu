@@ -64,6 +64,7 @@ __device__ __forceinline__ u64 ldg_u64_bytes(const u8 *p) {
 
 struct DecodeOut {
   u32 *xs, *ys, *len;
+  uint4 *rec4;  // when set: {xStart, yStart, length, flags} as one 16-byte word instead of the four arrays
   u8 *flags;
   float *identity;
   u32 *key0;
@@ -107,10 +108,14 @@ __device__ __forceinline__ void emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, 
       if (probes_next(c32y, g.my)) atomicOr(&o.link_y[(ky + 1) >> 5], 1u << ((ky + 1) & 31));
     }
   }
-  o.xs[idx] = (u32)xs;
-  o.ys[idx] = (u32)ys;
-  o.len[idx] = (u32)len;
-  o.flags[idx] = fl;
+  if (o.rec4) {
+    o.rec4[idx] = make_uint4((u32)xs, (u32)ys, (u32)len, fl);
+  } else {
+    o.xs[idx] = (u32)xs;
+    o.ys[idx] = (u32)ys;
+    o.len[idx] = (u32)len;
+    o.flags[idx] = fl;
+  }
   o.key0[idx] = key0;
   // (float)ident * 100 / (float)length — commonFunctions.cpp:103, float32 arithmetic without contraction
   // 0/0 (ident == 0, length == 0) is the only NaN this can produce; x86 SSE returns the default NaN with the
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
 }
 
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity, u32 *key0,
-                  u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st) {
+                  u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4) {
   if (n == 0) return 0;
   static bool attr_set = false;
   const int smem = DEC_STAGES * DEC_TILE_BYTES;
@@ -218,7 +223,7 @@ int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, 
   const u64 full_tiles = n / DEC_TILE;
   u64 grid = (u64)sms * 2;  // two CTAs (2 x 84 KB of staging) per SM, persistent over the tiles
   if (grid > full_tiles) grid = full_tiles ? full_tiles : 1;
-  DecodeOut o{xs, ys, len, flags, identity, key0, link_x, link_y, n_dropped, err};
+  DecodeOut o{xs, ys, len, rec4, flags, identity, key0, link_x, link_y, n_dropped, err};
   KScope ks(KID_DECODE, st, n);
   k_decode<<<(unsigned)grid, DEC_THREADS, smem, st>>>(aos, n, g, o);
   return 1;

@@ -41,30 +41,27 @@ __device__ __forceinline__ u32 run_start(const u32 *__restrict__ bm, u32 k) {
 }
 
 __global__ void __launch_bounds__(256)
-    k_keys(const u32 *__restrict__ fidx_r, u32 m, Geometry g, const u32 *__restrict__ xs, const u32 *__restrict__ ys,
-           const u32 *__restrict__ len, const u8 *__restrict__ flags, const u32 *__restrict__ link_x,
-           const u32 *__restrict__ link_y, u32 *__restrict__ cx_r, u32 *__restrict__ cy_r, u32 *__restrict__ len_r,
-           u32 *__restrict__ ys_r, u32 *__restrict__ kx, u32 *__restrict__ ky) {
+    k_keys(const u32 *__restrict__ fidx_r, u32 m, Geometry g, const uint4 *__restrict__ rec4, const u32 *__restrict__ link_x,
+           const u32 *__restrict__ link_y, uint2 *__restrict__ xl_r, uint2 *__restrict__ yl_r, u32 *__restrict__ ys_r,
+           u32 *__restrict__ kx, u32 *__restrict__ ky) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const u32 f = fidx_r[i];
-  const u32 x = xs[f], y = ys[f], l = len[f];
-  const u32 sc = flags[f] & FL_REVERSE;
+  const uint4 rec = rec4[fidx_r[i]];  // one 16-byte gather: {xStart, yStart, length, flags}
+  const u32 x = rec.x, y = rec.y, l = rec.z;
+  const u32 sc = rec.w & FL_REVERSE;
   const u32 cx = x + l / 2, cy = y + l / 2;  // commonFunctions.cpp:55,59
-  cx_r[i] = cx;
-  cy_r[i] = cy;
-  len_r[i] = l;
+  xl_r[i] = make_uint2(cx, l);
+  yl_r[i] = make_uint2(cy, l);
   ys_r[i] = y;
   kx[i] = run_start(link_x, sc * g.nbx + cx / DIVISOR);
   ky[i] = run_start(link_y, sc * g.nby + cy / DIVISOR);
 }
 
-int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *ys, const u32 *len, const u8 *flags,
-                const u32 *link_x, const u32 *link_y, u32 *cx_r, u32 *cy_r, u32 *len_r, u32 *ys_r, u32 *kx, u32 *ky,
-                cudaStream_t st) {
+int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, cudaStream_t st) {
   if (m == 0) return 0;
   KScope ks(KID_KEYS, st, m);
-  k_keys<<<(m + 255) / 256, 256, 0, st>>>(fidx_r, m, g, xs, ys, len, flags, link_x, link_y, cx_r, cy_r, len_r, ys_r, kx, ky);
+  k_keys<<<(m + 255) / 256, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky);
   return 1;
 }
 
@@ -168,8 +165,9 @@ __device__ __forceinline__ void load_elem(const MatchArgs &a, u32 pos, u32 &r, u
     len = a.slen[pos];
     xm = a.sxm != nullptr && a.sxm[pos] != 0;
   } else {
-    c = a.c_r[r];
-    len = a.len_r[r];
+    const uint2 cl = a.cl_r[r];
+    c = cl.x;
+    len = cl.y;
     xm = a.is_y && a.parent[r] != RK_NONE32;  // X-matched: Y-insert without a query (commonFunctions.cpp:59)
   }
 }

@@ -221,31 +221,62 @@ __device__ void dev_std_sort(P a, int n) {
   }
 }
 
-constexpr int GS_SMALL = 64;        // groups up to this size are sorted by the thread that owns their head
+constexpr int GS_SMALL = 64;         // groups up to this size are ordered inside the tile kernel
 constexpr int GS_SMEM_ELEMS = 6144;  // larger groups up to this size are sorted in shared memory (48 KB)
+constexpr int OT_THREADS = 256;
+constexpr int OT_TILE = OT_THREADS + GS_SMALL;  // groups that start in the first 256 positions end before 320
 
-__global__ void __launch_bounds__(256) k_pack(OrderArgs a) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.m) return;
-  const u32 r = a.srank ? a.srank[j] : j;  // direct layout: h/fidx/identity are already in this order
-  a.packed[j] = ((u64)a.h[r] << 32) | r;
+__device__ __forceinline__ void emit_line(const OrderArgs &a, u32 j, u64 pk, u32 g, u32 rep) {
+  const u32 r = (u32)pk;
+  const u32 f = a.fidx_r[r];
+  a.out_order[j] = f;
+  a.out_gid[j] = g;
+  a.out_repval[j] = (u8)rep;  // commonFunctions.cpp:106-115
+  a.out_identity[j] = a.identity_r ? a.identity_r[r] : a.identity_f[f];
 }
 
-__global__ void __launch_bounds__(128) k_groupsort_small(OrderArgs a) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.m) return;
-  const u32 g = a.sgid[j];
-  if (j > 0 && a.sgid[j - 1] == g) return;
-  u32 n = 1;
-  while (n <= (u32)GS_SMALL && j + n < a.m && a.sgid[j + n] == g) ++n;
-  if (n == 1) return;
-  if (n > (u32)GS_SMALL) {
-    const u32 slot = atomicAdd(a.work_count, 1u);
-    if (slot < a.work_cap) a.worklist[slot] = j;
-    else atomicOr(a.err, ERR_WORKLIST);
-    return;
+// K5b+c for groups of <= 64 members (all but a handful): a tile of the gid-sorted list is packed into shared memory as
+// (h << 32 | rank), the thread at a group's head orders the group there, and every thread writes the output line
+// of its position.  Larger groups go to the worklist of k_groupsort_large.
+__global__ void __launch_bounds__(OT_THREADS) k_order_tile(OrderArgs a) {
+  __shared__ u64 s_pk[OT_TILE];
+  __shared__ u32 s_gid[OT_TILE];
+  __shared__ u8 s_rep[OT_TILE];  // repval, 0xFF: not this tile's (continuation of the previous tile's group, or a large group)
+  __shared__ u32 s_prev;
+  const u32 tid = threadIdx.x;
+  const u32 bs = blockIdx.x * OT_THREADS;
+  const u32 count = min((u32)OT_TILE, a.m - bs);
+  for (u32 e = tid; e < (u32)OT_TILE; e += OT_THREADS) {
+    s_rep[e] = 0xFF;
+    if (e < count) {
+      const u32 j = bs + e;
+      const u32 r = a.srank ? a.srank[j] : j;  // direct layout: h/fidx/identity are already in this order
+      s_pk[e] = ((u64)a.h[r] << 32) | r;
+      s_gid[e] = a.sgid[j];
+    }
   }
-  dev_std_sort(a.packed + j, (int)n);
+  if (tid == 0) s_prev = bs ? a.sgid[bs - 1] : 0;
+  __syncthreads();
+  if (tid < count) {
+    const u32 g = s_gid[tid];
+    const bool head = tid == 0 ? (bs == 0 || s_prev != g) : s_gid[tid - 1] != g;
+    if (head) {
+      u32 n = 1;
+      while (n <= (u32)GS_SMALL && tid + n < count && s_gid[tid + n] == g) ++n;
+      if (n > (u32)GS_SMALL) {  // the tile holds head+64, so this is exact
+        const u32 slot = atomicAdd(a.work_count, 1u);
+        if (slot < a.work_cap) a.worklist[slot] = bs + tid;
+        else atomicOr(a.err, ERR_WORKLIST);
+      } else {
+        if (n > 1 && a.do_sort) dev_std_sort(s_pk + tid, (int)n);
+        s_rep[tid] = n == 1 ? 0 : 1;
+        for (u32 p = 1; p < n; ++p) s_rep[tid + p] = 2;
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 e = tid; e < count; e += OT_THREADS)
+    if (s_rep[e] != 0xFF) emit_line(a, bs + e, s_pk[e], s_gid[e], s_rep[e]);
 }
 
 // one warp per large group; lane 0 runs the (inherently sequential) introsort, all lanes move the data
@@ -269,63 +300,33 @@ __global__ void __launch_bounds__(32) k_groupsort_large(OrderArgs a) {
       if (bal != 0xFFFFFFFFu) break;
     }
     const u32 n = end - start;
-    if (n <= (u32)GS_SMEM_ELEMS) {
-      for (u32 t = lane; t < n; t += 32) buf[t] = a.packed[start + t];
-      __syncwarp();
-      if (lane == 0) dev_std_sort(buf, (int)n);
-      __syncwarp();
-      for (u32 t = lane; t < n; t += 32) a.packed[start + t] = buf[t];
-      __syncwarp();
-    } else {
-      if (lane == 0) dev_std_sort(a.packed + start, (int)n);
-      __syncwarp();
+    u64 *arr = n <= (u32)GS_SMEM_ELEMS ? buf : a.packed + start;  // beyond 48 KB: in the global scratch
+    for (u32 t = lane; t < n; t += 32) {
+      const u32 r = a.srank ? a.srank[start + t] : start + t;
+      arr[t] = ((u64)a.h[r] << 32) | r;
     }
+    __syncwarp();
+    if (lane == 0 && a.do_sort) dev_std_sort(arr, (int)n);
+    __syncwarp();
+    for (u32 t = lane; t < n; t += 32) emit_line(a, start + t, arr[t], g, t == 0 ? 1 : 2);
+    __syncwarp();
   }
-}
-
-// ---- K5c ---------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) k_finalize(OrderArgs a) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.m) return;
-  const u32 r = (u32)a.packed[j];
-  const u32 g = a.sgid[j];
-  const bool head = j == 0 || a.sgid[j - 1] != g;
-  const bool last = j + 1 == a.m || a.sgid[j + 1] != g;
-  const u32 f = a.fidx_r[r];
-  a.out_order[j] = f;
-  a.out_gid[j] = g;
-  a.out_repval[j] = (head && last) ? 0 : (head ? 1 : 2);  // commonFunctions.cpp:106-115
-  a.out_identity[j] = a.identity_r ? a.identity_r[r] : a.identity_f[f];
 }
 
 int launch_order(const OrderArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
-  int launches = 0;
   const u32 m = a.m;
+  cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
   {
-    KScope ks(KID_PACK, st, m);
-    k_pack<<<(m + 255) / 256, 256, 0, st>>>(a);
+    KScope ks(KID_GSORT_SMALL, st, m);
+    k_order_tile<<<(m + OT_THREADS - 1) / OT_THREADS, OT_THREADS, 0, st>>>(a);
   }
-  ++launches;
-  if (a.do_sort) {
-    cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
-    {
-      KScope ks(KID_GSORT_SMALL, st, m);
-      k_groupsort_small<<<(m + 127) / 128, 128, 0, st>>>(a);
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    {
-      KScope ks(KID_GSORT_LARGE, st, 0);
-      k_groupsort_large<<<sms * 4, 32, 0, st>>>(a);
-    }
-    launches += 2;
-  }
-  KScope ks(KID_FINALIZE, st, m);
-  k_finalize<<<(m + 255) / 256, 256, 0, st>>>(a);
-  return launches + 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  KScope ks(KID_GSORT_LARGE, st, 0);
+  k_groupsort_large<<<sms * 4, 32, 0, st>>>(a);
+  return 2;
 }
 
 }  // namespace rk

@@ -83,7 +83,7 @@ struct KScope {
 
 // K1: decode n packed records (device, 16-byte aligned) into file-order SoA, raise link bits.
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity,
-                  u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st);
+                  u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4 = nullptr);
 
 // K2: stable LSD radix sort of (key,value) pairs; result in keys_out/vals_out.
 u64 sort_work_bytes(u64 n);
@@ -91,9 +91,10 @@ int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32
                       u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word = nullptr);
 
 // K2 keys: rank-order SoA + super-bucket sort keys.
-int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const u32 *xs, const u32 *ys, const u32 *len, const u8 *flags,
-                const u32 *link_x, const u32 *link_y, u32 *cx_r, u32 *cy_r, u32 *len_r, u32 *ys_r, u32 *kx,
-                u32 *ky, cudaStream_t st);
+// rec4: file-order {xStart, yStart, length, flags}; xl_r/yl_r: rank-order {center, length} per axis (one 8-byte
+// gather per fragment in the match kernels)
+int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, cudaStream_t st);
 
 int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
                        const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
@@ -103,8 +104,7 @@ int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st);
 struct MatchArgs {
   const u32 *skey;   // sorted super-bucket keys
   const u32 *srank;  // rank of the fragment at each sorted position
-  const u32 *c_r;    // centers on this axis, rank order
-  const u32 *len_r;  // lengths, rank order
+  const uint2 *cl_r; // {center on this axis, length}, rank order
   u32 *parent;       // rank-indexed; X pass writes every entry, Y pass fills unmatched ones
   u32 m;
   u32 max_index;     // axis max_index
