@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--n", type=int, default=0, help="override the fragment count (same shape, scaled); testing only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sections", type=int, default=0, help="partitioned mode: CUDA-event time per section (adds syncs)")
     ap.add_argument("--multi", default="partitioned", choices=["partitioned", "independent"],
                     help="N > 1: one comparison range-partitioned over the GPUs (default) or one independent comparison per GPU")
     ap.add_argument("--profile-kernels", type=int, default=1, help="CUDA-event pairs around every kernel launch in the timed region")
@@ -227,9 +228,12 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    section_ms = {}
+
     def step_resident():
         if partitioned:
-            return group_partitioned(stages, comm, dev, n, lo, lx1, ly1, w.len_ratio, w.pos_ratio)
+            return group_partitioned(stages, comm, dev, n, lo, lx1, ly1, w.len_ratio, w.pos_ratio,
+                                     timings=section_ms if args.sections else None)
         st = ctx.load(dev.data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=False)
 
@@ -329,7 +333,7 @@ def ours(args):
             "roofline": roofline,
             "pipeline_alg_bytes_per_fragment": round(total_alg / args.steps / n, 1),
             "pipeline_hbm_frac": round(total_alg / (ms_total / 1e3) / 1e9 / peak_gbs, 4),
-            "stage_ms": stage_ms,
+            "stage_ms": stage_ms if not partitioned else {k: round(statistics.median(v[-args.steps:]), 3) for k, v in section_ms.items()},
             "kernels": kernels,
         }
     if world > 1:

@@ -156,6 +156,13 @@ int rk_st_decode(rk_ctx *ctx, const void *aos, uint64_t n, uint64_t seqx_len, ui
                  uint32_t *len, uint8_t *flags, float *identity, uint32_t *key0, uint32_t *link_x, uint32_t *link_y,
                  uint64_t *n_dropped);
 int rk_st_or_words(rk_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n_words);
+/* Row plumbing of the redistributions: a fragment travels as a row of k <= 8 32-bit words.  `cols` is a HOST array
+ * of k device pointers.  interleave: rows[i][j] = cols[j][i]; gather_rows: out[i][:] = rows[idx[i]][:];
+ * unpack_rows: cols[j][i] = rows[idx ? idx[i] : i][j] (NULL column pointers are skipped); scatter: out[idx[i]] = values[i]. */
+int rk_st_interleave(rk_ctx *ctx, const uint32_t *const *cols, uint64_t n, int k, uint32_t *rows);
+int rk_st_gather_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *out);
+int rk_st_unpack_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *const *cols);
+int rk_st_scatter(rk_ctx *ctx, const uint32_t *values, const uint32_t *idx, uint64_t n, uint32_t *out);
 /* centers and super-bucket sort keys of m fragments given in processing order */
 int rk_st_keys(rk_ctx *ctx, uint64_t m, uint64_t seqx_len, uint64_t seqy_len, const uint32_t *xs_r, const uint32_t *ys_r,
                const uint32_t *len_r, const uint8_t *flags_r, const uint32_t *link_x, const uint32_t *link_y, uint32_t *cx,

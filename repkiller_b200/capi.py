@@ -25,7 +25,7 @@ SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_se
            "rk_diagonal_func", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
            # multi-GPU stage entry points (bound in repkiller_b200/dist.py)
            "rk_st_link_words", "rk_st_decode", "rk_st_or_words", "rk_st_keys", "rk_st_match", "rk_st_forest", "rk_st_hkey",
-           "rk_st_order"]
+           "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter"]
 
 
 class RkError(RuntimeError):

@@ -684,6 +684,31 @@ int rk_st_or_words(rk_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n_w
   return RK_OK;
 }
 
+int rk_st_interleave(rk_ctx *ctx, const uint32_t *const *cols, uint64_t n, int k, uint32_t *rows) {
+  if (!ctx || k < 1 || k > 8) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  launch_interleave(cols, n, k, rows, ctx->stream);
+  return RK_OK;
+}
+int rk_st_gather_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *out) {
+  if (!ctx || k < 1 || k > 8) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  launch_gather_rows(rows, idx, n, k, out, ctx->stream);
+  return RK_OK;
+}
+int rk_st_unpack_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *const *cols) {
+  if (!ctx || k < 1 || k > 8) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  launch_unpack_rows(rows, idx, n, k, cols, ctx->stream);
+  return RK_OK;
+}
+int rk_st_scatter(rk_ctx *ctx, const uint32_t *values, const uint32_t *idx, uint64_t n, uint32_t *out) {
+  if (!ctx) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  launch_scatter_u32(values, idx, n, out, ctx->stream);
+  return RK_OK;
+}
+
 int rk_st_keys(rk_ctx *ctx, uint64_t m, uint64_t seqx_len, uint64_t seqy_len, const uint32_t *xs_r, const uint32_t *ys_r,
                const uint32_t *len_r, const uint8_t *flags_r, const uint32_t *link_x, const uint32_t *link_y, uint32_t *cx,
                uint32_t *cy, uint32_t *kx, uint32_t *ky) {

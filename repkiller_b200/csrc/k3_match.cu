@@ -99,6 +99,67 @@ int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st) {
   return 1;
 }
 
+// ---- row plumbing of the multi-GPU redistributions: fragments travel as rows of k 32-bit words -------------------
+struct ColPtrs {
+  const u32 *in[8];
+  u32 *out[8];
+};
+
+// rows[i][j] = cols[j][i]   (coalesced reads, row-major writes)
+__global__ void __launch_bounds__(256) k_interleave(ColPtrs c, u64 n, int k, u32 *__restrict__ rows) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int j = 0; j < k; ++j) rows[i * k + j] = c.in[j][i];
+}
+// out[i][:] = rows[idx[i]][:]
+__global__ void __launch_bounds__(256) k_gather_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
+                                                     u32 *__restrict__ out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 *src = rows + (u64)idx[i] * k;
+  for (int j = 0; j < k; ++j) out[i * k + j] = src[j];
+}
+// cols[j][i] = rows[idx ? idx[i] : i][j]   (row reads, coalesced column writes)
+__global__ void __launch_bounds__(256) k_unpack_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
+                                                     ColPtrs c) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 *src = rows + (u64)(idx ? idx[i] : (u32)i) * k;
+  for (int j = 0; j < k; ++j)
+    if (c.out[j]) c.out[j][i] = src[j];
+}
+// out[idx[i]] = v[i]
+__global__ void __launch_bounds__(256) k_scatter_u32(const u32 *__restrict__ v, const u32 *__restrict__ idx, u64 n,
+                                                     u32 *__restrict__ out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[idx[i]] = v[i];
+}
+
+int launch_interleave(const u32 *const *cols, u64 n, int k, u32 *rows, cudaStream_t st) {
+  if (n == 0) return 0;
+  ColPtrs c{};
+  for (int j = 0; j < k; ++j) c.in[j] = cols[j];
+  k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, n, k, rows);
+  return 1;
+}
+int launch_gather_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *out, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, out);
+  return 1;
+}
+int launch_unpack_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *const *cols, cudaStream_t st) {
+  if (n == 0) return 0;
+  ColPtrs c{};
+  for (int j = 0; j < k; ++j) c.out[j] = cols[j];
+  k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, c);
+  return 1;
+}
+int launch_scatter_u32(const u32 *v, const u32 *idx, u64 n, u32 *out, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_scatter_u32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, idx, n, out);
+  return 1;
+}
+
 // SequenceOcupationList::deviation (SequenceOcupationList.cpp:20-31).  t_len = length*len_ratio and
 // t_pos = length*pos_ratio are the query's (the relation is asymmetric).
 __device__ __forceinline__ double deviation(u32 ec, u32 el, u32 c, u32 len, double t_len, double t_pos) {

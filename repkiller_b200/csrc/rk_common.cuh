@@ -99,6 +99,11 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u
 int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
                        const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
 int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st);
+// rows of k <= 8 u32 words: interleave columns, gather rows by index, unpack (optionally permuted) rows to columns
+int launch_interleave(const u32 *const *cols, u64 n, int k, u32 *rows, cudaStream_t st);
+int launch_gather_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *out, cudaStream_t st);
+int launch_unpack_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *const *cols, cudaStream_t st);
+int launch_scatter_u32(const u32 *v, const u32 *idx, u64 n, u32 *out, cudaStream_t st);
 
 // K3: one axis pass of generate_fragment_groups.  is_y: fragments with parent != NONE insert unconditionally.
 struct MatchArgs {

@@ -141,10 +141,12 @@ class Comm:
             return [int(sorted_keys.shape[0])]
         shift = max(0, bits - 16)
         nb = 1 << min(bits, 16)
-        hist = torch.bincount((sorted_keys >> shift).to(torch.int64), minlength=nb)[:nb] if sorted_keys.numel() else \
-            torch.zeros(nb, dtype=torch.int64, device=sorted_keys.device)
-        hist = self.all_reduce_sum(hist.contiguous())
-        cum = torch.cumsum(hist, 0)
+        # local cumulative histogram over nb coarse bins straight from the sorted keys
+        edges = (torch.arange(1, nb + 1, dtype=torch.int64, device=sorted_keys.device) << shift)
+        edges = torch.clamp(edges, max=2 ** 31 - 1).to(sorted_keys.dtype)
+        cum = torch.searchsorted(sorted_keys, edges, right=False).to(torch.int64)
+        cum[-1] = sorted_keys.shape[0]
+        cum = self.all_reduce_sum(cum.contiguous())
         total = int(cum[-1].item())
         targets = torch.tensor([(total * r) // self.size for r in range(1, self.size)], dtype=torch.int64, device=cum.device)
         cut_bins = torch.searchsorted(cum, targets, right=False) + 1   # first bin boundary with cum >= target
@@ -183,9 +185,40 @@ class CudaStages:
         L.rk_st_forest.argtypes = [V, V, U64, U64, U64, V, C.POINTER(U64)]
         L.rk_st_hkey.argtypes = [V, V, V, U64, V]
         L.rk_st_order.argtypes = [V, U64, V, V, V, V, C.c_int, V, V, V, V]
+        L.rk_st_interleave.argtypes = [V, C.POINTER(V), U64, C.c_int, V]
+        L.rk_st_gather_rows.argtypes = [V, V, V, U64, C.c_int, V]
+        L.rk_st_unpack_rows.argtypes = [V, V, V, U64, C.c_int, C.POINTER(V)]
+        L.rk_st_scatter.argtypes = [V, V, V, U64, V]
 
     def _i32(self, n):
         return torch.empty(max(int(n), 0), dtype=torch.int32, device=self.device)
+
+    # -- row plumbing: a fragment travels between ranks as a row of k 32-bit words
+    def pack(self, cols: list, idx: torch.Tensor) -> torch.Tensor:
+        """rows[i][j] = cols[j][idx[i]] as an [len(idx), k] int32 tensor (interleave once, then one row gather)"""
+        k, n = len(cols), cols[0].shape[0]
+        cols = [c.contiguous() for c in cols]
+        ptrs = (C.c_void_p * k)(*[c.data_ptr() for c in cols])
+        table = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        self.ctx._check(self.L.rk_st_interleave(self.h, ptrs, n, k, _p(table)))
+        out = torch.empty((idx.shape[0], k), dtype=torch.int32, device=self.device)
+        self.ctx._check(self.L.rk_st_gather_rows(self.h, _p(table), _p(idx), idx.shape[0], k, _p(out)))
+        return out
+
+    def unpack(self, rows: torch.Tensor, idx, want: list) -> list:
+        """columns `want` of rows[idx] (idx None: rows in place) as contiguous 1-D tensors"""
+        k = rows.shape[1]
+        n = idx.shape[0] if idx is not None else rows.shape[0]
+        outs = {j: self._i32(n) for j in want}
+        ptrs = (C.c_void_p * k)(*[outs[j].data_ptr() if j in outs else None for j in range(k)])
+        self.ctx._check(self.L.rk_st_unpack_rows(self.h, _p(rows), _p(idx) if idx is not None else None, n, k, ptrs))
+        return [outs[j] for j in want]
+
+    def scatter(self, values: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """out[idx[i]] = values[i] (idx is a permutation)"""
+        out = torch.empty_like(values)
+        self.ctx._check(self.L.rk_st_scatter(self.h, _p(values), _p(idx), values.shape[0], _p(out)))
+        return out
 
     def decode(self, aos: torch.Tensor, n: int, lx1: int, ly1: int) -> dict:
         xs, ys, ln, k0 = (self._i32(n) for _ in range(4))
@@ -208,7 +241,7 @@ class CudaStages:
             work = torch.empty(self.ctx.sort_pairs_work_bytes(n), dtype=torch.uint8, device=self.device)
             self.ctx.sort_pairs_device(keys.data_ptr(), None, ko.data_ptr(), vo.data_ptr(), kt.data_ptr(), vt.data_ptr(), n,
                                        bits, work.data_ptr())
-        return ko, vo.to(torch.int64)
+        return ko, vo   # int32 permutation (torch indexes with it directly)
 
     def keys(self, m, lx1, ly1, xs_r, ys_r, len_r, flags_r, link_x, link_y):
         cx, cy, kx, ky = (self._i32(m) for _ in range(4))
@@ -262,9 +295,19 @@ class PartResult:
 
 
 def group_partitioned(st, comm: Comm, aos: torch.Tensor, n_local: int, file_offset: int, lx1: int, ly1: int,
-                      len_ratio: float, pos_ratio: float, do_sort: bool = True) -> PartResult:
-    """aos: this rank's records (uint8 tensor, n_local * 109 bytes, file order); file_offset: index of its first record."""
+                      len_ratio: float, pos_ratio: float, do_sort: bool = True, timings: dict | None = None) -> PartResult:
+    """aos: this rank's records (uint8 tensor, n_local * 109 bytes, file order); file_offset: index of its first record.
+    timings: if given (CUDA only), appended with the milliseconds of each section (CUDA events on the current stream)."""
     dev = aos.device
+    marks = []
+
+    def mark(name):
+        if timings is not None and dev.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     vsize = 1 + lx1 // 10
     bits0 = ceil_log2(vsize)
     bitsx = ceil_log2(2 * (lx1 // 100 + 2))
@@ -286,61 +329,79 @@ def group_partitioned(st, comm: Comm, aos: torch.Tensor, n_local: int, file_offs
                 link_y = acc
     kept = n_local - d["n_dropped"]
 
+    mark("decode+links")
     # -- redistribution 1: processing order (stable by xStart/10, file order inside a bucket)
     k0s, lidx = st.sort_pairs(d["key0"], bits0)
     k0s, lidx = k0s[:kept], lidx[:kept]          # the dropped last X bucket carries the largest key: it sorts last
-    pay = torch.stack([k0s, (lidx + file_offset).to(i32), d["xs"][lidx], d["ys"][lidx], d["len"][lidx],
-                       d["flags"][lidx].to(i32), d["identity"][lidx].view(i32)], dim=1)
-    recv, _ = comm.exchange(pay, comm.range_partition(k0s, bits0))
-    rk0, perm = st.sort_pairs(recv[:, 0].contiguous(), bits0)   # sources arrive in file order: stable sort = global order
-    rows = recv[perm]
-    k0_r, gfidx, xs_r, ys_r, len_r = (rows[:, j].contiguous() for j in range(5))
-    flags_r = rows[:, 5].to(torch.uint8).contiguous()
-    ident_r = rows[:, 6].contiguous()
-    m = rows.shape[0]
+    # one 28-byte row per fragment: build the rows once (coalesced), then ONE row gather into send order
+    gf = torch.arange(file_offset, file_offset + n_local, dtype=torch.int64, device=dev).to(i32)
+    rows = st.pack([d["key0"], gf, d["xs"], d["ys"], d["len"], d["flags"].to(i32), d["identity"].view(i32)], lidx)
+    recv, _ = comm.exchange(rows, comm.range_partition(k0s, bits0))
+    (rkeys,) = st.unpack(recv, None, [0])
+    rk0, perm = st.sort_pairs(rkeys, bits0)                     # sources arrive in file order: stable sort = global order
+    k0_r, gfidx, xs_r, ys_r, len_r, fl32, ident_r = st.unpack(recv, perm, [0, 1, 2, 3, 4, 5, 6])
+    flags_r = fl32.to(torch.uint8)
+    m = k0_r.shape[0]
     counts = comm.all_gather_ints(m, dev)
     off, m_total = sum(counts[: comm.rank]), sum(counts)
     grank = (torch.arange(m, dtype=torch.int64, device=dev) + off).to(i32)
 
+    mark("redistribute:rank")
     # -- K2 keys
     cx, cy, kx, ky = st.keys(m, lx1, ly1, xs_r, ys_r, len_r, flags_r, link_x, link_y)
 
     # -- redistributions 2a/2b: one axis pass each, owners sent back home
-    def axis_pass(key, c, xm, seq_len, bits):
+    def axis_pass(key, c, xm, seq_len, bits, tag):
         ks, p = st.sort_pairs(key, bits)
-        cols = [ks, grank[p], c[p], len_r[p]] + ([xm[p]] if xm is not None else [])
-        rcv, plan = comm.exchange(torch.stack(cols, dim=1), comm.range_partition(ks, bits))
-        rks, q = st.sort_pairs(rcv[:, 0].contiguous(), bits)    # sources arrive in rank order: stable sort keeps it
-        rr = rcv[q]
-        sxm = rr[:, 4].to(torch.uint8).contiguous() if xm is not None else None
-        owner_sorted = st.match(rks, rr[:, 1].contiguous(), rr[:, 2].contiguous(), rr[:, 3].contiguous(), sxm, seq_len,
-                                len_ratio, pos_ratio)
-        owner_rcv = torch.empty_like(owner_sorted)
-        owner_rcv[q] = owner_sorted
-        back = comm.exchange_back(owner_rcv, plan)
-        owner = torch.empty_like(back)
-        owner[p] = back
+        rows = st.pack([key, grank, c, len_r] + ([xm] if xm is not None else []), p)
+        mark(tag + ":sort+pack")
+        send_counts = comm.range_partition(ks, bits)
+        mark(tag + ":partition")
+        rcv, plan = comm.exchange(rows, send_counts)
+        mark(tag + ":all_to_all")
+        (rkeys,) = st.unpack(rcv, None, [0])
+        rks, q = st.sort_pairs(rkeys, bits)                     # sources arrive in rank order: stable sort keeps it
+        if xm is not None:
+            sid, sc, slen, sx = st.unpack(rcv, q, [1, 2, 3, 4])
+            sxm = sx.to(torch.uint8)
+        else:
+            sid, sc, slen = st.unpack(rcv, q, [1, 2, 3])
+            sxm = None
+        mark(tag + ":sort+unpack")
+        owner_sorted = st.match(rks, sid, sc, slen, sxm, seq_len, len_ratio, pos_ratio)
+        mark(tag + ":match")
+        back = comm.exchange_back(st.scatter(owner_sorted, q), plan)
+        owner = st.scatter(back, p)
+        mark(tag + ":owners_back")
         return owner
 
-    xo = axis_pass(kx, cx, None, lx1, bitsx)
+    mark("keys")
+    xo = axis_pass(kx, cx, None, lx1, bitsx, "x")
     xmatched = xo != NONE
-    yo = axis_pass(ky, cy, xmatched.to(i32), ly1, bitsy)
+    yo = axis_pass(ky, cy, xmatched.to(i32), ly1, bitsy, "y")
     parent = torch.where(xmatched, xo, yo)
 
     # -- K4 on the all-gathered forest
     parent_full = comm.all_gather_var(parent, counts)
     gid, n_groups = st.forest(parent_full.contiguous(), m_total, off, m)
 
+    mark("forest")
     # -- K5a at home (an X bucket never straddles ranks)
     h = st.hkey(k0_r, ys_r)
 
     # -- redistribution 3: by group id; K5b/c
     bitsg = ceil_log2(max(n_groups, 1))
     gs, p = st.sort_pairs(gid, bitsg)
-    pay = torch.stack([gs, grank[p], h[p], gfidx[p], ident_r[p]], dim=1)
-    recv, _ = comm.exchange(pay, comm.range_partition(gs, bitsg))
-    rgs, q = st.sort_pairs(recv[:, 0].contiguous(), bitsg)
-    rr = recv[q]
-    o, g, rep, idn = st.order(rgs, rr[:, 2].contiguous(), rr[:, 3].contiguous(), rr[:, 4].contiguous().view(torch.float32), do_sort)
+    rows = st.pack([gid, h, gfidx, ident_r], p)   # members arrive in rank order: the rank itself need not travel
+    recv, _ = comm.exchange(rows, comm.range_partition(gs, bitsg))
+    (rkeys,) = st.unpack(recv, None, [0])
+    rgs, q = st.sort_pairs(rkeys, bitsg)
+    sh, sf, si = st.unpack(recv, q, [1, 2, 3])
+    o, g, rep, idn = st.order(rgs, sh, sf, si.view(torch.float32), do_sort)
+    mark("redistribute:gid+order")
+    if marks:
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            timings.setdefault(n1, []).append(e0.elapsed_time(e1))
     return PartResult(o, g, rep, idn, int(n_groups), int(m_total), int(o.shape[0]), comm.bytes_sent,
                       {"m_local": m, "rank_offset": off})

@@ -38,6 +38,18 @@ def link_words(seq_len):
 class NumpyStages:
     device = torch.device("cpu")
 
+    def pack(self, cols, idx):
+        return torch.stack([c.to(torch.int32) for c in cols], dim=1)[idx.to(torch.int64)]
+
+    def unpack(self, rows, idx, want):
+        src = rows if idx is None else rows[idx.to(torch.int64)]
+        return [src[:, j].contiguous() for j in want]
+
+    def scatter(self, values, idx):
+        out = torch.empty_like(values)
+        out[idx.to(torch.int64)] = values
+        return out
+
     def decode(self, aos, n, lx1, ly1):
         rec = aos.numpy().view(FRAG_DTYPE)[:n]
         xs, ys, ln = (rec[k].astype(np.uint64) for k in ("xStart", "yStart", "length"))
