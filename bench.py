@@ -41,8 +41,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--n", type=int, default=0, help="override the fragment count (same shape, scaled); testing only")
+    ap.add_argument("--n", "--frags", dest="n", type=int, default=0, help="override the fragment count (same shape, scaled); testing only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-n", type=float, default=0, help="partitioned mode: total fragments of the one comparison (e.g. 1e9)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (very large slices)")
+    ap.add_argument("--checksum", type=int, default=0, help="also print a position-dependent checksum of the whole output")
     ap.add_argument("--sections", type=int, default=0, help="partitioned mode: CUDA-event time per section (adds syncs)")
     ap.add_argument("--multi", default="partitioned", choices=["partitioned", "independent"],
                     help="N > 1: one comparison range-partitioned over the GPUs (default) or one independent comparison per GPU")
@@ -195,8 +198,9 @@ def ours(args):
 
     base = workload(args)
     if partitioned:
-        # ONE comparison of world x the per-GPU size (same density), range-partitioned over the GPUs
-        w = gen.scaled(base, base.n * world)
+        # ONE comparison, range-partitioned over the GPUs: world x the per-GPU size of the named shape (same density;
+        # weak scaling), or with --total-n exactly that many fragments in all (config 5: --workload c5 --total-n 1e9)
+        w = gen.scaled(base, args.total_n) if args.total_n else gen.scaled(base, base.n * world)
         lo, hi = w.n * rank // world, w.n * (rank + 1) // world
         lo, hi = lo - lo % 16, (hi - hi % 16 if rank + 1 < world else hi)   # slices start on a 16-record boundary
         n_total = w.n
@@ -205,10 +209,21 @@ def ours(args):
         lo, hi = 0, w.n
         n_total = w.n * world
     n = hi - lo
-    rec = gen.generate(w, start=lo, count=n)
-    host = torch.from_numpy(rec.view(np.uint8).reshape(-1)).pin_memory()
-    dev = host.to(device)
     lx1, ly1 = w.lx + 1, w.ly + 1
+    ctx = capi.Context(local)
+    device_generated = n > 20_000_000   # large slices: same bytes from the device generator (tests pin it to gen.py)
+    if device_generated:
+        dev = torch.empty(n * 109 + 16, dtype=torch.uint8, device=device)
+        ctx.generate_device(w, lo, n, dev.data_ptr())
+        host = None
+    else:
+        rec = gen.generate(w, start=lo, count=n)
+        host = torch.from_numpy(rec.view(np.uint8).reshape(-1)).pin_memory()
+        dev = host.to(device)
+    do_e2e = not args.no_e2e
+    if host is None and do_e2e:
+        host = torch.empty(n * 109, dtype=torch.uint8).pin_memory()
+        host.copy_(dev[: n * 109])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -217,10 +232,9 @@ def ours(args):
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
     stream = torch.cuda.Stream()
-    ctx = capi.Context(local)
     ctx.set_stream(stream.cuda_stream)
     stages, comm = CudaStages(ctx, device), Comm()
-    dev2 = torch.empty_like(dev) if partitioned else None
+    dev2 = torch.empty(n * 109, dtype=torch.uint8, device=device) if partitioned and do_e2e else None
     pinned_out = {}
 
     def barrier():
@@ -281,10 +295,35 @@ def ours(args):
     ctx.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
 
-    with torch.cuda.stream(stream):
-        for _ in range(max(1, args.warmup // 2)):
-            step_e2e()
-    ms_e2e, last_e = timed(step_e2e, args.steps)
+    if do_e2e:
+        with torch.cuda.stream(stream):
+            for _ in range(max(1, args.warmup // 2)):
+                step_e2e()
+        ms_e2e, last_e = timed(step_e2e, args.steps)
+    else:
+        ms_e2e = float("nan")
+
+    checksum = None
+    if args.checksum:
+        # position-dependent 64-bit checksum of the whole output (sum over ranks): equal for any number of GPUs
+        with torch.cuda.stream(stream):
+            if partitioned:
+                o, g_, rp, idn = last.order, last.gid, last.repval, last.identity
+                lines_all = comm.all_gather_ints(int(o.shape[0]), device)
+                off = sum(lines_all[:rank])
+            else:
+                res_h = ctx.group(w.len_ratio, w.pos_ratio, host_result=True)
+                o, g_, rp, idn = (torch.from_numpy(a).to(device) for a in (res_h.order.view(np.int32), res_h.gid.view(np.int32),
+                                                                           res_h.repval, res_h.identity))
+                off = 0
+            pos = torch.arange(off, off + o.shape[0], dtype=torch.int64, device=device)
+            mix = (pos + 1) * 0x1E3779B97F4A7C15   # int64 arithmetic wraps
+            word = (o.to(torch.int64) & 0xFFFFFFFF) * 1000003 + (g_.to(torch.int64) & 0xFFFFFFFF) * 10007 + rp.to(torch.int64) * 101 \
+                + (idn.view(torch.int32).to(torch.int64) & 0xFFFFFFFF)
+            cs = ((word ^ mix) * 0x2545F4914F6CDD1D).sum().reshape(1)
+            if world > 1 and partitioned:
+                dist.all_reduce(cs)
+            checksum = int(cs.item()) & ((1 << 64) - 1)
 
     value = n_total * args.steps / (ms_total / 1e3)
     e2e_value = n_total * args.steps / (ms_e2e / 1e3)
@@ -326,7 +365,8 @@ def ours(args):
                        "multi_gpu": ("one comparison range-partitioned over the GPUs: 3 all-to-all redistributions + parent all-gather over NCCL, "
                                      f"{exchanged / 1e6:.0f} MB sent per GPU and step" if partitioned else
                                      "independent sequence pairs per rank, no data-path collective") if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(lines * 13 + 40),
+            "checksum": checksum,
+            "e2e": {"value": e2e_value if do_e2e else None, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(lines * 13 + 40),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(sum(v[0] for v in prof.values())) if prof else None,
             "clocks": clocks,
@@ -355,6 +395,7 @@ def ours(args):
 
 def main():
     args = parse()
+    args.total_n = int(args.total_n)
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -180,6 +180,11 @@ int rk_st_hkey(rk_ctx *ctx, const uint32_t *k0_r, const uint32_t *ys_r, uint64_t
 int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *sh, const uint32_t *sfidx, const float *sident,
                 int do_sort, uint32_t *out_order, uint32_t *out_gid, uint8_t *out_repval, float *out_identity);
 
+/* Tooling: records start .. start+count of the synthetic workload of repkiller_b200/gen.py, generated on the device
+ * (lx, ly are the header values, i.e. loaded length - 1). */
+int rk_gen_workload(rk_ctx *ctx, uint64_t seed, uint64_t lx, uint64_t ly, double p_rep, uint64_t families, uint64_t ax, uint64_t ay,
+                    uint64_t tandem_every, uint64_t start, uint64_t count, void *out_device);
+
 const char *rk_version(void);
 
 #ifdef __cplusplus

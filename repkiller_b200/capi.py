@@ -25,7 +25,7 @@ SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_se
            "rk_diagonal_func", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
            # multi-GPU stage entry points (bound in repkiller_b200/dist.py)
            "rk_st_link_words", "rk_st_decode", "rk_st_or_words", "rk_st_keys", "rk_st_match", "rk_st_forest", "rk_st_hkey",
-           "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter"]
+           "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter", "rk_gen_workload"]
 
 
 class RkError(RuntimeError):
@@ -177,6 +177,14 @@ class Context:
                       arr(r.identity, np.float32),
                       {"order": r.d_order, "gid": r.d_gid, "repval": r.d_repval, "identity": r.d_identity},
                       {STAGES[i]: r.ms_stage[i] for i in range(NSTAGES)}, r.ms_device, r.n_launches)
+
+    def generate_device(self, w, start: int, count: int, out_ptr: int):
+        """Records start..start+count of workload `w` (repkiller_b200.gen.Workload) written to device memory at out_ptr
+        (count * 109 bytes).  Same bytes as gen.generate(w, start, count)."""
+        f = self._L.rk_gen_workload
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double] + [C.c_uint64] * 6 + [C.c_void_p]
+        self._check(f(self._h, w.seed, w.lx, w.ly, w.p_rep, w.families, w.ax, w.ay, w.tandem_every, start, count,
+                      C.c_void_p(out_ptr)))
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.rk_profile_enable(self._h, int(on)))

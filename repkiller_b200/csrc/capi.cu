@@ -656,6 +656,16 @@ static int st_check_errors(rk_ctx *ctx, bool range_errors) {
   return RK_OK;
 }
 
+int rk_gen_workload(rk_ctx *ctx, uint64_t seed, uint64_t lx, uint64_t ly, double p_rep, uint64_t families, uint64_t ax, uint64_t ay,
+                    uint64_t tandem_every, uint64_t start, uint64_t count, void *out_device) {
+  if (!ctx || (count && !out_device)) return RK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  launch_gen(seed, lx, ly, p_rep, families, ax, ay, tandem_every, start, count, (u8 *)out_device, ctx->stream);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return RK_OK;
+}
+
 uint64_t rk_st_link_words(uint64_t seq_len) { return (2ull * (seq_len / DIVISOR + 2) + 31) / 32 + 1; }
 
 int rk_st_decode(rk_ctx *ctx, const void *aos, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, uint32_t *xs, uint32_t *ys,

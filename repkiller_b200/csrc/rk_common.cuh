@@ -81,6 +81,10 @@ struct KScope {
 
 // ---- launchers (each returns the number of kernels it launched) -------------------------------------
 
+// tooling: synthetic workload on the device, identical to repkiller_b200/gen.py
+int launch_gen(u64 seed, u64 lx, u64 ly, double p_rep, u64 families, u64 ax, u64 ay, u64 tandem_every, u64 start, u64 count,
+               u8 *out, cudaStream_t st);
+
 // K1: decode n packed records (device, 16-byte aligned) into file-order SoA, raise link bits.
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity,
                   u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4 = nullptr);

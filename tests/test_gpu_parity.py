@@ -253,3 +253,19 @@ def test_full_size_workloads_match_oracle(ctx, name):
     size = np.bincount(res.gid)[res.gid]
     assert np.array_equal(res.repval, np.where(size == 1, 0, np.where(head, 1, 2)).astype(np.uint8))
     print(name, "groups", res.n_groups, "max group", int(size.max()), "device ms", res.ms_device)
+
+
+def test_device_generator_matches_host_generator(ctx):
+    """rk_gen_workload (device) must produce the bytes of repkiller_b200.gen.generate (host) — it is what the
+    1e9-fragment benchmark uses instead of a host-generated file."""
+    import torch
+    from dataclasses import replace
+    for w, start, count in [(gen.WORKLOADS["c2"], 9_000_000, 300_001), (gen.WORKLOADS["c3"], 123, 200_000),
+                            (gen.WORKLOADS["c5"], 999_000_000, 100_000), (replace(gen.WORKLOADS["c1"], seed=77), 0, 100_000)]:
+        host = gen.generate(w, start=start, count=count)
+        out = torch.empty(count * 109, dtype=torch.uint8, device="cuda:0")
+        ctx.generate_device(w, start, count, out.data_ptr())
+        got = out.cpu().numpy()
+        want = host.view(np.uint8).reshape(-1)
+        d = np.nonzero(got != want)[0]
+        assert d.size == 0, f"{w.name}: {d.size} bytes differ, first at record {d[0] // 109} byte {d[0] % 109}"
