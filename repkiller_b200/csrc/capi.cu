@@ -3,6 +3,7 @@
 // generate_diagonal_func + sort_groups (rk_group).  Reference call sites: /root/reference/src/repkiller.cpp:52,84-91.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,9 +101,10 @@ struct rk_ctx {
 
   // carved pointers
   u8 *d_aos = nullptr;
-  uint4 *rec4 = nullptr;  // file order {xStart, yStart, length, flags}
+  uint4 *rec4 = nullptr;  // file order, two words per record: {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
+  float *identity_r = nullptr;  // rank order
+  uint4 *hfi_r = nullptr;       // rank order {h, file index, identity bits, 0}
   u32 *key0 = nullptr;
-  float *identity_f = nullptr;
   u32 *link_x = nullptr, *link_y = nullptr;
   u64 link_x_words = 0, link_y_words = 0;
   Counters *d_cnt = nullptr;
@@ -112,6 +114,7 @@ struct rk_ctx {
   u32 *ys_r = nullptr, *kx = nullptr, *ky = nullptr;
   u32 *skx = nullptr, *rx = nullptr, *sky = nullptr, *ry = nullptr;
   void *sort_work = nullptr;
+  u32 *xm_bits = nullptr;
   u32 *parent = nullptr, *gid_rank = nullptr, *h = nullptr, *sgid = nullptr, *srank = nullptr;
   void *forest_work = nullptr;
   u64 *packed = nullptr;
@@ -152,9 +155,10 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   const u64 n1 = n ? n : 1;
   c->d_cnt = (Counters *)take(sizeof(Counters));
   c->d_aos = need_aos ? take(align_up(n1 * RK_FRAG_BYTES, 16) + 16) : nullptr;
-  c->rec4 = (uint4 *)take(n1 * 16);
+  c->rec4 = (uint4 *)take(n1 * 32);
   c->key0 = (u32 *)take(n1 * 4);
-  c->identity_f = (float *)take(n1 * 4);
+  c->identity_r = (float *)take(n1 * 4);
+  c->hfi_r = (uint4 *)take(n1 * 16);
   c->link_x = (u32 *)take(lxw * 4);
   c->link_y = (u32 *)take(lyw * 4);
   c->k0_r = (u32 *)take(n1 * 4);
@@ -172,6 +176,7 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   c->ry = (u32 *)take(n1 * 4);
   c->sort_work = take(sort_work_bytes(n1));
   c->parent = (u32 *)take(n1 * 4);
+  c->xm_bits = (u32 *)take((n1 + 31) / 32 * 4);
   c->gid_rank = (u32 *)take(n1 * 4);
   c->h = (u32 *)take(n1 * 4);
   c->sgid = (u32 *)take(n1 * 4);
@@ -253,7 +258,7 @@ namespace {
 // K5b tail + K5c on the state the last rk_group left on the device
 u64 run_order(rk_ctx *ctx, unsigned flags) {
   OrderArgs oa{};
-  oa.sgid = ctx->sgid, oa.srank = ctx->srank, oa.h = ctx->h, oa.fidx_r = ctx->fidx_r, oa.identity_f = ctx->identity_f;
+  oa.sgid = ctx->sgid, oa.srank = ctx->srank, oa.hfi_r = ctx->hfi_r;
   oa.packed = ctx->packed, oa.m = ctx->m, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1;
   oa.worklist = ctx->worklist, oa.work_count = ctx->d_cnt->work_g, oa.work_cap = ctx->work_cap;
   oa.out_order = ctx->out_order, oa.out_gid = ctx->out_gid, oa.out_repval = ctx->out_repval, oa.out_identity = ctx->out_identity;
@@ -349,6 +354,7 @@ rk_ctx *rk_create(int device) {
     return nullptr;
   }
   c->own_stream = true;
+  if (const char *gr = getenv("RK_L2_GRAN")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));  // tuning switch
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   if (cudaMalloc((void **)&c->st_cnt, sizeof(Counters)) != cudaSuccess) c->st_cnt = nullptr;
   return c;
@@ -439,7 +445,7 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   CK(cudaMemsetAsync(ctx->link_x, 0, lxw * 4, st));
   CK(cudaMemsetAsync(ctx->link_y, 0, lyw * 4, st));
   u64 launches = 0;
-  launches += launch_decode(aos, n, g, nullptr, nullptr, nullptr, nullptr, ctx->identity_f, ctx->key0, ctx->link_x, ctx->link_y,
+  launches += launch_decode(aos, n, g, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->key0, ctx->link_x, ctx->link_y,
                             &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st, ctx->rec4);
   CK(cudaEventRecord(ev[2], st));
   // the rank sort does not depend on the number of dropped records: they carry the largest key and sort last
@@ -454,7 +460,10 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   ctx->m = m;
 
   CK(cudaEventRecord(ev[4], st));
-  launches += launch_keys(ctx->fidx_r, m, g, ctx->rec4, ctx->link_x, ctx->link_y, ctx->xl_r, ctx->yl_r, ctx->ys_r, ctx->kx, ctx->ky, st);
+  launches += launch_keys(ctx->fidx_r, m, g, ctx->rec4, ctx->link_x, ctx->link_y, ctx->xl_r, ctx->yl_r, ctx->ys_r, ctx->kx, ctx->ky,
+                          ctx->identity_r, st);
+  // generate_diagonal_func does not depend on the ratios: h and the per-rank output record are load-time work
+  launches += launch_hkey(ctx->k0_r, ctx->ys_r, m, ctx->h, st, ctx->fidx_r, ctx->identity_r, ctx->hfi_r);
   CK(cudaEventRecord(ev[5], st));
   launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st, &ctx->d_cnt->err);
   CK(cudaEventRecord(ev[6], st));
@@ -498,7 +507,7 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
 
   CK(cudaEventRecord(ev[0], st));
   MatchArgs mx{};
-  mx.skey = ctx->skx, mx.srank = ctx->rx, mx.cl_r = ctx->xl_r, mx.parent = ctx->parent;
+  mx.skey = ctx->skx, mx.srank = ctx->rx, mx.cl_r = ctx->xl_r, mx.parent = ctx->parent, mx.xm_bits = ctx->xm_bits;
   mx.m = m, mx.max_index = ctx->g.mx, mx.len_ratio = len_ratio, mx.pos_ratio = pos_ratio, mx.is_y = 0;
   mx.worklist = ctx->worklist, mx.work_count = ctx->d_cnt->work_x, mx.work_cap = ctx->work_cap;
   mx.ent_rank = ctx->ent_rank, mx.ent_c = ctx->ent_c, mx.ent_len = ctx->ent_len, mx.err = &ctx->d_cnt->err;
@@ -511,7 +520,6 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
   CK(cudaEventRecord(ev[2], st));
   launches += launch_forest(ctx->parent, m, ctx->gid_rank, &ctx->d_cnt->n_groups, ctx->forest_work, st);
   CK(cudaEventRecord(ev[3], st));
-  launches += launch_hkey(ctx->k0_r, ctx->ys_r, m, ctx->h, st);
   CK(cudaEventRecord(ev[4], st));
   // gids are < number of groups <= m; sorting by ceil_log2(m) bits avoids a host round trip for the count
   launches += launch_sort_pairs(ctx->gid_rank, nullptr, ctx->sgid, ctx->srank, ctx->tmp_k, ctx->tmp_v, m, ceil_log2(m),
@@ -565,7 +573,7 @@ int64_t rk_debug_fetch(rk_ctx *ctx, const char *name, void *host, uint64_t bytes
   else if (!strcmp(name, "gid_rank")) src = ctx->gid_rank;
   else if (!strcmp(name, "hkey")) src = ctx->h;
   else return fail(ctx, RK_ERR_ARG, "unknown array %s", name);
-  if ((!strcmp(name, "parent") || !strcmp(name, "gid_rank") || !strcmp(name, "hkey")) && !ctx->have_group)
+  if ((!strcmp(name, "parent") || !strcmp(name, "gid_rank")) && !ctx->have_group)
     return fail(ctx, RK_ERR_STATE, "no rk_group result yet");
   if (host && bytes >= sz && sz) {
     CK(cudaSetDevice(ctx->device));
@@ -785,7 +793,7 @@ int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *s
   const int rc = st_scratch(ctx, m1 * 8 + (u64)cap * 4 + 1024, &scr);
   if (rc != RK_OK) return rc;
   OrderArgs oa{};
-  oa.sgid = sgid, oa.srank = nullptr, oa.h = sh, oa.fidx_r = sfidx, oa.identity_f = nullptr, oa.identity_r = sident;
+  oa.sgid = sgid, oa.srank = nullptr, oa.hfi_r = nullptr, oa.h = sh, oa.fidx_r = sfidx, oa.identity_r = sident;
   oa.packed = (u64 *)scr, oa.m = (u32)m, oa.do_sort = do_sort;
   oa.worklist = (u32 *)((u8 *)scr + m1 * 8), oa.work_count = ctx->st_cnt->work_g, oa.work_cap = cap;
   oa.out_order = out_order, oa.out_gid = out_gid, oa.out_repval = out_repval, oa.out_identity = out_identity;

@@ -64,7 +64,8 @@ __device__ __forceinline__ u64 ldg_u64_bytes(const u8 *p) {
 
 struct DecodeOut {
   u32 *xs, *ys, *len;
-  uint4 *rec4;  // when set: {xStart, yStart, length, flags} as one 16-byte word instead of the four arrays
+  uint4 *rec4;  // when set: two 16-byte words per record {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
+                // instead of the five arrays (one 32-byte sector per gather in k_keys)
   u8 *flags;
   float *identity;
   u32 *key0;
@@ -108,21 +109,22 @@ __device__ __forceinline__ void emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, 
       if (probes_next(c32y, g.my)) atomicOr(&o.link_y[(ky + 1) >> 5], 1u << ((ky + 1) & 31));
     }
   }
-  if (o.rec4) {
-    o.rec4[idx] = make_uint4((u32)xs, (u32)ys, (u32)len, fl);
-  } else {
-    o.xs[idx] = (u32)xs;
-    o.ys[idx] = (u32)ys;
-    o.len[idx] = (u32)len;
-    o.flags[idx] = fl;
-  }
-  o.key0[idx] = key0;
   // (float)ident * 100 / (float)length — commonFunctions.cpp:103, float32 arithmetic without contraction
   // 0/0 (ident == 0, length == 0) is the only NaN this can produce; x86 SSE returns the default NaN with the
   // sign bit set (0xFFC00000, printed "-nan" by the reference's writer), so mirror that bit pattern.
   float idv = __fdiv_rn(__fmul_rn(__ull2float_rn(ident), 100.0f), __ull2float_rn(len));
   if (idv != idv) idv = __int_as_float(0xFFC00000);
-  o.identity[idx] = idv;
+  o.key0[idx] = key0;
+  if (o.rec4) {
+    o.rec4[2 * idx] = make_uint4((u32)xs, (u32)ys, (u32)len, fl);
+    o.rec4[2 * idx + 1] = make_uint4(__float_as_uint(idv), 0u, 0u, 0u);
+  } else {
+    o.xs[idx] = (u32)xs;
+    o.ys[idx] = (u32)ys;
+    o.len[idx] = (u32)len;
+    o.flags[idx] = fl;
+    o.identity[idx] = idv;
+  }
 }
 
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ aos, u64 n, Geometry g, DecodeOut o) {

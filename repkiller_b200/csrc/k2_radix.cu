@@ -26,6 +26,16 @@ constexpr int RS_THREADS = 256;
 #define RK_RS_MINBLOCKS 3
 #endif
 constexpr int RS_ITEMS = RK_RS_ITEMS;
+#ifndef RK_OS_THREADS
+#define RK_OS_THREADS 256
+#endif
+#ifndef RK_OS_LB
+#define RK_OS_LB 16
+#endif
+constexpr int OS_THREADS = RK_OS_THREADS;  // one-sweep pass CTA (a multiple of 256: one thread per digit does the prefix work)
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_TILE = OS_THREADS * RS_ITEMS;
+constexpr int OS_SMEM_BYTES = (OS_WARPS * 256 + 2 * 256 + 2 * OS_TILE) * 4;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_WARP_TILE = 32 * RS_ITEMS;  // 512 consecutive keys per warp
@@ -165,17 +175,47 @@ constexpr u32 OS_VAL = (1u << 30) - 1;
 constexpr u64 OS_MAX_N = 1ull << 30;
 constexpr int OS_MAX_PASSES = 4;
 
+// Keys of a warp often share a digit (the top digits of nearly sorted keys: gids, bucket keys in processing order), which
+// would serialise 32 shared-memory atomics on one address; a uniform digit is counted once by lane 0.
+template <int VEC>
 __global__ void __launch_bounds__(256) k_onesweep_hist(const u32 *__restrict__ keys, u64 n, int passes, int key_bits,
                                                        u32 *__restrict__ ghist) {
   __shared__ u32 h[OS_MAX_PASSES][RADIX];
   for (int p = 0; p < OS_MAX_PASSES; ++p) h[p][threadIdx.x] = 0;
   __syncthreads();
   const u32 last_mask = (1u << (key_bits - 8 * (passes - 1))) - 1;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-    const u32 k = keys[i];
+  const u32 lane = threadIdx.x & 31;
+  const u64 nv = n / VEC;  // whole vectors; the loop bounds are warp-uniform so every lane takes part in the votes
+  const u64 warp0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull;
+  for (u64 base = warp0; base < nv; base += (u64)gridDim.x * blockDim.x) {
+    const u64 i = base + lane;
+    const bool valid = i < nv;
+    u32 k[VEC];
+    if (VEC == 4) {
+      const uint4 v = valid ? reinterpret_cast<const uint4 *>(keys)[i] : make_uint4(0, 0, 0, 0);
+      k[0] = v.x, k[VEC > 1 ? 1 : 0] = v.y, k[VEC > 2 ? 2 : 0] = v.z, k[VEC > 3 ? 3 : 0] = v.w;
+    } else {
+      k[0] = valid ? keys[i] : 0;
+    }
 #pragma unroll
-    for (int p = 0; p < OS_MAX_PASSES; ++p)
-      if (p < passes) atomicAdd(&h[p][(k >> (8 * p)) & (p == passes - 1 ? last_mask : 0xFFu)], 1u);
+    for (int j = 0; j < VEC; ++j) {
+#pragma unroll
+      for (int p = 0; p < OS_MAX_PASSES; ++p) {
+        if (p < passes) {
+          const u32 d = (k[j] >> (8 * p)) & (p == passes - 1 ? last_mask : 0xFFu);
+          const u32 d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
+          if (__all_sync(0xFFFFFFFFu, valid && d == d0)) {
+            if (lane == 0) atomicAdd(&h[p][d], 32u);
+          } else if (valid) {
+            atomicAdd(&h[p][d], 1u);
+          }
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - nv * VEC) {  // the n % VEC keys after the last whole vector
+    const u32 kk = keys[nv * VEC + threadIdx.x];
+    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(kk >> (8 * p)) & (p == passes - 1 ? last_mask : 0xFFu)], 1u);
   }
   __syncthreads();
   for (int p = 0; p < passes; ++p) {
@@ -191,24 +231,24 @@ __global__ void __launch_bounds__(RADIX) k_onesweep_bases(u32 *ghist) {
   g[threadIdx.x] = block_excl_scan<RADIX>(v, nullptr);
 }
 
-__global__ void __launch_bounds__(RS_THREADS, RK_RS_MINBLOCKS)
+__global__ void __launch_bounds__(OS_THREADS, RK_RS_MINBLOCKS)
     k_onesweep_pass(const u32 *__restrict__ kin, const u32 *__restrict__ vin, u32 *__restrict__ kout, u32 *__restrict__ vout,
                     u64 n, int shift, u32 mask, const u32 *__restrict__ digit_start, u32 *state, u32 *tile_counter, u32 *err) {
-  __shared__ u32 warp_cnt[RS_WARPS][RADIX];
-  __shared__ u32 digit_base[RADIX];
-  __shared__ u32 gbase[RADIX];
-  __shared__ u32 skeys[RS_TILE];
-  __shared__ u32 svals[RS_TILE];
+  extern __shared__ u32 os_smem[];
+  u32(*warp_cnt)[RADIX] = reinterpret_cast<u32(*)[RADIX]>(os_smem);  // [OS_WARPS][RADIX]
+  u32 *digit_base = os_smem + OS_WARPS * RADIX;
+  u32 *gbase = digit_base + RADIX;
+  u32 *skeys = gbase + RADIX;
+  u32 *svals = skeys + OS_TILE;
   __shared__ u32 s_tile;
 
   const u32 tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-#pragma unroll
-  for (int q = 0; q < RS_WARPS; ++q) warp_cnt[q][tid] = 0;
+  for (u32 q = tid; q < (u32)(OS_WARPS * RADIX); q += OS_THREADS) os_smem[q] = 0;
   __syncthreads();
   const u32 tile = s_tile;
-  const u64 tile_start = (u64)tile * RS_TILE;
-  const u32 nvalid = (u32)((n - tile_start < (u64)RS_TILE) ? (n - tile_start) : RS_TILE);
+  const u64 tile_start = (u64)tile * OS_TILE;
+  const u32 nvalid = (u32)((n - tile_start < (u64)OS_TILE) ? (n - tile_start) : OS_TILE);
 
   u32 key[RS_ITEMS], val[RS_ITEMS], rnk[RS_ITEMS];
 #pragma unroll
@@ -247,35 +287,57 @@ __global__ void __launch_bounds__(RS_THREADS, RK_RS_MINBLOCKS)
   __syncthreads();
 
   // thread tid = digit tid: count of VALID keys with this digit (padding sits in the top digit, after them)
+  const bool digit_thread = tid < (u32)RADIX;
   u32 total = 0;
+  if (digit_thread) {
 #pragma unroll
-  for (int q = 0; q < RS_WARPS; ++q) {
-    const u32 c = warp_cnt[q][tid];
-    warp_cnt[q][tid] = total;
-    total += c;
+    for (int q = 0; q < OS_WARPS; ++q) {
+      const u32 c = warp_cnt[q][tid];
+      warp_cnt[q][tid] = total;
+      total += c;
+    }
   }
   u32 valid_total = total;
-  if (tid == mask) valid_total -= (u32)RS_TILE - nvalid;
+  if (tid == mask) valid_total -= (u32)OS_TILE - nvalid;
 
   // publish this tile's counts, look back over the predecessors, publish the inclusive prefix
   volatile u32 *my_state = state + (u64)tile * RADIX + tid;
   u32 excl = 0;
-  if (tile == 0) {
+  if (!digit_thread) {
+    // threads beyond the 256 digits only help with loading, ranking and writing
+  } else if (tile == 0) {
     *my_state = OS_PFX | valid_total;
   } else {
     *my_state = OS_AGG | valid_total;
     // Batches of LB independent loads: the tiles of one wave start together and all sit in the AGG state, so the
     // walk back to the last published prefix is as long as the wave; one load in flight would cost an L2 round
     // trip per predecessor.
-    constexpr int LB = 16;
+    constexpr int LB = RK_OS_LB;
     u32 next = tile;  // predecessors next-1, next-2, ... are still to be added
     u32 spins = 0;
     bool done = false;
     while (!done) {
       u32 v[LB];
+      const volatile u32 *row = state + (u64)next * RADIX + tid;  // row of tile `next`; predecessors are below it
+      if (next >= (u32)LB) {
 #pragma unroll
-      for (int j = 0; j < LB; ++j)
-        v[j] = ((u32)j < next) ? *(volatile u32 *)(state + (u64)(next - 1 - j) * RADIX + tid) : (2u << 30) /* OS_PFX | 0 */;
+        for (int j = 0; j < LB; ++j) v[j] = *(row - (j + 1) * RADIX);
+        // fast path: all LB predecessors have published their count and none its prefix yet
+        u32 all_and = v[0], all_or = v[0];
+#pragma unroll
+        for (int j = 1; j < LB; ++j) all_and &= v[j], all_or |= v[j];
+        if ((all_and & OS_AGG) && !(all_or & OS_PFX)) {
+          u32 sum = 0;
+#pragma unroll
+          for (int j = 0; j < LB; ++j) sum += v[j];
+          excl += sum - LB * OS_AGG;  // every word carries exactly the AGG flag
+          next -= LB;
+          continue;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < LB; ++j) v[j] = ((u32)j < next) ? *(row - (j + 1) * RADIX) : (2u << 30) /* OS_PFX | 0 */;
+      }
       u32 used = 0;
 #pragma unroll
       for (int j = 0; j < LB; ++j) {
@@ -297,9 +359,11 @@ __global__ void __launch_bounds__(RS_THREADS, RK_RS_MINBLOCKS)
     *my_state = OS_PFX | (excl + valid_total);
   }
 
-  const u32 dbase = block_excl_scan<RS_THREADS>(total, nullptr);
-  digit_base[tid] = dbase;
-  gbase[tid] = digit_start[tid] + excl - dbase;
+  const u32 dbase = block_excl_scan<OS_THREADS>(total, nullptr);
+  if (digit_thread) {
+    digit_base[tid] = dbase;
+    gbase[tid] = digit_start[tid] + excl - dbase;
+  }
   __syncthreads();
 
 #pragma unroll
@@ -311,7 +375,7 @@ __global__ void __launch_bounds__(RS_THREADS, RK_RS_MINBLOCKS)
   }
   __syncthreads();
 
-  for (u32 p = tid; p < nvalid; p += RS_THREADS) {
+  for (u32 p = tid; p < nvalid; p += OS_THREADS) {
     const u32 k = skeys[p];
     const u32 dst = gbase[(k >> shift) & mask] + p;
     kout[dst] = k;
@@ -322,7 +386,7 @@ __global__ void __launch_bounds__(RS_THREADS, RK_RS_MINBLOCKS)
 static inline u64 align_up(u64 x, u64 a) { return (x + a - 1) / a * a; }
 
 static inline u64 onesweep_state_words(u64 n) {
-  const u64 tiles = (n + RS_TILE - 1) / RS_TILE;
+  const u64 tiles = (n + OS_TILE - 1) / OS_TILE;
   return OS_MAX_PASSES * RADIX + 64 + OS_MAX_PASSES * tiles * RADIX;
 }
 
@@ -338,7 +402,12 @@ u64 sort_work_bytes(u64 n) {
 static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp, u32 *vals_tmp,
                            u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word) {
   const int passes = (key_bits + 7) / 8;
-  const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+  const u32 tiles = (u32)((n + OS_TILE - 1) / OS_TILE);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM_BYTES);
+    attr_set = true;
+  }
   u32 *ghist = reinterpret_cast<u32 *>(work);          // [4][256]
   u32 *counters = ghist + OS_MAX_PASSES * RADIX;          // [4] tile counters, [4] = error word when none was set
   u32 *state = counters + 64;                            // [passes][tiles][256]
@@ -351,7 +420,8 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
     KScope ks(KID_RADIX_HIST, st, n);
     u64 blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (blocks > (u64)sms * 8) blocks = (u64)sms * 8;
-    k_onesweep_hist<<<(unsigned)blocks, 256, 0, st>>>(keys_in, n, passes, key_bits, ghist);
+    if (((uintptr_t)keys_in & 15) == 0) k_onesweep_hist<4><<<(unsigned)blocks, 256, 0, st>>>(keys_in, n, passes, key_bits, ghist);
+    else k_onesweep_hist<1><<<(unsigned)blocks, 256, 0, st>>>(keys_in, n, passes, key_bits, ghist);
     k_onesweep_bases<<<passes, RADIX, 0, st>>>(ghist);
   }
   const u32 *ksrc = keys_in, *vsrc = vals_in;
@@ -363,7 +433,7 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
     u32 *kdst = to_out ? keys_out : keys_tmp;
     u32 *vdst = to_out ? vals_out : vals_tmp;
     KScope ks(KID_RADIX_SCATTER, st, n);
-    k_onesweep_pass<<<tiles, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask, ghist + p * RADIX,
+    k_onesweep_pass<<<tiles, OS_THREADS, OS_SMEM_BYTES, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask, ghist + p * RADIX,
                                                   state + (u64)p * tiles * RADIX, counters + p, err);
     ksrc = kdst;
     vsrc = vdst;

@@ -43,10 +43,13 @@ __device__ __forceinline__ u32 run_start(const u32 *__restrict__ bm, u32 k) {
 __global__ void __launch_bounds__(256)
     k_keys(const u32 *__restrict__ fidx_r, u32 m, Geometry g, const uint4 *__restrict__ rec4, const u32 *__restrict__ link_x,
            const u32 *__restrict__ link_y, uint2 *__restrict__ xl_r, uint2 *__restrict__ yl_r, u32 *__restrict__ ys_r,
-           u32 *__restrict__ kx, u32 *__restrict__ ky) {
+           u32 *__restrict__ kx, u32 *__restrict__ ky, float *__restrict__ identity_r) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const uint4 rec = rec4[fidx_r[i]];  // one 16-byte gather: {xStart, yStart, length, flags}
+  // one 32-byte gather (one sector): {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
+  const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
+  const uint4 rec = src[0];
+  identity_r[i] = __uint_as_float(src[1].x);
   const u32 x = rec.x, y = rec.y, l = rec.z;
   const u32 sc = rec.w & FL_REVERSE;
   const u32 cx = x + l / 2, cy = y + l / 2;  // commonFunctions.cpp:55,59
@@ -58,10 +61,10 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
-                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, cudaStream_t st) {
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st) {
   if (m == 0) return 0;
   KScope ks(KID_KEYS, st, m);
-  k_keys<<<(m + 255) / 256, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky);
+  k_keys<<<(m + 255) / 256, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r);
   return 1;
 }
 
@@ -229,135 +232,220 @@ __device__ __forceinline__ void load_elem(const MatchArgs &a, u32 pos, u32 &r, u
     const uint2 cl = a.cl_r[r];
     c = cl.x;
     len = cl.y;
-    xm = a.is_y && a.parent[r] != RK_NONE32;  // X-matched: Y-insert without a query (commonFunctions.cpp:59)
+    // X-matched: Y-insert without a query (commonFunctions.cpp:59); one bit per rank, set by the X pass (the 1.25 MB
+    // map of 10M fragments stays in L2, a gather of parent[r] would cost a DRAM sector)
+    xm = a.is_y && ((a.xm_bits[r >> 5] >> (r & 31)) & 1u);
   }
 }
 __device__ __forceinline__ void store_owner(const MatchArgs &a, u32 pos, u32 r, u32 v) {
-  if (a.direct) a.owner[pos] = v;
-  else a.parent[r] = v;
+  if (a.direct) {
+    a.owner[pos] = v;
+  } else {
+    a.parent[r] = v;
+    if (!a.is_y && v != RK_NONE32) atomicOr(&a.xm_bits[r >> 5], 1u << (r & 31));
+  }
 }
 // "no match" is stored by the X pass only: in the Y pass parent[] already holds the X result (indirect), and the
 // direct owner[] array is pre-filled with NONE by the launcher.
 __device__ __forceinline__ bool stores_none(const MatchArgs &a) { return !a.is_y && !a.direct; }
 
-constexpr int MT_THREADS = 256;
-constexpr int MT_TILE = MT_THREADS + 32;  // heads live in the first 256 positions, their segments end before 288
+constexpr int MT_HEADS = 256;           // a CTA stages 256 positions + 32 of halo; warp w owns the segments whose head
+constexpr int MT_TILE = MT_HEADS + 32;  // lies in positions [32w, 32w+32) — they end before 32w+64 (the warp's window)
+#ifndef RK_MT_MINB
+#define RK_MT_MINB 6
+#endif
 
-__global__ void __launch_bounds__(MT_THREADS) k_match_small(MatchArgs a) {
-  __shared__ u32 s_key[MT_TILE], s_c[MT_TILE], s_len[MT_TILE], s_rank[MT_TILE], s_bkt[MT_TILE], s_cand[MT_TILE];
-  __shared__ u8 s_xm[MT_TILE];
-  __shared__ u32 s_nz[MT_TILE];  // per head: positions of its segment that have candidates
-  __shared__ u32 s_prev_key;
+// The rare tails of the candidate search are kept out of line so that the hot loop stays small.
+// In-band pair: both differences are within Thresh::rej but at least one is not below Thresh::pass; the correctly
+// rounded quotients decide (deviation > 0 <=> both <= 1 and not both == 1).
+__device__ __noinline__ bool band_candidate(u32 dl, u32 dc, u32 len, double len_ratio, double pos_ratio) {
+  const double ql = __ddiv_rn((double)dl, __dmul_rn((double)len, len_ratio));
+  if (ql > 1.0) return false;
+  const double qp = __ddiv_rn((double)dc, __dmul_rn((double)len, pos_ratio));
+  if (qp > 1.0) return false;
+  return !(ql == 1.0 && qp == 1.0);
+}
 
-  const u32 tid = threadIdx.x;
-  const u32 bs = blockIdx.x * MT_THREADS;
+// owner among several inserted candidates: greatest score, own bucket before neighbour, newest first (:40 strict >).
+// hit: bit q <-> window position q; returns the window position of the winner
+__device__ __noinline__ u32 best_of(unsigned long long hit, const uint2 *s_cl_win, u32 c, u32 len, double len_ratio,
+                                    double pos_ratio) {
+  const u32 b = c / DIVISOR;
+  const double t_len = __dmul_rn((double)len, len_ratio);
+  const double t_pos = __dmul_rn((double)len, pos_ratio);
+  double best_sc = 0.0;
+  int best = -1;
+  bool best_own = false;
+  while (hit) {
+    const int k = 63 - __clzll(hit);
+    hit &= ~(1ull << k);
+    const uint2 ecl = s_cl_win[k];
+    const bool own = ecl.x / DIVISOR == b;
+    const double sc = deviation(ecl.x, ecl.y, c, len, t_len, t_pos);
+    if (sc > best_sc || (sc == best_sc && best >= 0 && own && !best_own)) {
+      best_sc = sc;
+      best = k;
+      best_own = own;
+    }
+  }
+  return (u32)best;
+}
+
+// what a query needs for the candidate test, worked out once per tile position while the tile is staged
+struct QueryTh {
+  u32 pass_len, rej_len, pass_pos, rej_pos;  // Thresh::pass / Thresh::rej of the two similarity terms
+};
+
+// deviation(entry, query) > 0 ?
+__device__ __forceinline__ bool is_candidate(uint2 ecl, u32 c, u32 len, u32 b, u32 nbk, const uint4 &th, const MatchArgs &a) {
+  const u32 dl = absdiff(len, ecl.y);
+  if (dl > th.y) return false;  // rejects almost every unrelated pair after one 8-byte shared load
+  const u32 dc = absdiff(c, ecl.x);
+  if (dc > th.w) return false;
+  const u32 bk = ecl.x / DIVISOR;
+  if (bk != b && bk != nbk) return false;
+  if (dl < th.x && dc < th.z) return true;
+  return band_candidate(dl, dc, len, a.len_ratio, a.pos_ratio);
+}
+
+// Tier 1.  After the tile is staged in shared memory the warps work independently, each on a window of 64 positions:
+// lane l holds window positions l ("A") and 32+l ("B"; only the segment that straddles the middle of the window has B
+// members).  All segment state lives in ballots:
+//   phase 0: segment heads = ballot of key changes;
+//   phase 1: candidate mask of every member over its predecessors in the segment (bit q <-> window position q);
+//   phase 2: status in rounds — UNK / INS (an entry) / NOT.  A member with an inserted candidate is NOT at once; a member
+//            whose candidates are all decided and none inserted is INS.  The first undecided member of a segment can
+//            always decide, and a family of mutual candidates settles in two rounds (first member INS, all others NOT);
+//   phase 3: owners from the final INS mask: one inserted candidate -> that entry; several -> exact scores.
+__global__ void __launch_bounds__(MT_HEADS, RK_MT_MINB) k_match_small(MatchArgs a) {
+  __shared__ u32 s_key[MT_TILE + 1];  // s_key[1 + e]; s_key[0] = key before the tile
+  __shared__ u32 s_rank[MT_TILE];
+  __shared__ uint2 s_cl[MT_TILE];
+  __shared__ uint4 s_th[MT_TILE];     // {pass_len, rej_len, pass_pos, rej_pos}
+  __shared__ uint2 s_bn[MT_TILE];     // {own bucket, neighbour bucket | NO_BUCKET}; x == NO_BUCKET: not a query
+  __shared__ u32 s_pref[MT_HEADS / 32][64];     // per warp: exclusive prefix of the pair counts of the 64 window slots
+  __shared__ u32 s_cand[MT_HEADS / 32][64][2];  // per warp: candidate mask of every slot (bit q <-> window position q)
+
+  const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const u32 bs = blockIdx.x * MT_HEADS;
   const u32 count = min((u32)MT_TILE, a.m - bs);  // valid tile positions
-
-  for (u32 e = tid; e < (u32)MT_TILE; e += MT_THREADS) {
-    s_nz[e] = 0;
+  for (u32 e = tid; e < (u32)MT_TILE; e += MT_HEADS) {
+    u32 key = 0xFFFFFFFFu;  // no real key (bucket indices are < 2^31): padding never continues a segment
     if (e < count) {
       u32 r, c, len;
       bool xm;
+      key = a.skey[bs + e];
       load_elem(a, bs + e, r, c, len, xm);
-      s_key[e] = a.skey[bs + e];
       s_rank[e] = r;
-      s_c[e] = c;
-      s_len[e] = len;
-      s_bkt[e] = c / DIVISOR;
-      s_xm[e] = xm ? 1 : 0;
-    }
-  }
-  if (tid == 0) s_prev_key = bs ? a.skey[bs - 1] : 0;
-  __syncthreads();
-
-  // phase 1: candidate mask of every tile element over its predecessors in the segment (bit d-1: element e-d)
-  const bool foreign0 = bs != 0 && s_prev_key == s_key[0];
-  for (u32 e = tid; e < (u32)MT_TILE; e += MT_THREADS) {
-    u32 dist_mask = 0, pos = 0;
-    if (e < count) {
-      const u32 key = s_key[e];
-      const u32 c = s_c[e], len = s_len[e];
-      const bool query = !s_xm[e] && len != 0;  // length 0: every score is NaN or 0 -> never matches
-      const u32 b = s_bkt[e];
-      const u32 nbk = neighbour_bucket(c, a.max_index);
+      s_cl[e] = make_uint2(c, len);
       const Thresh tl = make_thresh(len, a.len_ratio), tp = make_thresh(len, a.pos_ratio);
-      for (u32 d = 1; d <= e && d <= 32; ++d) {
-        const u32 k = e - d;
-        if (s_key[k] != key) break;
-        pos = d;
-        if (!query) continue;
-        const u32 el = s_len[k], ec = s_c[k], bk = s_bkt[k];
-        const u32 dl = len > el ? len - el : el - len;
-        const u32 dc = c > ec ? c - ec : ec - c;
-        if (dl > tl.rej || dc > tp.rej || (bk != b && bk != nbk)) continue;
-        const int ql = quotient_vs_one(dl, tl);
-        if (ql == 0) continue;
-        const int qp = quotient_vs_one(dc, tp);
-        if (qp == 0 || (ql == 2 && qp == 2)) continue;
-        dist_mask |= 1u << (d - 1);
-      }
+      s_th[e] = make_uint4(tl.pass, tl.rej, tp.pass, tp.rej);
+      // X-matched fragments (Y pass) and length 0 (every score is NaN or 0) never query; they are entries
+      s_bn[e] = make_uint2((xm || len == 0) ? NO_BUCKET : c / DIVISOR, neighbour_bucket(c, a.max_index));
     }
-    // position-based mask: bit p <-> element head+p, p = pos - d
-    const u32 cand = pos ? (__brev(dist_mask) >> (32 - pos)) : 0;
-    s_cand[e] = cand;
-    if (e < count) {
-      const u32 h = e - pos;
-      if (cand) {
-        if (pos < 32) atomicOr(&s_nz[h], 1u << pos);
-      } else if (stores_none(a) && !(h == 0 && foreign0)) {
-        // no candidate at all: an X entry for sure.  (Continuations of the previous tile's segment are that
-        // CTA's; elements whose head lies beyond position 255 are written again, identically, by the next CTA.)
-        store_owner(a, bs + e, s_rank[e], RK_NONE32);
-      }
-    }
+    s_key[1 + e] = key;
   }
+  if (tid == 0) s_key[0] = bs ? a.skey[bs - 1] : 0xFFFFFFFEu;  // a segment running in from the previous tile is that CTA's
   __syncthreads();
 
-  // phase 2: the thread at a segment's head replays, in order, only the positions that have candidates; every
-  // other position (no candidate, or X-matched in the Y pass) is inserted from the start.
-  if (tid >= count) return;
-  const u32 key = s_key[tid];
-  const bool head = tid == 0 ? !foreign0 : s_key[tid - 1] != key;
-  if (!head) return;
-  if (tid + 32 < count && s_key[tid + 32] == key) {  // more than 32 fragments: the tile holds head+32, exact
+  // phase 0
+  const u32 wb = w << 5;  // tile position of window position 0
+  const u32 eA = wb + lane, eB = eA + 32;
+  const u32 hbA = __ballot_sync(0xFFFFFFFFu, s_key[1 + eA] != s_key[eA]);
+  const u32 hbB = __ballot_sync(0xFFFFFFFFu, s_key[1 + eB] != s_key[eB]);
+  const u32 le = 0xFFFFFFFFu >> (31 - lane);  // lanes <= this one
+  const u32 lastA = hbA ? 31 - __clz(hbA) : 0;             // head of the straddling segment (when hbA != 0)
+  const u32 firstB = hbB ? __ffs(hbB) - 1 : 32;            // its end, as a B index
+  const bool straddle_long = firstB > lastA;               // 32 + firstB - lastA > 32 members
+  const u32 ownA = hbA & le;
+  const u32 hpA = ownA ? 31 - __clz(ownA) : 0;             // head (window position) of A's segment
+  const bool actA = eA < count && ownA != 0 && !(hpA == lastA && straddle_long);
+  const bool actB = eB < count && hbA != 0 && lane < firstB && !straddle_long;
+  if (eA < count && hbA != 0 && lane == lastA && straddle_long) {  // more than 32 fragments: tier 2
     const u32 slot = atomicAdd(a.work_count, 1u);
-    if (slot < a.work_cap) a.worklist[slot] = bs + tid;
+    if (slot < a.work_cap) a.worklist[slot] = bs + eA;
     else atomicOr(a.err, ERR_WORKLIST);
-    return;
   }
-  u32 todo = s_nz[tid];
-  u32 inserted = ~todo;
-  while (todo) {
-    const u32 p = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const u32 e = tid + p;
-    const u32 hit = s_cand[e] & inserted;
-    if (!hit) {
-      inserted |= 1u << p;
-      if (stores_none(a)) store_owner(a, bs + e, s_rank[e], RK_NONE32);
-    } else if ((hit & (hit - 1)) == 0) {
-      store_owner(a, bs + e, s_rank[e], s_rank[tid + __ffs(hit) - 1]);
-    } else {
-      // several inserted candidates: greatest score, own bucket before neighbour, newest first (:40 strict >)
-      const u32 c = s_c[e], len = s_len[e], b = s_bkt[e];
-      const double t_len = __dmul_rn((double)len, a.len_ratio);
-      const double t_pos = __dmul_rn((double)len, a.pos_ratio);
-      double best_sc = 0.0;
-      int best = -1;
-      bool best_own = false;
-      for (u32 msk = hit; msk;) {
-        const int k = 31 - __clz(msk);
-        msk &= ~(1u << k);
-        const bool own = s_bkt[tid + k] == b;
-        const double sc = deviation(s_c[tid + k], s_len[tid + k], c, len, t_len, t_pos);
-        if (sc > best_sc || (sc == best_sc && best >= 0 && own && !best_own)) {
-          best_sc = sc;
-          best = k;
-          best_own = own;
-        }
+
+  // phase 1: the (query, predecessor) pairs of the window are spread evenly over the lanes — a family of 13 mutual
+  // candidates has 78 pairs, and a lane-per-query loop would run as long as the longest segment of the window.
+  // Pair t belongs to the last slot whose exclusive prefix of pair counts is <= t (binary search in shared memory).
+  const uint2 *win = s_cl + wb;
+  uint2 bnA = make_uint2(NO_BUCKET, 0), bnB = make_uint2(NO_BUCKET, 0);
+  if (actA) bnA = s_bn[eA];
+  if (actB) bnB = s_bn[eB];
+  const u32 nA = bnA.x != NO_BUCKET ? lane - hpA : 0;  // predecessors to test
+  const u32 nB = bnB.x != NO_BUCKET ? 32 + lane - lastA : 0;
+  u32 incA = nA, incB = nB;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 va = __shfl_up_sync(0xFFFFFFFFu, incA, o), vb = __shfl_up_sync(0xFFFFFFFFu, incB, o);
+    if ((int)lane >= o) incA += va, incB += vb;
+  }
+  const u32 totA = __shfl_sync(0xFFFFFFFFu, incA, 31);
+  const u32 tot = totA + __shfl_sync(0xFFFFFFFFu, incB, 31);
+  u32 candA = 0;
+  unsigned long long candB = 0;
+  if (tot) {
+    u32 *pref = s_pref[w];
+    u32(*cw)[2] = s_cand[w];
+    pref[lane] = incA - nA;
+    pref[32 + lane] = totA + incB - nB;
+    cw[lane][0] = 0, cw[lane][1] = 0, cw[32 + lane][0] = 0, cw[32 + lane][1] = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (u32 t = lane; t < tot; t += 32) {
+      u32 i = 0, base = 0;
+#pragma unroll
+      for (int step = 32; step >= 1; step >>= 1) {
+        const u32 v = pref[i + step];
+        if (v <= t) i += step, base = v;
       }
-      store_owner(a, bs + e, s_rank[e], s_rank[tid + best]);
+      const u32 q = i - (t - base + 1);  // window position of the predecessor
+      const uint2 qcl = win[i], bn = s_bn[wb + i];
+      if (is_candidate(win[q], qcl.x, qcl.y, bn.x, bn.y, s_th[wb + i], a)) atomicOr(&cw[i][q >> 5], 1u << (q & 31));
     }
+    __syncwarp();
+    candA = cw[lane][0];
+    candB = ((unsigned long long)cw[32 + lane][1] << 32) | cw[32 + lane][0];
+  }
+  const uint2 clA = win[lane], clB = win[32 + lane];
+
+  // phase 2
+  enum { UNK = 0, INS = 1, NOT = 2 };
+  int stA = candA ? UNK : (actA ? INS : NOT);
+  int stB = candB ? UNK : (actB ? INS : NOT);
+  u32 insA, insB;
+  for (;;) {
+    insA = __ballot_sync(0xFFFFFFFFu, stA == INS);
+    insB = __ballot_sync(0xFFFFFFFFu, stB == INS);
+    const u32 unkA = __ballot_sync(0xFFFFFFFFu, stA == UNK);
+    const u32 unkB = __ballot_sync(0xFFFFFFFFu, stB == UNK);
+    if ((unkA | unkB) == 0) break;
+    if (stA == UNK) {
+      if (candA & insA) stA = NOT;
+      else if ((candA & unkA) == 0) stA = INS;
+    }
+    if (stB == UNK) {
+      const unsigned long long ins = ((unsigned long long)insB << 32) | insA, unk = ((unsigned long long)unkB << 32) | unkA;
+      if (candB & ins) stB = NOT;
+      else if ((candB & unk) == 0) stB = INS;
+    }
+  }
+
+  // phase 3 (a fragment that does not query keeps what it has: X-matched in the Y pass; length 0 gets "none")
+  const bool y_or_direct = !stores_none(a);
+  if (actA && !(y_or_direct && bnA.x == NO_BUCKET)) {
+    const u32 hit = candA & insA;
+    u32 owner = RK_NONE32;
+    if (hit) owner = s_rank[wb + ((hit & (hit - 1)) == 0 ? (u32)__ffs(hit) - 1 : best_of(hit, win, clA.x, clA.y, a.len_ratio, a.pos_ratio))];
+    if (hit || !y_or_direct) store_owner(a, bs + eA, s_rank[eA], owner);
+  }
+  if (actB && !(y_or_direct && bnB.x == NO_BUCKET)) {
+    const unsigned long long hit = candB & (((unsigned long long)insB << 32) | insA);
+    u32 owner = RK_NONE32;
+    if (hit) owner = s_rank[wb + ((hit & (hit - 1)) == 0 ? (u32)__ffsll((long long)hit) - 1 : best_of(hit, win, clB.x, clB.y, a.len_ratio, a.pos_ratio))];
+    if (hit || !y_or_direct) store_owner(a, bs + eB, s_rank[eB], owner);
   }
 }
 
@@ -511,10 +599,11 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
 int launch_match(const MatchArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
   cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
+  if (!a.direct && !a.is_y) cudaMemsetAsync(a.xm_bits, 0, ((size_t)a.m + 31) / 32 * sizeof(u32), st);
   if (a.direct) cudaMemsetAsync(a.owner, 0xFF, (size_t)a.m * sizeof(u32), st);
   {
     KScope ks(KID_MATCH_SMALL, st, a.m);
-    k_match_small<<<(a.m + MT_THREADS - 1) / MT_THREADS, MT_THREADS, 0, st>>>(a);
+    k_match_small<<<(a.m + MT_HEADS - 1) / MT_HEADS, MT_HEADS, 0, st>>>(a);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -19,7 +19,8 @@ namespace rk {
 // ---- K5a ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_hkey(const u32 *__restrict__ k0_r, const u32 *__restrict__ ys_r, u32 m,
-                                              u32 *__restrict__ h) {
+                                              u32 *__restrict__ h, const u32 *__restrict__ fidx_r,
+                                              const float *__restrict__ identity_r, uint4 *__restrict__ hfi_r) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const u32 key = k0_r[i];
@@ -34,13 +35,17 @@ __global__ void __launch_bounds__(256) k_hkey(const u32 *__restrict__ k0_r, cons
     if (k0_r[mid] == key) lo = mid;
     else hi = mid;
   }
-  h[i] = absdiff(ys_r[i], ys_r[lo]);  // commonFunctions.cpp:152-155
+  const u32 hv = absdiff(ys_r[i], ys_r[lo]);  // commonFunctions.cpp:152-155
+  if (h) h[i] = hv;
+  // everything K5b/c needs about a fragment in one 16-byte word (one gather by rank instead of three)
+  if (hfi_r) hfi_r[i] = make_uint4(hv, fidx_r[i], __float_as_uint(identity_r[i]), 0u);
 }
 
-int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st) {
+int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st, const u32 *fidx_r, const float *identity_r,
+                uint4 *hfi_r) {
   if (m == 0) return 0;
   KScope ks(KID_HKEY, st, m);
-  k_hkey<<<(m + 255) / 256, 256, 0, st>>>(k0_r, ys_r, m, h);
+  k_hkey<<<(m + 255) / 256, 256, 0, st>>>(k0_r, ys_r, m, h, fidx_r, identity_r, hfi_r);
   return 1;
 }
 
@@ -222,61 +227,109 @@ __device__ void dev_std_sort(P a, int n) {
 }
 
 constexpr int GS_SMALL = 64;         // groups up to this size are ordered inside the tile kernel
+constexpr int GS_STABLE = 16;        // std::sort of <= 16 elements is one insertion sort == a stable sort by h
 constexpr int GS_SMEM_ELEMS = 6144;  // larger groups up to this size are sorted in shared memory (48 KB)
-constexpr int OT_THREADS = 256;
-constexpr int OT_TILE = OT_THREADS + GS_SMALL;  // groups that start in the first 256 positions end before 320
+constexpr int OT_HEADS = 256;        // a CTA owns the groups whose head lies in its first 256 positions
+constexpr int OT_TILE = OT_HEADS + GS_SMALL;  // ... and those groups end before position 320: one thread per position
+constexpr int OT_WARPS = OT_TILE / 32;
 
-__device__ __forceinline__ void emit_line(const OrderArgs &a, u32 j, u64 pk, u32 g, u32 rep) {
-  const u32 r = (u32)pk;
-  const u32 f = a.fidx_r[r];
-  a.out_order[j] = f;
-  a.out_gid[j] = g;
-  a.out_repval[j] = (u8)rep;  // commonFunctions.cpp:106-115
-  a.out_identity[j] = a.identity_r ? a.identity_r[r] : a.identity_f[f];
+// what the output line of a fragment needs besides its group: {h, file index, identity bits}
+__device__ __forceinline__ void load_member(const OrderArgs &a, u32 j, u32 &r, u32 &h, u32 &fidx, u32 &ident) {
+  if (a.srank) {  // single GPU: one 16-byte gather by processing rank
+    r = a.srank[j];
+    const uint4 rec = a.hfi_r[r];
+    h = rec.x, fidx = rec.y, ident = rec.z;
+  } else {  // multi-GPU stages: the three arrays are already in this order
+    r = j;
+    h = a.h[j], fidx = a.fidx_r[j], ident = __float_as_uint(a.identity_r[j]);
+  }
 }
 
-// K5b+c for groups of <= 64 members (all but a handful): a tile of the gid-sorted list is packed into shared memory as
-// (h << 32 | rank), the thread at a group's head orders the group there, and every thread writes the output line
-// of its position.  Larger groups go to the worklist of k_groupsort_large.
-__global__ void __launch_bounds__(OT_THREADS) k_order_tile(OrderArgs a) {
+// K5b+c for groups of <= 64 members (all but a handful).  One thread per position of the gid-sorted list:
+//   * group boundaries from a ballot of gid changes;
+//   * <= 16 members: every member counts the members that sort before it (smaller h, or equal h and earlier) — the
+//     stable order libstdc++'s insertion sort produces — and drops its source position at that output slot;
+//   * 17..64 members (rare): the head thread runs the restated introsort on (h << 32 | tile position) words;
+//   * > 64: worklist of k_groupsort_large;
+// then every thread writes the output line of its position.
+__global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
+  __shared__ u32 s_gid[OT_TILE], s_h[OT_TILE], s_fidx[OT_TILE], s_ident[OT_TILE], s_perm[OT_TILE];
   __shared__ u64 s_pk[OT_TILE];
-  __shared__ u32 s_gid[OT_TILE];
-  __shared__ u8 s_rep[OT_TILE];  // repval, 0xFF: not this tile's (continuation of the previous tile's group, or a large group)
+  __shared__ u32 s_heads[OT_WARPS];
   __shared__ u32 s_prev;
-  const u32 tid = threadIdx.x;
-  const u32 bs = blockIdx.x * OT_THREADS;
+  const u32 e = threadIdx.x, lane = e & 31, w = e >> 5;
+  const u32 bs = blockIdx.x * OT_HEADS;
   const u32 count = min((u32)OT_TILE, a.m - bs);
-  for (u32 e = tid; e < (u32)OT_TILE; e += OT_THREADS) {
-    s_rep[e] = 0xFF;
-    if (e < count) {
-      const u32 j = bs + e;
-      const u32 r = a.srank ? a.srank[j] : j;  // direct layout: h/fidx/identity are already in this order
-      s_pk[e] = ((u64)a.h[r] << 32) | r;
-      s_gid[e] = a.sgid[j];
-    }
+  const bool valid = e < count;
+  u32 gid = 0xFFFFFFFFu;  // no real group id (gid < m <= 2^32-16): padding never continues a group
+  if (valid) {
+    u32 r, h, fidx, ident;
+    gid = a.sgid[bs + e];
+    load_member(a, bs + e, r, h, fidx, ident);
+    s_h[e] = h, s_fidx[e] = fidx, s_ident[e] = ident;
   }
-  if (tid == 0) s_prev = bs ? a.sgid[bs - 1] : 0;
+  s_gid[e] = gid;
+  if (e == 0) s_prev = bs ? a.sgid[bs - 1] : 0;
   __syncthreads();
-  if (tid < count) {
-    const u32 g = s_gid[tid];
-    const bool head = tid == 0 ? (bs == 0 || s_prev != g) : s_gid[tid - 1] != g;
-    if (head) {
-      u32 n = 1;
-      while (n <= (u32)GS_SMALL && tid + n < count && s_gid[tid + n] == g) ++n;
-      if (n > (u32)GS_SMALL) {  // the tile holds head+64, so this is exact
-        const u32 slot = atomicAdd(a.work_count, 1u);
-        if (slot < a.work_cap) a.worklist[slot] = bs + tid;
-        else atomicOr(a.err, ERR_WORKLIST);
-      } else {
-        if (n > 1 && a.do_sort) dev_std_sort(s_pk + tid, (int)n);
-        s_rep[tid] = n == 1 ? 0 : 1;
-        for (u32 p = 1; p < n; ++p) s_rep[tid + p] = 2;
+
+  const bool is_head = e == 0 || s_gid[e - 1] != gid;
+  const u32 hb = __ballot_sync(0xFFFFFFFFu, is_head);
+  if (lane == 0) s_heads[w] = hb;
+  const bool foreign0 = bs != 0 && s_prev == s_gid[0];
+  __syncthreads();
+  // start: last head at or before e (64 positions back are enough); end: first head after e
+  u32 start = 0xFFFFFFFFu, end = 0xFFFFFFFFu;
+  {
+    const u32 own = hb & (0xFFFFFFFFu >> (31 - lane));
+    u32 x;
+    if (own) start = (w << 5) + 31 - __clz(own);
+    else if (w >= 1 && (x = s_heads[w - 1]) != 0) start = ((w - 1) << 5) + 31 - __clz(x);
+    else if (w >= 2 && (x = s_heads[w - 2]) != 0) start = ((w - 2) << 5) + 31 - __clz(x);
+    const u32 above = hb & (0xFFFFFFFEu << lane);
+    if (above) end = (w << 5) + __ffs(above) - 1;
+    else if (w + 1 < (u32)OT_WARPS && (x = s_heads[w + 1]) != 0) end = ((w + 1) << 5) + __ffs(x) - 1;
+    else if (w + 2 < (u32)OT_WARPS && (x = s_heads[w + 2]) != 0) end = ((w + 2) << 5) + __ffs(x) - 1;
+  }
+  // No head within reach on either side means more than 64 members.  A group that starts before position 256 and
+  // shows no end inside the tile has at least 65 members too (the tile holds start+64).
+  const bool large = start == 0xFFFFFFFFu || end == 0xFFFFFFFFu || end - start > (u32)GS_SMALL;
+  const bool owned = valid && start != 0xFFFFFFFFu && start < (u32)OT_HEADS && !(start == 0 && foreign0);
+  const u32 n = large ? 0 : end - start;
+  if (valid && is_head && large && e < (u32)OT_HEADS && !(e == 0 && foreign0)) {
+    const u32 slot = atomicAdd(a.work_count, 1u);
+    if (slot < a.work_cap) a.worklist[slot] = bs + e;
+    else atomicOr(a.err, ERR_WORKLIST);
+  }
+  const bool mine = owned && !large;
+  const bool mid = mine && n > (u32)GS_STABLE && a.do_sort;
+  if (mine) {
+    if (n == 1 || !a.do_sort) {
+      s_perm[e] = e;
+    } else if (n <= (u32)GS_STABLE) {
+      const u32 h = s_h[e], me = e - start;
+      u32 before = 0;
+      for (u32 q = 0; q < n; ++q) {
+        const u32 o = s_h[start + q];
+        before += (o < h || (o == h && q < me)) ? 1u : 0u;
       }
+      s_perm[start + before] = e;
+    } else {
+      s_pk[e] = ((u64)s_h[e] << 32) | e;
     }
   }
-  __syncthreads();
-  for (u32 e = tid; e < count; e += OT_THREADS)
-    if (s_rep[e] != 0xFF) emit_line(a, bs + e, s_pk[e], s_gid[e], s_rep[e]);
+  if (__syncthreads_or(mid)) {
+    if (mid && e == start) dev_std_sort(s_pk + start, (int)n);
+    __syncthreads();
+    if (mid) s_perm[e] = (u32)s_pk[e];
+    __syncthreads();
+  }
+  if (mine) {
+    const u32 src = s_perm[e], j = bs + e;
+    a.out_order[j] = s_fidx[src];
+    a.out_gid[j] = gid;
+    a.out_repval[j] = (u8)(n == 1 ? 0 : (e == start ? 1 : 2));  // commonFunctions.cpp:106-115
+    a.out_identity[j] = __uint_as_float(s_ident[src]);
+  }
 }
 
 // one warp per large group; lane 0 runs the (inherently sequential) introsort, all lanes move the data
@@ -302,13 +355,27 @@ __global__ void __launch_bounds__(32) k_groupsort_large(OrderArgs a) {
     const u32 n = end - start;
     u64 *arr = n <= (u32)GS_SMEM_ELEMS ? buf : a.packed + start;  // beyond 48 KB: in the global scratch
     for (u32 t = lane; t < n; t += 32) {
-      const u32 r = a.srank ? a.srank[start + t] : start + t;
-      arr[t] = ((u64)a.h[r] << 32) | r;
+      u32 r, h, fidx, ident;
+      load_member(a, start + t, r, h, fidx, ident);
+      arr[t] = ((u64)h << 32) | r;
     }
     __syncwarp();
     if (lane == 0 && a.do_sort) dev_std_sort(arr, (int)n);
     __syncwarp();
-    for (u32 t = lane; t < n; t += 32) emit_line(a, start + t, arr[t], g, t == 0 ? 1 : 2);
+    for (u32 t = lane; t < n; t += 32) {
+      const u32 r = (u32)arr[t], j = start + t;
+      u32 fidx, ident;
+      if (a.srank) {
+        const uint4 rec = a.hfi_r[r];
+        fidx = rec.y, ident = rec.z;
+      } else {
+        fidx = a.fidx_r[r], ident = __float_as_uint(a.identity_r[r]);
+      }
+      a.out_order[j] = fidx;
+      a.out_gid[j] = g;
+      a.out_repval[j] = (u8)(t == 0 ? 1 : 2);
+      a.out_identity[j] = __uint_as_float(ident);
+    }
     __syncwarp();
   }
 }
@@ -319,7 +386,7 @@ int launch_order(const OrderArgs &a, cudaStream_t st) {
   cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
   {
     KScope ks(KID_GSORT_SMALL, st, m);
-    k_order_tile<<<(m + OT_THREADS - 1) / OT_THREADS, OT_THREADS, 0, st>>>(a);
+    k_order_tile<<<(m + OT_HEADS - 1) / OT_HEADS, OT_TILE, 0, st>>>(a);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

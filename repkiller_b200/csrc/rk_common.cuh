@@ -95,10 +95,11 @@ int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32
                       u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word = nullptr);
 
 // K2 keys: rank-order SoA + super-bucket sort keys.
-// rec4: file-order {xStart, yStart, length, flags}; xl_r/yl_r: rank-order {center, length} per axis (one 8-byte
-// gather per fragment in the match kernels)
+// rec4: file order, two 16-byte words per record {xStart, yStart, length, flags} {identity bits, 0, 0, 0} (one 32-byte
+// sector per gather); xl_r/yl_r: rank-order {center, length} per axis (one 8-byte gather per fragment in the match
+// kernels); identity_r: rank order
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
-                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, cudaStream_t st);
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st);
 
 int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
                        const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
@@ -115,6 +116,7 @@ struct MatchArgs {
   const u32 *srank;  // rank of the fragment at each sorted position
   const uint2 *cl_r; // {center on this axis, length}, rank order
   u32 *parent;       // rank-indexed; X pass writes every entry, Y pass fills unmatched ones
+  u32 *xm_bits;      // one bit per rank: matched in the X pass (written by the X pass, read by the Y pass)
   u32 m;
   u32 max_index;     // axis max_index
   double len_ratio, pos_ratio;
@@ -139,7 +141,9 @@ int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *
                   u32 cnt = 0xFFFFFFFFu);
 
 // K5a: h = |yStart - yStart(last fragment of the same xStart/10 bucket)| per rank.
-int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st);
+// With hfi_r: also the packed per-rank record {h, file index, identity bits, 0} K5b/c gathers (h may then be null).
+int launch_hkey(const u32 *k0_r, const u32 *ys_r, u32 m, u32 *h, cudaStream_t st, const u32 *fidx_r = nullptr,
+                const float *identity_r = nullptr, uint4 *hfi_r = nullptr);
 
 // K5a': the full diag_func table with carry-forward (only for rk_diagonal_func).
 int launch_diag_table(const u32 *k0_r, const u32 *ys_r, u32 m, u32 vsize, u64 *diag, void *work, cudaStream_t st);
@@ -148,10 +152,11 @@ int launch_diag_table(const u32 *k0_r, const u32 *ys_r, u32 m, u32 vsize, u64 *d
 struct OrderArgs {
   const u32 *sgid;    // sorted gids
   const u32 *srank;   // rank at each sorted position
-  const u32 *h;       // by rank
-  const u32 *fidx_r;  // file index by rank
-  const float *identity_f;  // by file index
-  const float *identity_r;  // direct layout: by the same index as h/fidx_r (srank == nullptr)
+  const uint4 *hfi_r; // single GPU: {h, file index, identity bits, 0} by rank (gathered through srank)
+  // direct layout (srank == nullptr, multi-GPU stages): the three arrays are already in gid-sorted order
+  const u32 *h;
+  const u32 *fidx_r;
+  const float *identity_r;
   u64 *packed;        // scratch m
   u32 m;
   int do_sort;
