@@ -160,7 +160,10 @@ class Context:
         return LoadStats(st.n_loaded, st.n_kept, st.vsize, {STAGES[i]: st.ms_stage[i] for i in range(NSTAGES)}, st.ms_device,
                          st.n_launches)
 
-    def group(self, len_ratio: float, pos_ratio: float, host_result: bool = True, sort: bool = True, timing: bool = True) -> Groups:
+    def group(self, len_ratio: float, pos_ratio: float, host_result: bool = True, sort: bool = True, timing: bool = True,
+              copy: bool = True) -> Groups:
+        """copy=False: the host arrays are views of the library-owned pinned result buffers (what a C caller gets);
+        they are valid until the next call on this context."""
         flags = (F_HOST_RESULT if host_result else 0) | (0 if sort else F_NO_SORT) | (F_TIMING if timing else 0)
         r = _Result()
         self._check(self._L.rk_group(self._h, len_ratio, pos_ratio, flags, C.byref(r)))
@@ -171,7 +174,8 @@ class Context:
                 return None
             if m == 0:
                 return np.zeros(0, dt)
-            return np.ctypeslib.as_array(p, shape=(m,)).copy()
+            v = np.ctypeslib.as_array(p, shape=(m,))
+            return v.copy() if copy else v
 
         return Groups(m, r.n_groups, arr(r.order, np.uint32), arr(r.gid, np.uint32), arr(r.repval, np.uint8),
                       arr(r.identity, np.float32),

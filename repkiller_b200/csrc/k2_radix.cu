@@ -30,7 +30,7 @@ constexpr int RS_ITEMS = RK_RS_ITEMS;
 #define RK_OS_THREADS 256
 #endif
 #ifndef RK_OS_LB
-#define RK_OS_LB 16
+#define RK_OS_LB 8
 #endif
 constexpr int OS_THREADS = RK_OS_THREADS;  // one-sweep pass CTA (a multiple of 256: one thread per digit does the prefix work)
 constexpr int OS_WARPS = OS_THREADS / 32;
@@ -300,15 +300,30 @@ __global__ void __launch_bounds__(OS_THREADS, RK_RS_MINBLOCKS)
   u32 valid_total = total;
   if (tid == mask) valid_total -= (u32)OS_TILE - nvalid;
 
-  // publish this tile's counts, look back over the predecessors, publish the inclusive prefix
+  // Publish this tile's counts at once, reorder the tile in shared memory (which needs no global offsets), and only
+  // then look back over the predecessors: by then more of them have published their inclusive prefix, so the walk
+  // is shorter, and its latency no longer sits between the ranking and the reordering of this tile.
   volatile u32 *my_state = state + (u64)tile * RADIX + tid;
+  if (digit_thread && tile != 0) *my_state = OS_AGG | valid_total;
+
+  const u32 dbase = block_excl_scan<OS_THREADS>(total, nullptr);
+  if (digit_thread) digit_base[tid] = dbase;
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 d = (key[j] >> shift) & mask;
+    const u32 pos = digit_base[d] + warp_cnt[w][d] + rnk[j];
+    skeys[pos] = key[j];
+    svals[pos] = val[j];
+  }
+
   u32 excl = 0;
   if (!digit_thread) {
     // threads beyond the 256 digits only help with loading, ranking and writing
   } else if (tile == 0) {
     *my_state = OS_PFX | valid_total;
   } else {
-    *my_state = OS_AGG | valid_total;
     // Batches of LB independent loads: the tiles of one wave start together and all sit in the AGG state, so the
     // walk back to the last published prefix is as long as the wave; one load in flight would cost an L2 round
     // trip per predecessor.
@@ -359,20 +374,7 @@ __global__ void __launch_bounds__(OS_THREADS, RK_RS_MINBLOCKS)
     *my_state = OS_PFX | (excl + valid_total);
   }
 
-  const u32 dbase = block_excl_scan<OS_THREADS>(total, nullptr);
-  if (digit_thread) {
-    digit_base[tid] = dbase;
-    gbase[tid] = digit_start[tid] + excl - dbase;
-  }
-  __syncthreads();
-
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    const u32 d = (key[j] >> shift) & mask;
-    const u32 pos = digit_base[d] + warp_cnt[w][d] + rnk[j];
-    skeys[pos] = key[j];
-    svals[pos] = val[j];
-  }
+  if (digit_thread) gbase[tid] = digit_start[tid] + excl - dbase;
   __syncthreads();
 
   for (u32 p = tid; p < nvalid; p += OS_THREADS) {

@@ -226,11 +226,12 @@ __device__ void dev_std_sort(P a, int n) {
   }
 }
 
-constexpr int GS_SMALL = 64;         // groups up to this size are ordered inside the tile kernel
 constexpr int GS_STABLE = 16;        // std::sort of <= 16 elements is one insertion sort == a stable sort by h
-constexpr int GS_SMEM_ELEMS = 6144;  // larger groups up to this size are sorted in shared memory (48 KB)
+constexpr int GS_WARP_CAP0 = 128;    // groups of 17..128 members: one warp each, 2 KB of shared memory per warp
+constexpr int GS_WARP_CAP = 1024;    // groups of 129..1024 members: one warp each, 17 KB per warp
+constexpr int GS_SMEM_ELEMS = 6144;  // beyond that one lane sorts: up to this size in shared memory (48 KB), else in global
 constexpr int OT_HEADS = 256;        // a CTA owns the groups whose head lies in its first 256 positions
-constexpr int OT_TILE = OT_HEADS + GS_SMALL;  // ... and those groups end before position 320: one thread per position
+constexpr int OT_TILE = OT_HEADS + 32;  // one thread per position; a group of <= 16 that starts before 256 ends before 272
 constexpr int OT_WARPS = OT_TILE / 32;
 
 // what the output line of a fragment needs besides its group: {h, file index, identity bits}
@@ -245,16 +246,14 @@ __device__ __forceinline__ void load_member(const OrderArgs &a, u32 j, u32 &r, u
   }
 }
 
-// K5b+c for groups of <= 64 members (all but a handful).  One thread per position of the gid-sorted list:
-//   * group boundaries from a ballot of gid changes;
-//   * <= 16 members: every member counts the members that sort before it (smaller h, or equal h and earlier) — the
-//     stable order libstdc++'s insertion sort produces — and drops its source position at that output slot;
-//   * 17..64 members (rare): the head thread runs the restated introsort on (h << 32 | tile position) words;
-//   * > 64: worklist of k_groupsort_large;
+// K5b+c for groups of <= 16 members (all but a few per cent).  One thread per position of the gid-sorted list:
+//   * group boundaries from a ballot of gid changes (32 positions back and forth are enough to tell "<= 16");
+//   * every member counts the members that sort before it (smaller h, or equal h and earlier) — the stable order
+//     libstdc++'s insertion sort produces — and drops its source position at that output slot;
+//   * larger groups go to the worklist of k_groupsort_warp;
 // then every thread writes the output line of its position.
 __global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
   __shared__ u32 s_gid[OT_TILE], s_h[OT_TILE], s_fidx[OT_TILE], s_ident[OT_TILE], s_perm[OT_TILE];
-  __shared__ u64 s_pk[OT_TILE];
   __shared__ u32 s_heads[OT_WARPS];
   __shared__ u32 s_prev;
   const u32 e = threadIdx.x, lane = e & 31, w = e >> 5;
@@ -277,35 +276,31 @@ __global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
   if (lane == 0) s_heads[w] = hb;
   const bool foreign0 = bs != 0 && s_prev == s_gid[0];
   __syncthreads();
-  // start: last head at or before e (64 positions back are enough); end: first head after e
+  // start: last head at or before e; end: first head after e.  A head that is more than a word away on either side
+  // means more than 16 members.
   u32 start = 0xFFFFFFFFu, end = 0xFFFFFFFFu;
   {
     const u32 own = hb & (0xFFFFFFFFu >> (31 - lane));
     u32 x;
     if (own) start = (w << 5) + 31 - __clz(own);
     else if (w >= 1 && (x = s_heads[w - 1]) != 0) start = ((w - 1) << 5) + 31 - __clz(x);
-    else if (w >= 2 && (x = s_heads[w - 2]) != 0) start = ((w - 2) << 5) + 31 - __clz(x);
     const u32 above = hb & (0xFFFFFFFEu << lane);
     if (above) end = (w << 5) + __ffs(above) - 1;
     else if (w + 1 < (u32)OT_WARPS && (x = s_heads[w + 1]) != 0) end = ((w + 1) << 5) + __ffs(x) - 1;
-    else if (w + 2 < (u32)OT_WARPS && (x = s_heads[w + 2]) != 0) end = ((w + 2) << 5) + __ffs(x) - 1;
   }
-  // No head within reach on either side means more than 64 members.  A group that starts before position 256 and
-  // shows no end inside the tile has at least 65 members too (the tile holds start+64).
-  const bool large = start == 0xFFFFFFFFu || end == 0xFFFFFFFFu || end - start > (u32)GS_SMALL;
-  const bool owned = valid && start != 0xFFFFFFFFu && start < (u32)OT_HEADS && !(start == 0 && foreign0);
-  const u32 n = large ? 0 : end - start;
-  if (valid && is_head && large && e < (u32)OT_HEADS && !(e == 0 && foreign0)) {
+  // (a group that starts before position 256 and shows no end inside the tile has more than 32 members)
+  const bool big = start == 0xFFFFFFFFu || end == 0xFFFFFFFFu || end - start > (u32)GS_STABLE;
+  if (valid && is_head && big && e < (u32)OT_HEADS && !(e == 0 && foreign0)) {
     const u32 slot = atomicAdd(a.work_count, 1u);
-    if (slot < a.work_cap) a.worklist[slot] = bs + e;
+    if (slot < a.work_cap[0]) a.worklist[0][slot] = bs + e;
     else atomicOr(a.err, ERR_WORKLIST);
   }
-  const bool mine = owned && !large;
-  const bool mid = mine && n > (u32)GS_STABLE && a.do_sort;
+  const bool mine = valid && !big && start < (u32)OT_HEADS && !(start == 0 && foreign0);
+  const u32 n = big ? 0 : end - start;
   if (mine) {
     if (n == 1 || !a.do_sort) {
       s_perm[e] = e;
-    } else if (n <= (u32)GS_STABLE) {
+    } else {
       const u32 h = s_h[e], me = e - start;
       u32 before = 0;
       for (u32 q = 0; q < n; ++q) {
@@ -313,16 +308,9 @@ __global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
         before += (o < h || (o == h && q < me)) ? 1u : 0u;
       }
       s_perm[start + before] = e;
-    } else {
-      s_pk[e] = ((u64)s_h[e] << 32) | e;
     }
   }
-  if (__syncthreads_or(mid)) {
-    if (mid && e == start) dev_std_sort(s_pk + start, (int)n);
-    __syncthreads();
-    if (mid) s_perm[e] = (u32)s_pk[e];
-    __syncthreads();
-  }
+  __syncthreads();
   if (mine) {
     const u32 src = s_perm[e], j = bs + e;
     a.out_order[j] = s_fidx[src];
@@ -332,17 +320,229 @@ __global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
   }
 }
 
-// one warp per large group; lane 0 runs the (inherently sequential) introsort, all lanes move the data
+// ---- the same std::sort, run by a whole warp on a group of 17..1024 members held in shared memory ------------------
+// __introsort_loop only ever compares against a pivot, so one __unguarded_partition is a pure function of two bit
+// masks over the range: GE (not less than the pivot) and LE (not greater).  Its two pointers stop at the k-th GE
+// position from the left and the k-th LE position from the right, swap them, and go on while the first lies left of
+// the second.  So, with f(c) = #GE before position c and g(c) = #LE at or after c:
+//     number of swaps K = max over c of min(f(c), g(c)),   swap k pairs listA[k] with listB[k]   (k < K),
+//     the returned cut  = min(listA[K], listB[K-1])         (listB[-1] = last; a pointer that finds nothing new stops on
+//                                                            the position of the last swap, which holds a stopping value).
+// All of it is ballots, popcounts and one scan over the 32-position chunks of the range.
+// __final_insertion_sort is a stable sort of whatever the partitions left, and it never moves an element out of its
+// final partition range (<= 16 elements, everything left of a cut is <= everything right of it): every element counts
+// the elements of its own range that must precede it.
+template <int CAP>
+struct WarpSortMem {
+  u64 a[CAP];      // the group, (h << 32 | index in the group)
+  u64 b[CAP];      // listA / listB during the partitions, the sorted group at the end
+  u32 gew[CAP / 32 + 1], lew[CAP / 32 + 1];  // GE / LE masks per chunk
+  u32 gep[CAP / 32 + 1], les[CAP / 32 + 1];  // #GE in earlier chunks / #LE in later chunks
+  u32 bounds[CAP / 32 + 1];                  // bit p: a final partition range starts at p
+};
+
+template <int CAP>
+__device__ void warp_std_sort(WarpSortMem<CAP> &m, int n, u32 lane) {
+  u64 *a = m.a;
+  u32 *listA = reinterpret_cast<u32 *>(m.b), *listB = listA + CAP;
+  for (int c = (int)lane; c <= (n >> 5); c += 32) m.bounds[c] = c == 0 ? 1u : 0u;
+  __syncwarp();
+  if (n > 16) {
+    int st_first[40], st_last[40], st_depth[40];  // explicit recursion: the larger side is stacked, depth <= lg n
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    int sp = 1;
+    st_first[0] = 0, st_last[0] = n, st_depth[0] = 2 * lg;
+    while (sp > 0) {
+      --sp;
+      int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+      while (last - first > 16) {
+        if (depth == 0) {  // __partial_sort(first, last, last): heap sort, sequential (adversarial inputs only)
+          if (lane == 0) {
+            SubArray sub{a + first};
+            dev_heap_sort(sub, last - first);
+          }
+          __syncwarp();
+          for (int p = first + (int)lane; p < last; p += 32) atomicOr(&m.bounds[p >> 5], 1u << (p & 31));  // keep its order
+          __syncwarp();
+          break;
+        }
+        --depth;
+        // __move_median_to_first(first, first+1, mid, last-1)
+        const int mid = first + (last - first) / 2;
+        const u64 vx = a[first + 1], vy = a[mid], vz = a[last - 1];
+        int pick;
+        if (hless(vx, vy)) pick = hless(vy, vz) ? mid : (hless(vx, vz) ? last - 1 : first + 1);
+        else pick = hless(vx, vz) ? first + 1 : (hless(vy, vz) ? last - 1 : mid);
+        __syncwarp();
+        if (lane == 0) swp(a, first, pick);
+        __syncwarp();
+        const u64 pivot = a[first];
+        // pass 1: masks of the range (first, last) per chunk of 32 positions
+        const int c0 = (first + 1) >> 5, c1 = (last - 1) >> 5;  // chunks c0..c1 (at most 33)
+        for (int c = c0; c <= c1; ++c) {
+          const int p = (c << 5) + (int)lane;
+          const bool in = p > first && p < last;
+          const u64 v = in ? a[p] : 0;
+          const u32 ge = __ballot_sync(0xFFFFFFFFu, in && !hless(v, pivot));
+          const u32 le = __ballot_sync(0xFFFFFFFFu, in && !hless(pivot, v));
+          if (lane == 0) m.gew[c - c0] = ge, m.lew[c - c0] = le;
+        }
+        __syncwarp();
+        // exclusive prefix of #GE from the left, exclusive suffix of #LE from the right, over the chunks
+        const int nch = c1 - c0 + 1;
+        int tot_ge = 0;
+        for (int base = 0; base < nch; base += 32) {  // (two rounds only when the range touches 33 chunks)
+          const int c = base + (int)lane;
+          int v = c < nch ? __popc(m.gew[c]) : 0;
+          const int mine_cnt = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if ((int)lane >= o) v += t;
+          }
+          if (c < nch) m.gep[c] = tot_ge + v - mine_cnt;
+          tot_ge += __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+        int tot_le = 0;
+        for (int base = 0; base < nch; base += 32) {
+          const int c = nch - 1 - (base + (int)lane);  // from the right
+          int v = c >= 0 ? __popc(m.lew[c]) : 0;
+          const int mine_cnt = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if ((int)lane >= o) v += t;
+          }
+          if (c >= 0) m.les[c] = tot_le + v - mine_cnt;
+          tot_le += __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+        __syncwarp();
+        // pass 2: position lists and K
+        int kmax = 0;
+        const u32 lt = lanemask_lt();
+        for (int c = 0; c < nch; ++c) {
+          const u32 ge = m.gew[c], le = m.lew[c];
+          const int p = ((c0 + c) << 5) + (int)lane;
+          const int f = (int)m.gep[c] + __popc(ge & lt);                // #GE before p
+          const int g = (int)m.les[c] + __popc(le & ~lt);               // #LE at or after p
+          if (p > first && p <= last) kmax = max(kmax, min(f, g));      // split points first+1 .. last
+          if ((ge >> lane) & 1u) listA[f] = (u32)p;
+          if ((le >> lane) & 1u) listB[g - 1] = (u32)p;                 // g-1 = #LE after p
+        }
+        // (a split point `last` that falls into a further chunk has g = 0 and cannot raise the maximum)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, o));
+        __syncwarp();
+        const int K = kmax;
+        const int cutA = K < tot_ge ? (int)listA[K] : 0x7FFFFFFF;
+        const int cutB = K > 0 ? (int)listB[K - 1] : last;
+        const int cut = min(cutA, cutB);
+        __syncwarp();
+        for (int k = (int)lane; k < K; k += 32) swp(a, (int)listA[k], (int)listB[k]);
+        if (lane == 0) atomicOr(&m.bounds[cut >> 5], 1u << (cut & 31));
+        __syncwarp();
+        // __introsort_loop(cut, last, depth) and last = cut: the two sides are independent, keep the smaller one
+        if (cut - first < last - cut) {
+          if (last - cut > 16 && sp < 40) st_first[sp] = cut, st_last[sp] = last, st_depth[sp] = depth, ++sp;
+          last = cut;
+        } else {
+          if (cut - first > 16 && sp < 40) st_first[sp] = first, st_last[sp] = cut, st_depth[sp] = depth, ++sp;
+          first = cut;
+        }
+      }
+    }
+  }
+  // __final_insertion_sort: stable by h inside every final range
+  for (int base = 0; base < n; base += 32) {
+    const int p = base + (int)lane;
+    if (p < n) {
+      const int wd = p >> 5;
+      const u32 own = m.bounds[wd] & (0xFFFFFFFFu >> (31 - (p & 31)));
+      int rs;  // ranges that are not kept verbatim have <= 16 elements: the start is in this word or the previous one
+      if (own) rs = (wd << 5) + 31 - __clz(own);
+      else rs = ((wd - 1) << 5) + 31 - __clz(m.bounds[wd - 1]);
+      const u64 v = a[p];
+      const u32 h = (u32)(v >> 32);
+      int before = 0, q = rs;
+      for (; q < p; ++q) before += ((u32)(a[q] >> 32) <= h) ? 1 : 0;                     // earlier: precedes when <=
+      for (q = p + 1; q < n && !((m.bounds[q >> 5] >> (q & 31)) & 1u); ++q)             // later, same range: when <
+        before += ((u32)(a[q] >> 32) < h) ? 1 : 0;
+      m.b[rs + before] = v;
+    }
+  }
+  __syncwarp();
+}
+
+// one warp per group of worklist LIST: up to CAP members here, larger ones are passed on to the next worklist
+template <int CAP, int WARPS, int LIST>
+__global__ void __launch_bounds__(WARPS * 32) k_groupsort_warp(OrderArgs a) {
+  extern __shared__ __align__(16) unsigned char gw_smem[];
+  const u32 lane = threadIdx.x & 31;
+  WarpSortMem<CAP> &mem = reinterpret_cast<WarpSortMem<CAP> *>(gw_smem)[threadIdx.x >> 5];
+  u32 *const count_in = a.work_count + 2 * LIST, *const count_out = a.work_count + 2 * (LIST + 1);
+  const u32 *const list_in = a.worklist[LIST];
+  u32 *const list_out = a.worklist[LIST + 1];
+  const u32 nseg = min(*count_in, a.work_cap[LIST]);
+  for (;;) {
+    u32 seg = 0;
+    if (lane == 0) seg = atomicAdd(count_in + 1, 1u);
+    seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
+    if (seg >= nseg) return;
+    const u32 start = list_in[seg];
+    const u32 g = a.sgid[start];
+    u32 end = start;
+    for (;;) {
+      const u32 idx = end + lane;
+      const bool same = idx < a.m && a.sgid[idx] == g;
+      const u32 bal = __ballot_sync(0xFFFFFFFFu, same);
+      end += __popc(bal);
+      if (bal != 0xFFFFFFFFu || end - start > (u32)CAP) break;
+    }
+    const u32 n = end - start;
+    if (n > (u32)CAP) {
+      if (lane == 0) {
+        const u32 slot = atomicAdd(count_out, 1u);
+        if (slot < a.work_cap[LIST + 1]) list_out[slot] = start;
+        else atomicOr(a.err, ERR_WORKLIST);
+      }
+      continue;
+    }
+    for (u32 t = lane; t < n; t += 32) {
+      u32 r, h, fidx, ident;
+      load_member(a, start + t, r, h, fidx, ident);
+      mem.a[t] = ((u64)h << 32) | t;
+    }
+    __syncwarp();
+    const u64 *sorted = mem.a;
+    if (a.do_sort) {
+      warp_std_sort(mem, (int)n, lane);
+      sorted = mem.b;
+    }
+    for (u32 t = lane; t < n; t += 32) {
+      u32 r, h, fidx, ident;
+      load_member(a, start + (u32)sorted[t], r, h, fidx, ident);
+      const u32 j = start + t;
+      a.out_order[j] = fidx;
+      a.out_gid[j] = g;
+      a.out_repval[j] = (u8)(t == 0 ? 1 : 2);  // commonFunctions.cpp:106-115
+      a.out_identity[j] = __uint_as_float(ident);
+    }
+    __syncwarp();
+  }
+}
+
+// groups of more than 1024 members: one warp each; lane 0 runs the sequential introsort, all lanes move the data
 __global__ void __launch_bounds__(32) k_groupsort_large(OrderArgs a) {
   __shared__ u64 buf[GS_SMEM_ELEMS];
   const u32 lane = threadIdx.x;
-  const u32 nseg = min(*a.work_count, a.work_cap);
+  const u32 nseg = min(a.work_count[4], a.work_cap[2]);
   for (;;) {
     u32 seg = 0;
-    if (lane == 0) seg = atomicAdd(a.work_count + 1, 1u);
+    if (lane == 0) seg = atomicAdd(a.work_count + 5, 1u);
     seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
     if (seg >= nseg) return;
-    const u32 start = a.worklist[seg];
+    const u32 start = a.worklist[2][seg];
     const u32 g = a.sgid[start];
     u32 end = start;
     for (;;) {
@@ -380,10 +580,12 @@ __global__ void __launch_bounds__(32) k_groupsort_large(OrderArgs a) {
   }
 }
 
+constexpr int GW0_WARPS = 8, GW1_WARPS = 4;
+
 int launch_order(const OrderArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
   const u32 m = a.m;
-  cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
+  cudaMemsetAsync(a.work_count, 0, 6 * sizeof(u32), st);
   {
     KScope ks(KID_GSORT_SMALL, st, m);
     k_order_tile<<<(m + OT_HEADS - 1) / OT_HEADS, OT_TILE, 0, st>>>(a);
@@ -391,9 +593,20 @@ int launch_order(const OrderArgs &a, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int smem0 = GW0_WARPS * (int)sizeof(WarpSortMem<GS_WARP_CAP0>), smem1 = GW1_WARPS * (int)sizeof(WarpSortMem<GS_WARP_CAP>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_groupsort_warp<GS_WARP_CAP, GW1_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    attr_set = true;
+  }
+  {
+    KScope ks(KID_GSORT_WARP, st, 0);
+    k_groupsort_warp<GS_WARP_CAP0, GW0_WARPS, 0><<<sms * 6, GW0_WARPS * 32, smem0, st>>>(a);
+    k_groupsort_warp<GS_WARP_CAP, GW1_WARPS, 1><<<sms * 3, GW1_WARPS * 32, smem1, st>>>(a);
+  }
   KScope ks(KID_GSORT_LARGE, st, 0);
   k_groupsort_large<<<sms * 4, 32, 0, st>>>(a);
-  return 2;
+  return 4;
 }
 
 }  // namespace rk

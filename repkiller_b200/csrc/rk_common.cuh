@@ -69,7 +69,7 @@ __device__ __forceinline__ u32 absdiff(u32 a, u32 b) { return a > b ? a - b : b 
 // ---- per-kernel timing (CUDA events around every launch; off unless rk_profile_enable) ---------------
 enum KernelId {
   KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
-  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_COUNT
+  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_COUNT
 };
 void prof_begin(int kid, cudaStream_t st, unsigned long long units);
 void prof_end(cudaStream_t st);
@@ -160,8 +160,11 @@ struct OrderArgs {
   u64 *packed;        // scratch m
   u32 m;
   int do_sort;
-  u32 *worklist, *work_count;
-  u32 work_cap;
+  // start positions of the groups of more than 16 / 128 / 1024 members; work_count[2*i] = entries of list i,
+  // work_count[2*i+1] = its pop cursor
+  u32 *worklist[3];
+  u32 *work_count;
+  u32 work_cap[3];
   u32 *out_order, *out_gid;
   u8 *out_repval;
   float *out_identity;
