@@ -63,7 +63,7 @@ struct Counters {  // small device block, mirrored in pinned host memory
   u32 pad;
   u32 work_x[2];
   u32 work_y[2];
-  u32 work_g[6];
+  u32 work_g[8];
 };
 
 }  // namespace
@@ -117,9 +117,9 @@ struct rk_ctx {
   u32 *xm_bits = nullptr;
   u32 *parent = nullptr, *gid_rank = nullptr, *h = nullptr, *sgid = nullptr, *srank = nullptr;
   void *forest_work = nullptr;
-  u64 *packed = nullptr;
-  u32 *worklist = nullptr, *worklist1 = nullptr, *worklist2 = nullptr;
-  u32 work_cap = 0, work_cap1 = 0, work_cap2 = 0;
+  void *order_scratch = nullptr;
+  u32 *worklist = nullptr;
+  u32 work_cap = 0;
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr;
   u32 *out_order = nullptr, *out_gid = nullptr;
   u8 *out_repval = nullptr;
@@ -182,13 +182,9 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   c->sgid = (u32 *)take(n1 * 4);
   c->srank = (u32 *)take(n1 * 4);
   c->forest_work = take(forest_work_bytes((u32)n1));
-  c->packed = (u64 *)take(n1 * 8);
-  c->work_cap = (u32)(n1 / 16 + 2);   // segments of more than 32 fragments (K3), groups of more than 16 members (K5)
+  c->order_scratch = take(order_scratch_bytes(n1));
+  c->work_cap = (u32)(n1 / 32 + 2);   // segments of more than 32 fragments (K3)
   c->worklist = (u32 *)take((u64)c->work_cap * 4);
-  c->work_cap1 = (u32)(n1 / 128 + 2);
-  c->worklist1 = (u32 *)take((u64)c->work_cap1 * 4);
-  c->work_cap2 = (u32)(n1 / 1024 + 2);
-  c->worklist2 = (u32 *)take((u64)c->work_cap2 * 4);
   c->ent_rank = (u32 *)take(n1 * 4);
   c->ent_c = (u32 *)take(n1 * 4);
   c->ent_len = (u32 *)take(n1 * 4);
@@ -263,9 +259,8 @@ namespace {
 u64 run_order(rk_ctx *ctx, unsigned flags) {
   OrderArgs oa{};
   oa.sgid = ctx->sgid, oa.srank = ctx->srank, oa.hfi_r = ctx->hfi_r;
-  oa.packed = ctx->packed, oa.m = ctx->m, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1;
-  oa.worklist[0] = ctx->worklist, oa.worklist[1] = ctx->worklist1, oa.worklist[2] = ctx->worklist2;
-  oa.work_cap[0] = ctx->work_cap, oa.work_cap[1] = ctx->work_cap1, oa.work_cap[2] = ctx->work_cap2;
+  oa.m = ctx->m, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1;
+  order_carve(oa, ctx->order_scratch, ctx->n);
   oa.work_count = ctx->d_cnt->work_g;
   oa.out_order = ctx->out_order, oa.out_gid = ctx->out_gid, oa.out_repval = ctx->out_repval, oa.out_identity = ctx->out_identity;
   oa.err = &ctx->d_cnt->err;
@@ -794,15 +789,13 @@ int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *s
   CK(cudaSetDevice(ctx->device));
   ProfGuard pg(ctx);
   const u64 m1 = m ? m : 1;
-  const u32 cap = (u32)(m1 / 16 + 2), cap1 = (u32)(m1 / 128 + 2), cap2 = (u32)(m1 / 1024 + 2);
   void *scr = nullptr;
-  const int rc = st_scratch(ctx, m1 * 8 + ((u64)cap + cap1 + cap2) * 4 + 1024, &scr);
+  const int rc = st_scratch(ctx, order_scratch_bytes(m1), &scr);
   if (rc != RK_OK) return rc;
   OrderArgs oa{};
   oa.sgid = sgid, oa.srank = nullptr, oa.hfi_r = nullptr, oa.h = sh, oa.fidx_r = sfidx, oa.identity_r = sident;
-  oa.packed = (u64 *)scr, oa.m = (u32)m, oa.do_sort = do_sort;
-  oa.worklist[0] = (u32 *)((u8 *)scr + m1 * 8), oa.worklist[1] = oa.worklist[0] + cap, oa.worklist[2] = oa.worklist[1] + cap1;
-  oa.work_cap[0] = cap, oa.work_cap[1] = cap1, oa.work_cap[2] = cap2;
+  oa.m = (u32)m, oa.do_sort = do_sort;
+  order_carve(oa, scr, m1);
   oa.work_count = ctx->st_cnt->work_g;
   oa.out_order = out_order, oa.out_gid = out_gid, oa.out_repval = out_repval, oa.out_identity = out_identity;
   oa.err = &ctx->st_cnt->err;

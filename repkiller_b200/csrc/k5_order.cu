@@ -229,7 +229,6 @@ __device__ void dev_std_sort(P a, int n) {
 constexpr int GS_STABLE = 16;        // std::sort of <= 16 elements is one insertion sort == a stable sort by h
 constexpr int GS_WARP_CAP0 = 128;    // groups of 17..128 members: one warp each, 2 KB of shared memory per warp
 constexpr int GS_WARP_CAP = 1024;    // groups of 129..1024 members: one warp each, 17 KB per warp
-constexpr int GS_SMEM_ELEMS = 6144;  // beyond that one lane sorts: up to this size in shared memory (48 KB), else in global
 constexpr int OT_HEADS = 256;        // a CTA owns the groups whose head lies in its first 256 positions
 constexpr int OT_TILE = OT_HEADS + 32;  // one thread per position; a group of <= 16 that starts before 256 ends before 272
 constexpr int OT_WARPS = OT_TILE / 32;
@@ -332,27 +331,116 @@ __global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
 // __final_insertion_sort is a stable sort of whatever the partitions left, and it never moves an element out of its
 // final partition range (<= 16 elements, everything left of a cut is <= everything right of it): every element counts
 // the elements of its own range that must precede it.
-template <int CAP>
-struct WarpSortMem {
-  u64 a[CAP];      // the group, (h << 32 | index in the group)
-  u64 b[CAP];      // listA / listB during the partitions, the sorted group at the end
-  u32 gew[CAP / 32 + 1], lew[CAP / 32 + 1];  // GE / LE masks per chunk
-  u32 gep[CAP / 32 + 1], les[CAP / 32 + 1];  // #GE in earlier chunks / #LE in later chunks
-  u32 bounds[CAP / 32 + 1];                  // bit p: a final partition range starts at p
+struct SortPtrs {  // where one warp keeps a range while it partitions it (shared or global memory)
+  u64 *a;
+  u32 *listA, *listB;           // positions of the GE / LE elements, by rank from the left / from the right
+  u32 *gew, *lew, *gep, *les;   // per chunk: GE / LE masks, #GE in earlier chunks, #LE in later chunks
 };
 
-template <int CAP>
-__device__ void warp_std_sort(WarpSortMem<CAP> &m, int n, u32 lane) {
+// __unguarded_partition_pivot(first, last) by a warp: median of three to *first, partition of (first, last) around it;
+// returns the cut.  Every lane gets the same result.
+__device__ int warp_partition(const SortPtrs &m, int first, int last, u32 lane) {
   u64 *a = m.a;
-  u32 *listA = reinterpret_cast<u32 *>(m.b), *listB = listA + CAP;
+  // __move_median_to_first(first, first+1, mid, last-1)
+  const int mid = first + (last - first) / 2;
+  const u64 vx = a[first + 1], vy = a[mid], vz = a[last - 1];
+  int pick;
+  if (hless(vx, vy)) pick = hless(vy, vz) ? mid : (hless(vx, vz) ? last - 1 : first + 1);
+  else pick = hless(vx, vz) ? first + 1 : (hless(vy, vz) ? last - 1 : mid);
+  __syncwarp();
+  if (lane == 0) swp(a, first, pick);
+  __syncwarp();
+  const u64 pivot = a[first];
+  // pass 1: masks of the range (first, last) per chunk of 32 positions
+  const int c0 = (first + 1) >> 5, c1 = (last - 1) >> 5;
+  const int nch = c1 - c0 + 1;
+  for (int c = 0; c < nch; ++c) {
+    const int p = ((c0 + c) << 5) + (int)lane;
+    const bool in = p > first && p < last;
+    const u64 v = in ? a[p] : 0;
+    const u32 ge = __ballot_sync(0xFFFFFFFFu, in && !hless(v, pivot));
+    const u32 le = __ballot_sync(0xFFFFFFFFu, in && !hless(pivot, v));
+    if (lane == 0) m.gew[c] = ge, m.lew[c] = le;
+  }
+  __syncwarp();
+  // exclusive prefix of #GE from the left, exclusive suffix of #LE from the right, over the chunks
+  int tot_ge = 0;
+  for (int base = 0; base < nch; base += 32) {
+    const int c = base + (int)lane;
+    int v = c < nch ? __popc(m.gew[c]) : 0;
+    const int own = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if ((int)lane >= o) v += t;
+    }
+    if (c < nch) m.gep[c] = tot_ge + v - own;
+    tot_ge += __shfl_sync(0xFFFFFFFFu, v, 31);
+  }
+  int tot_le = 0;
+  for (int base = 0; base < nch; base += 32) {
+    const int c = nch - 1 - (base + (int)lane);  // from the right
+    int v = c >= 0 ? __popc(m.lew[c]) : 0;
+    const int own = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if ((int)lane >= o) v += t;
+    }
+    if (c >= 0) m.les[c] = tot_le + v - own;
+    tot_le += __shfl_sync(0xFFFFFFFFu, v, 31);
+  }
+  __syncwarp();
+  // pass 2: position lists and K
+  int kmax = 0;
+  const u32 lt = lanemask_lt();
+  for (int c = 0; c < nch; ++c) {
+    const u32 ge = m.gew[c], le = m.lew[c];
+    const int p = ((c0 + c) << 5) + (int)lane;
+    const int f = (int)m.gep[c] + __popc(ge & lt);            // #GE before p
+    const int g = (int)m.les[c] + __popc(le & ~lt);           // #LE at or after p
+    if (p > first && p <= last) kmax = max(kmax, min(f, g));  // split points first+1 .. last
+    if ((ge >> lane) & 1u) m.listA[f] = (u32)p;
+    if ((le >> lane) & 1u) m.listB[g - 1] = (u32)p;           // g-1 = #LE after p
+  }
+  // (a split point `last` that falls into a further chunk has g = 0 and cannot raise the maximum)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, o));
+  __syncwarp();
+  const int K = kmax;
+  const int cutA = K < tot_ge ? (int)m.listA[K] : 0x7FFFFFFF;
+  const int cutB = K > 0 ? (int)m.listB[K - 1] : last;
+  __syncwarp();
+  for (int k = (int)lane; k < K; k += 32) swp(a, (int)m.listA[k], (int)m.listB[k]);
+  __syncwarp();
+  return min(cutA, cutB);
+}
+
+template <int CAP>
+struct WarpSortMem {
+  u64 a[CAP];      // the range, (h << 32 | index in the group)
+  u64 b[CAP];      // listA / listB during the partitions, the sorted range at the end
+  u32 gew[CAP / 32 + 1], lew[CAP / 32 + 1], gep[CAP / 32 + 1], les[CAP / 32 + 1];
+  u32 bounds[CAP / 32 + 1];  // bit p: a final partition range starts at p
+};
+
+// std::sort of m.a[0..n) into m.b[0..n).  depth < 0: a whole group (depth limit 2*lg n); otherwise a range that the
+// giant-group kernel split off, with the depth limit it had reached.
+template <int CAP>
+__device__ void warp_std_sort(WarpSortMem<CAP> &m, int n, u32 lane, int depth0) {
+  u64 *a = m.a;
+  SortPtrs sp_{m.a, reinterpret_cast<u32 *>(m.b), reinterpret_cast<u32 *>(m.b) + CAP, m.gew, m.lew, m.gep, m.les};
   for (int c = (int)lane; c <= (n >> 5); c += 32) m.bounds[c] = c == 0 ? 1u : 0u;
   __syncwarp();
   if (n > 16) {
     int st_first[40], st_last[40], st_depth[40];  // explicit recursion: the larger side is stacked, depth <= lg n
-    int lg = 0;
-    for (int t = n; t > 1; t >>= 1) ++lg;
+    if (depth0 < 0) {
+      int lg = 0;
+      for (int t = n; t > 1; t >>= 1) ++lg;
+      depth0 = 2 * lg;
+    }
     int sp = 1;
-    st_first[0] = 0, st_last[0] = n, st_depth[0] = 2 * lg;
+    st_first[0] = 0, st_last[0] = n, st_depth[0] = depth0;
     while (sp > 0) {
       --sp;
       int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
@@ -368,78 +456,7 @@ __device__ void warp_std_sort(WarpSortMem<CAP> &m, int n, u32 lane) {
           break;
         }
         --depth;
-        // __move_median_to_first(first, first+1, mid, last-1)
-        const int mid = first + (last - first) / 2;
-        const u64 vx = a[first + 1], vy = a[mid], vz = a[last - 1];
-        int pick;
-        if (hless(vx, vy)) pick = hless(vy, vz) ? mid : (hless(vx, vz) ? last - 1 : first + 1);
-        else pick = hless(vx, vz) ? first + 1 : (hless(vy, vz) ? last - 1 : mid);
-        __syncwarp();
-        if (lane == 0) swp(a, first, pick);
-        __syncwarp();
-        const u64 pivot = a[first];
-        // pass 1: masks of the range (first, last) per chunk of 32 positions
-        const int c0 = (first + 1) >> 5, c1 = (last - 1) >> 5;  // chunks c0..c1 (at most 33)
-        for (int c = c0; c <= c1; ++c) {
-          const int p = (c << 5) + (int)lane;
-          const bool in = p > first && p < last;
-          const u64 v = in ? a[p] : 0;
-          const u32 ge = __ballot_sync(0xFFFFFFFFu, in && !hless(v, pivot));
-          const u32 le = __ballot_sync(0xFFFFFFFFu, in && !hless(pivot, v));
-          if (lane == 0) m.gew[c - c0] = ge, m.lew[c - c0] = le;
-        }
-        __syncwarp();
-        // exclusive prefix of #GE from the left, exclusive suffix of #LE from the right, over the chunks
-        const int nch = c1 - c0 + 1;
-        int tot_ge = 0;
-        for (int base = 0; base < nch; base += 32) {  // (two rounds only when the range touches 33 chunks)
-          const int c = base + (int)lane;
-          int v = c < nch ? __popc(m.gew[c]) : 0;
-          const int mine_cnt = v;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
-            if ((int)lane >= o) v += t;
-          }
-          if (c < nch) m.gep[c] = tot_ge + v - mine_cnt;
-          tot_ge += __shfl_sync(0xFFFFFFFFu, v, 31);
-        }
-        int tot_le = 0;
-        for (int base = 0; base < nch; base += 32) {
-          const int c = nch - 1 - (base + (int)lane);  // from the right
-          int v = c >= 0 ? __popc(m.lew[c]) : 0;
-          const int mine_cnt = v;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
-            if ((int)lane >= o) v += t;
-          }
-          if (c >= 0) m.les[c] = tot_le + v - mine_cnt;
-          tot_le += __shfl_sync(0xFFFFFFFFu, v, 31);
-        }
-        __syncwarp();
-        // pass 2: position lists and K
-        int kmax = 0;
-        const u32 lt = lanemask_lt();
-        for (int c = 0; c < nch; ++c) {
-          const u32 ge = m.gew[c], le = m.lew[c];
-          const int p = ((c0 + c) << 5) + (int)lane;
-          const int f = (int)m.gep[c] + __popc(ge & lt);                // #GE before p
-          const int g = (int)m.les[c] + __popc(le & ~lt);               // #LE at or after p
-          if (p > first && p <= last) kmax = max(kmax, min(f, g));      // split points first+1 .. last
-          if ((ge >> lane) & 1u) listA[f] = (u32)p;
-          if ((le >> lane) & 1u) listB[g - 1] = (u32)p;                 // g-1 = #LE after p
-        }
-        // (a split point `last` that falls into a further chunk has g = 0 and cannot raise the maximum)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, o));
-        __syncwarp();
-        const int K = kmax;
-        const int cutA = K < tot_ge ? (int)listA[K] : 0x7FFFFFFF;
-        const int cutB = K > 0 ? (int)listB[K - 1] : last;
-        const int cut = min(cutA, cutB);
-        __syncwarp();
-        for (int k = (int)lane; k < K; k += 32) swp(a, (int)listA[k], (int)listB[k]);
+        const int cut = warp_partition(sp_, first, last, lane);
         if (lane == 0) atomicOr(&m.bounds[cut >> 5], 1u << (cut & 31));
         __syncwarp();
         // __introsort_loop(cut, last, depth) and last = cut: the two sides are independent, keep the smaller one
@@ -465,13 +482,40 @@ __device__ void warp_std_sort(WarpSortMem<CAP> &m, int n, u32 lane) {
       const u64 v = a[p];
       const u32 h = (u32)(v >> 32);
       int before = 0, q = rs;
-      for (; q < p; ++q) before += ((u32)(a[q] >> 32) <= h) ? 1 : 0;                     // earlier: precedes when <=
-      for (q = p + 1; q < n && !((m.bounds[q >> 5] >> (q & 31)) & 1u); ++q)             // later, same range: when <
+      for (; q < p; ++q) before += ((u32)(a[q] >> 32) <= h) ? 1 : 0;          // earlier: precedes when <=
+      for (q = p + 1; q < n && !((m.bounds[q >> 5] >> (q & 31)) & 1u); ++q)  // later, same range: when <
         before += ((u32)(a[q] >> 32) < h) ? 1 : 0;
       m.b[rs + before] = v;
     }
   }
   __syncwarp();
+}
+
+// members of the group [start, end) of the gid-sorted list
+__device__ __forceinline__ u32 group_end(const OrderArgs &a, u32 start, u32 lane, u32 stop_after) {
+  const u32 g = a.sgid[start];
+  u32 end = start;
+  for (;;) {
+    const u32 idx = end + lane;
+    const bool same = idx < a.m && a.sgid[idx] == g;
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, same);
+    end += __popc(bal);  // sorted: the matching lanes are a prefix
+    if (bal != 0xFFFFFFFFu || end - start > stop_after) break;
+  }
+  return end;
+}
+
+// output lines gstart+first .. of a group from the sorted (h, member index) words
+__device__ __forceinline__ void emit_sorted(const OrderArgs &a, const u64 *sorted, u32 gstart, u32 first, u32 n, u32 g, u32 lane) {
+  for (u32 t = lane; t < n; t += 32) {
+    u32 r, h, fidx, ident;
+    load_member(a, gstart + (u32)sorted[t], r, h, fidx, ident);
+    const u32 j = gstart + first + t;
+    a.out_order[j] = fidx;
+    a.out_gid[j] = g;
+    a.out_repval[j] = (u8)(first + t == 0 ? 1 : 2);  // commonFunctions.cpp:106-115
+    a.out_identity[j] = __uint_as_float(ident);
+  }
 }
 
 // one warp per group of worklist LIST: up to CAP members here, larger ones are passed on to the next worklist
@@ -490,16 +534,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_groupsort_warp(OrderArgs a) {
     seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
     if (seg >= nseg) return;
     const u32 start = list_in[seg];
-    const u32 g = a.sgid[start];
-    u32 end = start;
-    for (;;) {
-      const u32 idx = end + lane;
-      const bool same = idx < a.m && a.sgid[idx] == g;
-      const u32 bal = __ballot_sync(0xFFFFFFFFu, same);
-      end += __popc(bal);
-      if (bal != 0xFFFFFFFFu || end - start > (u32)CAP) break;
-    }
-    const u32 n = end - start;
+    const u32 n = group_end(a, start, lane, CAP) - start;
     if (n > (u32)CAP) {
       if (lane == 0) {
         const u32 slot = atomicAdd(count_out, 1u);
@@ -516,26 +551,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_groupsort_warp(OrderArgs a) {
     __syncwarp();
     const u64 *sorted = mem.a;
     if (a.do_sort) {
-      warp_std_sort(mem, (int)n, lane);
+      warp_std_sort(mem, (int)n, lane, -1);
       sorted = mem.b;
     }
-    for (u32 t = lane; t < n; t += 32) {
-      u32 r, h, fidx, ident;
-      load_member(a, start + (u32)sorted[t], r, h, fidx, ident);
-      const u32 j = start + t;
-      a.out_order[j] = fidx;
-      a.out_gid[j] = g;
-      a.out_repval[j] = (u8)(t == 0 ? 1 : 2);  // commonFunctions.cpp:106-115
-      a.out_identity[j] = __uint_as_float(ident);
-    }
+    emit_sorted(a, sorted, start, 0, n, a.sgid[start], lane);
     __syncwarp();
   }
 }
 
-// groups of more than 1024 members: one warp each; lane 0 runs the sequential introsort, all lanes move the data
-__global__ void __launch_bounds__(32) k_groupsort_large(OrderArgs a) {
-  __shared__ u64 buf[GS_SMEM_ELEMS];
-  const u32 lane = threadIdx.x;
+// Groups of more than 1024 members (repeat families of 10^4 and more fragments).  One warp runs the top of the
+// introsort recursion on the group in global memory — the same partition routine, its lists and masks in global
+// scratch — and hands every range of <= 1024 elements, with the depth limit reached there, to k_rangesort_warp.
+constexpr u32 RANGE_FROZEN = 0x80000000u;  // the range is final as it stands (heap-sorted, or do_sort == 0)
+
+__device__ __forceinline__ void push_range(const OrderArgs &a, u32 gstart, u32 first, u32 last, u32 depth, u32 lane) {
+  if (lane == 0) {
+    const u32 slot = atomicAdd(a.work_count + 6, 1u);
+    if (slot < a.range_cap) a.ranges[slot] = make_uint4(gstart, first, last, depth);
+    else atomicOr(a.err, ERR_WORKLIST);
+  }
+}
+
+template <int LEAF>
+__global__ void __launch_bounds__(128) k_giant_split(OrderArgs a) {
+  const u32 lane = threadIdx.x & 31;
   const u32 nseg = min(a.work_count[4], a.work_cap[2]);
   for (;;) {
     u32 seg = 0;
@@ -543,49 +582,112 @@ __global__ void __launch_bounds__(32) k_groupsort_large(OrderArgs a) {
     seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
     if (seg >= nseg) return;
     const u32 start = a.worklist[2][seg];
-    const u32 g = a.sgid[start];
-    u32 end = start;
-    for (;;) {
-      const u32 idx = end + lane;
-      const bool same = idx < a.m && a.sgid[idx] == g;
-      const u32 bal = __ballot_sync(0xFFFFFFFFu, same);
-      end += __popc(bal);
-      if (bal != 0xFFFFFFFFu) break;
-    }
-    const u32 n = end - start;
-    u64 *arr = n <= (u32)GS_SMEM_ELEMS ? buf : a.packed + start;  // beyond 48 KB: in the global scratch
+    const u32 n = group_end(a, start, lane, 0xFFFFFFFFu) - start;
+    u64 *arr = a.packed + start;
     for (u32 t = lane; t < n; t += 32) {
       u32 r, h, fidx, ident;
       load_member(a, start + t, r, h, fidx, ident);
-      arr[t] = ((u64)h << 32) | r;
+      arr[t] = ((u64)h << 32) | t;
     }
     __syncwarp();
-    if (lane == 0 && a.do_sort) dev_std_sort(arr, (int)n);
-    __syncwarp();
-    for (u32 t = lane; t < n; t += 32) {
-      const u32 r = (u32)arr[t], j = start + t;
-      u32 fidx, ident;
-      if (a.srank) {
-        const uint4 rec = a.hfi_r[r];
-        fidx = rec.y, ident = rec.z;
-      } else {
-        fidx = a.fidx_r[r], ident = __float_as_uint(a.identity_r[r]);
+    if (!a.do_sort) {
+      push_range(a, start, 0, n, RANGE_FROZEN, lane);
+      continue;
+    }
+    // scratch of this group: n/16 >= n/32 + 2 chunk slots from start/16 on never reach the next giant group's
+    const u64 cs = start >> 4;
+    SortPtrs sp_{arr, reinterpret_cast<u32 *>(a.packed2 + start), reinterpret_cast<u32 *>(a.packed2 + start) + n,
+                 a.chunk_words + cs, a.chunk_words + a.chunk_stride + cs, a.chunk_words + 2 * a.chunk_stride + cs,
+                 a.chunk_words + 3 * a.chunk_stride + cs};
+    int st_first[40], st_last[40], st_depth[40];
+    int lg = 0;
+    for (u32 t = n; t > 1; t >>= 1) ++lg;
+    int sp = 1;
+    st_first[0] = 0, st_last[0] = (int)n, st_depth[0] = 2 * lg;
+    while (sp > 0) {
+      --sp;
+      int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+      for (;;) {
+        if (last - first <= LEAF) {
+          push_range(a, start, (u32)first, (u32)last, (u32)depth, lane);
+          break;
+        }
+        if (depth == 0) {
+          if (lane == 0) {
+            SubArray sub{arr + first};
+            dev_heap_sort(sub, last - first);
+          }
+          __syncwarp();
+          push_range(a, start, (u32)first, (u32)last, RANGE_FROZEN, lane);
+          break;
+        }
+        --depth;
+        const int cut = warp_partition(sp_, first, last, lane);
+        // the larger side is stacked (or handed over when it is a leaf), the smaller one continues
+        int of, ol;
+        if (cut - first < last - cut) of = cut, ol = last, last = cut;
+        else of = first, ol = cut, first = cut;
+        if (ol - of <= LEAF) push_range(a, start, (u32)of, (u32)ol, (u32)depth, lane);
+        else if (sp < 40) st_first[sp] = of, st_last[sp] = ol, st_depth[sp] = depth, ++sp;
       }
-      a.out_order[j] = fidx;
-      a.out_gid[j] = g;
-      a.out_repval[j] = (u8)(t == 0 ? 1 : 2);
-      a.out_identity[j] = __uint_as_float(ident);
     }
+  }
+}
+
+// one warp per range handed over by k_giant_split: the rest of its introsort recursion, the final insertion sort,
+// and the output lines of the range
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_rangesort_warp(OrderArgs a) {
+  extern __shared__ __align__(16) unsigned char gw_smem[];
+  const u32 lane = threadIdx.x & 31;
+  WarpSortMem<CAP> &mem = reinterpret_cast<WarpSortMem<CAP> *>(gw_smem)[threadIdx.x >> 5];
+  const u32 nseg = min(a.work_count[6], a.range_cap);
+  for (;;) {
+    u32 seg = 0;
+    if (lane == 0) seg = atomicAdd(a.work_count + 7, 1u);
+    seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
+    if (seg >= nseg) return;
+    const uint4 it = a.ranges[seg];
+    const u32 gstart = it.x, first = it.y, n = it.z - it.y;
+    const u32 g = a.sgid[gstart];
+    const u64 *src = a.packed + gstart + first;
+    if (it.w == RANGE_FROZEN || n > (u32)CAP) {  // (n > CAP only for frozen ranges)
+      emit_sorted(a, src, gstart, first, n, g, lane);
+      continue;
+    }
+    for (u32 t = lane; t < n; t += 32) mem.a[t] = src[t];
+    __syncwarp();
+    warp_std_sort(mem, (int)n, lane, (int)it.w);
+    emit_sorted(a, mem.b, gstart, first, n, g, lane);
     __syncwarp();
   }
 }
 
 constexpr int GW0_WARPS = 8, GW1_WARPS = 4;
 
+// scratch of the order stage: packed (h, index) words of the giant groups, their lists, chunk words, range and group lists
+u64 order_scratch_bytes(u64 m) {
+  const u64 m1 = m ? m : 1;
+  return m1 * 8 + m1 * 8 + (m1 / 8 + 64) * 16 + 4 * (m1 / 16 + 2) * 4 + (m1 / 16 + 2 + m1 / 128 + 2 + m1 / 1024 + 2) * 4 + 256;
+}
+void order_carve(OrderArgs &a, void *scratch, u64 m) {
+  const u64 m1 = m ? m : 1;
+  u8 *p = (u8 *)scratch;
+  a.packed = (u64 *)p, p += m1 * 8;
+  a.packed2 = (u64 *)p, p += m1 * 8;
+  a.ranges = (uint4 *)p, a.range_cap = (u32)(m1 / 8 + 64), p += (u64)a.range_cap * 16;
+  a.chunk_stride = m1 / 16 + 2;
+  a.chunk_words = (u32 *)p, p += 4 * a.chunk_stride * 4;
+  a.work_cap[0] = (u32)(m1 / 16 + 2), a.work_cap[1] = (u32)(m1 / 128 + 2), a.work_cap[2] = (u32)(m1 / 1024 + 2);
+  a.worklist[0] = (u32 *)p, p += (u64)a.work_cap[0] * 4;
+  a.worklist[1] = (u32 *)p, p += (u64)a.work_cap[1] * 4;
+  a.worklist[2] = (u32 *)p;
+}
+
 int launch_order(const OrderArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
   const u32 m = a.m;
-  cudaMemsetAsync(a.work_count, 0, 6 * sizeof(u32), st);
+  cudaMemsetAsync(a.work_count, 0, 8 * sizeof(u32), st);
   {
     KScope ks(KID_GSORT_SMALL, st, m);
     k_order_tile<<<(m + OT_HEADS - 1) / OT_HEADS, OT_TILE, 0, st>>>(a);
@@ -597,6 +699,7 @@ int launch_order(const OrderArgs &a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_groupsort_warp<GS_WARP_CAP, GW1_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    cudaFuncSetAttribute(k_rangesort_warp<GS_WARP_CAP, GW1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     attr_set = true;
   }
   {
@@ -605,8 +708,9 @@ int launch_order(const OrderArgs &a, cudaStream_t st) {
     k_groupsort_warp<GS_WARP_CAP, GW1_WARPS, 1><<<sms * 3, GW1_WARPS * 32, smem1, st>>>(a);
   }
   KScope ks(KID_GSORT_LARGE, st, 0);
-  k_groupsort_large<<<sms * 4, 32, 0, st>>>(a);
-  return 4;
+  k_giant_split<GS_WARP_CAP><<<sms * 4, 128, 0, st>>>(a);
+  k_rangesort_warp<GS_WARP_CAP, GW1_WARPS><<<sms * 3, GW1_WARPS * 32, smem1, st>>>(a);
+  return 5;
 }
 
 }  // namespace rk

@@ -157,11 +157,16 @@ struct OrderArgs {
   const u32 *h;
   const u32 *fidx_r;
   const float *identity_r;
-  u64 *packed;        // scratch m
+  // scratch of the giant groups (order_carve): (h, index) words, position lists, chunk words, ranges handed to warps
+  u64 *packed, *packed2;
+  u32 *chunk_words;
+  u64 chunk_stride;
+  uint4 *ranges;
+  u32 range_cap;
   u32 m;
   int do_sort;
   // start positions of the groups of more than 16 / 128 / 1024 members; work_count[2*i] = entries of list i,
-  // work_count[2*i+1] = its pop cursor
+  // work_count[2*i+1] = its pop cursor; work_count[6], [7]: the same for `ranges`
   u32 *worklist[3];
   u32 *work_count;
   u32 work_cap[3];
@@ -170,6 +175,8 @@ struct OrderArgs {
   float *out_identity;
   u32 *err;
 };
+u64 order_scratch_bytes(u64 m);
+void order_carve(OrderArgs &a, void *scratch, u64 m);  // sets packed .. worklist, work_cap
 int launch_order(const OrderArgs &a, cudaStream_t st);
 
 }  // namespace rk
