@@ -31,8 +31,8 @@ METRIC = "fragments grouped/sec (device-timed)"
 UNIT = "fragments/s"
 CPU_SAMPLE_N = 1_000_000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {  # profiles/r01_ncu_full_top_kernels.json (C2, 10M fragments)
-    "k_match_small": 646479104, "k_radix_scatter": 100497692, "k_order_tile": 571010048, "k_keys": 1136891904,
+NCU_TRAFFIC = {  # profiles/r01b_ncu_full_top_kernels.json (C2, 10M fragments), mean over the launches of a step
+    "k_match_small": 470000000, "k_radix_scatter": 98000000, "k_order_tile": 425000000, "k_keys": 1427000000,
 }
 
 
@@ -168,15 +168,15 @@ class ClockSampler:
 
 # Algorithmic HBM bytes per unit a kernel processes: what it must read and write once.
 ALG_BYTES_PER_UNIT = {
-    "k_decode": 109 + 21,        # record in; xs, ys, len, key0 u32 + flags u8 + identity f32 out
+    "k_decode": 109 + 36,        # record in; 32-byte {xs, ys, len, flags, identity} record + key0 u32 out
     "k_radix_hist": 4,           # one read of the keys for all digit histograms of a sort
     "k_radix_scatter": 16,       # (key, value) in, (key, value) out, per pass
-    "k_keys": 4 + 13 + 24,       # file index, gather of xs/ys/len/flags, rank-order SoA + two keys out
-    "k_match_small": 22,         # key, rank, center, length (+ X flag) in, owner out
+    "k_keys": 4 + 32 + 32,       # file index, one 32-byte record gather; {c,len} x 2, ys, kx, ky, identity out
+    "k_match_small": 20,         # key, rank, {center, length} in, owner out (+ 1 bit per rank of the X-match map)
     "k_chase": 12,
     "k_scan": 12,
-    "k_hkey": 16,
-    "k_order_tile": 8 + 4 + 4 + 4 + 4 + 13,   # gid, rank, h, file index, identity in; four output arrays out
+    "k_hkey": 16 + 20,           # bucket key, ys, file index, identity in; h + 16-byte {h, fidx, identity} record out
+    "k_order_tile": 8 + 16 + 13, # gid, rank, one 16-byte record gather in; four output arrays out
 }
 
 

@@ -112,6 +112,22 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
  * rk_group with RK_F_NO_SORT, orders the members of every group on the device and returns the result again. */
 int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out);
 
+/* Replaces the formatting half of save_frags_from_group / store_frag (src/commonFunctions.cpp:101-115) for the
+ * result of the last rk_group / rk_sort_groups: the text of output lines first_line .. first_line+n_lines-1
+ *   Frag,xStart,yStart,xEnd,yEnd,strand,gid,length,score,ident,similarity,identity,0,repval\n
+ * byte for byte what the reference writes (integers as ostream << uint64_t, the two floats as printf("%g")),
+ * formatted on the device from the loaded records.  At most RK_FORMAT_MAX_LINES lines per call; the caller writes
+ * the 16 header lines itself (sequence_manager::write_header) and appends the chunks.  text: pinned host memory owned
+ * by the context, valid until the next rk_format_lines / rk_destroy.  The records must still be where rk_load_aos
+ * found them when they were given as a DEVICE pointer (host records are kept in the context).  Synchronous. */
+#define RK_FORMAT_MAX_LINES 8000000ull
+typedef struct {
+  const char *text;
+  uint64_t n_bytes;
+  float ms_device; /* formatting kernels + device -> host copy */
+} rk_text;
+int rk_format_lines(rk_ctx *ctx, uint64_t first_line, uint64_t n_lines, rk_text *out);
+
 /* Pinned host memory for record arrays handed to rk_load_aos (full-speed H2D); NULL on failure. */
 void *rk_host_alloc(size_t bytes);
 void rk_host_free(void *p);

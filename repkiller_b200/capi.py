@@ -22,7 +22,7 @@ NSTAGES = len(STAGES)
 
 # every symbol include/rk_b200.h declares
 SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_group", "rk_sort_groups", "rk_host_alloc", "rk_host_free",
-           "rk_diagonal_func", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
+           "rk_diagonal_func", "rk_format_lines", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
            # multi-GPU stage entry points (bound in repkiller_b200/dist.py)
            "rk_st_link_words", "rk_st_decode", "rk_st_or_words", "rk_st_keys", "rk_st_match", "rk_st_forest", "rk_st_hkey",
            "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter", "rk_gen_workload"]
@@ -78,10 +78,18 @@ def load_library():
     L.rk_sort_pairs_work_bytes.restype = C.c_uint64
     L.rk_sort_pairs.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_uint64, C.c_int, C.c_void_p]
     L.rk_version.restype = C.c_char_p
+    L.rk_format_lines.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(_Text)]
     L.rk_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.rk_profile_read.argtypes = [C.c_void_p, C.POINTER(_KernelTime), C.c_int, C.c_int]
     _lib = L
     return L
+
+
+class _Text(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("n_bytes", C.c_uint64), ("ms_device", C.c_float)]
+
+
+FORMAT_MAX_LINES = 8_000_000
 
 
 @dataclass
@@ -168,6 +176,7 @@ class Context:
         r = _Result()
         self._check(self._L.rk_group(self._h, len_ratio, pos_ratio, flags, C.byref(r)))
         m = r.n_kept
+        self._last_m = m
 
         def arr(p, dt):
             if not host_result:
@@ -181,6 +190,23 @@ class Context:
                       arr(r.identity, np.float32),
                       {"order": r.d_order, "gid": r.d_gid, "repval": r.d_repval, "identity": r.d_identity},
                       {STAGES[i]: r.ms_stage[i] for i in range(NSTAGES)}, r.ms_device, r.n_launches)
+
+    def format_lines(self, first_line: int = 0, n_lines: int | None = None) -> bytes:
+        """Text of the output lines of the last group() (commonFunctions.cpp:101-115), formatted on the device; the
+        16 header lines are the caller's.  Chunks of FORMAT_MAX_LINES lines are concatenated."""
+        out, self.ms_format = [], 0.0
+        total = self._last_m if n_lines is None else n_lines
+        done = 0
+        while done < total or (total == 0 and not out):
+            cnt = min(FORMAT_MAX_LINES, total - done)
+            t = _Text()
+            self._check(self._L.rk_format_lines(self._h, first_line + done, cnt, C.byref(t)))
+            out.append(C.string_at(t.text, t.n_bytes) if t.n_bytes else b"")
+            self.ms_format += t.ms_device
+            done += cnt
+            if total == 0:
+                break
+        return b"".join(out)
 
     def generate_device(self, w, start: int, count: int, out_ptr: int):
         """Records start..start+count of workload `w` (repkiller_b200.gen.Workload) written to device memory at out_ptr

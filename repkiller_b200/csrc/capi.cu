@@ -26,7 +26,7 @@ inline int ceil_log2(u64 x) {  // bits needed to represent values 0 .. x-1
 
 const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan", "k_radix_scatter", "k_keys", "k_match_small",
                                              "k_match_long", "k_chase", "k_hkey", "k_pack", "k_order_tile",
-                                             "k_groupsort_large", "k_finalize", "k_diag_table", "k_groupsort_warp"};
+                                             "k_groupsort_large", "k_finalize", "k_diag_table", "k_groupsort_warp", "k_format"};
 
 // CUDA-event pair around every launch group; folded into per-kernel totals after each synchronisation
 struct Profiler {
@@ -91,6 +91,13 @@ struct rk_ctx {
   Counters *st_cnt = nullptr;
   void *st_scratch = nullptr;
   u64 st_scratch_bytes = 0;
+
+  // K6 text output: device text + work area (grow-only), pinned host mirror
+  const u8 *aos_dev = nullptr;  // the loaded records on the device (own copy, or the caller's device pointer)
+  void *d_text = nullptr;
+  u64 d_text_bytes = 0;
+  char *h_text = nullptr;
+  u64 h_text_bytes = 0;
 
   bool loaded = false;
   u64 n = 0;
@@ -368,6 +375,8 @@ void rk_destroy(rk_ctx *c) {
   if (c->arena) cudaFree(c->arena);
   if (c->st_cnt) cudaFree(c->st_cnt);
   if (c->st_scratch) cudaFree(c->st_scratch);
+  if (c->d_text) cudaFree(c->d_text);
+  if (c->h_text) cudaFreeHost(c->h_text);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -441,6 +450,7 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
     CK(cudaMemcpyAsync(ctx->d_aos, frags, n * RK_FRAG_BYTES, cudaMemcpyHostToDevice, st));
     aos = ctx->d_aos;
   }
+  ctx->aos_dev = aos;
   CK(cudaEventRecord(ev[1], st));
   CK(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), st));
   CK(cudaMemsetAsync(ctx->link_x, 0, lxw * 4, st));
@@ -556,6 +566,56 @@ int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d);
   if (e != cudaSuccess) return fail(ctx, RK_ERR_CUDA, "rk_diagonal_func: %s", cudaGetErrorString(e));
+  return RK_OK;
+}
+
+int rk_format_lines(rk_ctx *ctx, uint64_t first_line, uint64_t n_lines, rk_text *out) {
+  if (!ctx || !out) return RK_ERR_ARG;
+  if (!ctx->loaded || !ctx->have_group) return fail(ctx, RK_ERR_STATE, "rk_format_lines before rk_group");
+  if (first_line > ctx->m || n_lines > ctx->m - first_line) return fail(ctx, RK_ERR_ARG, "line range beyond the %u output lines", ctx->m);
+  if (n_lines > RK_FORMAT_MAX_LINES) return fail(ctx, RK_ERR_ARG, "at most %llu lines per call", (unsigned long long)RK_FORMAT_MAX_LINES);
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  memset(out, 0, sizeof *out);
+  cudaStream_t st = ctx->stream;
+  const u64 text_cap = align_up(n_lines * RK_FORMAT_MAX_LINE + 16, 256);
+  const u64 need = text_cap + format_work_bytes((u32)n_lines);
+  if (need > ctx->d_text_bytes) {
+    CK(cudaStreamSynchronize(st));
+    if (ctx->d_text) cudaFree(ctx->d_text);
+    ctx->d_text = nullptr, ctx->d_text_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->d_text, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, RK_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)need, cudaGetErrorString(e));
+    }
+    ctx->d_text_bytes = need;
+  }
+  FormatArgs fa{};
+  fa.aos = ctx->aos_dev, fa.order = ctx->out_order, fa.gid = ctx->out_gid, fa.repval = ctx->out_repval, fa.identity = ctx->out_identity;
+  fa.first_line = (u32)first_line, fa.n_lines = (u32)n_lines;
+  fa.text = (char *)ctx->d_text;
+  u32 *work = (u32 *)((u8 *)ctx->d_text + text_cap);
+  fa.total_bytes = work;  // first word of the work area; launch_format carves the rest after it
+  CK(cudaEventRecord(ctx->ev[0], st));
+  launch_format(fa, work + 8, st);
+  CK(cudaMemcpyAsync(&ctx->h_cnt->pad, fa.total_bytes, sizeof(u32), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  const u64 nbytes = ctx->h_cnt->pad;
+  if (nbytes + 1 > ctx->h_text_bytes) {
+    if (ctx->h_text) cudaFreeHost(ctx->h_text);
+    ctx->h_text = nullptr, ctx->h_text_bytes = 0;
+    const u64 cap = align_up(nbytes + nbytes / 8 + 4096, 4096);
+    CK(cudaHostAlloc((void **)&ctx->h_text, cap, cudaHostAllocDefault));
+    ctx->h_text_bytes = cap;
+  }
+  if (nbytes) CK(cudaMemcpyAsync(ctx->h_text, ctx->d_text, nbytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev[1], st));
+  CK(cudaStreamSynchronize(st));
+  out->text = ctx->h_text;
+  out->n_bytes = nbytes;
+  out->ms_device = ev_ms(ctx->ev[0], ctx->ev[1]);
   return RK_OK;
 }
 

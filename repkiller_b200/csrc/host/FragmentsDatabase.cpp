@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 // One CSV row -> record.  Semantics of the reference's readFragment (FragmentsDatabase.cpp:17-50), which
@@ -71,9 +72,49 @@ long long value_after_colon(const std::string &line) {  // atoll(line.substr(lin
 }
 }  // namespace
 
+namespace {
+// rows of data[begin, end) in file order, parsed by one thread ("\n"-separated like std::getline; the caller makes
+// sure a range starts at the beginning of a row)
+struct ParsedChunk {
+  std::vector<FragFile> rows;
+};
+void parse_range(const char *data, size_t begin, size_t end, bool last_range, ParsedChunk *out) {
+  size_t pos = begin;
+  bool eof = begin >= end && !last_range;
+  while (!eof) {  // reference: FragmentsDatabase.cpp:92-100; the final getline on an exhausted stream yields one empty line
+    const size_t s = pos;
+    while (pos < end && data[pos] != '\n') ++pos;
+    const size_t l = pos - s;
+    if (pos < end) {
+      ++pos;
+      if (pos >= end && !last_range) eof = true;  // the row after this '\n' belongs to the next range
+    } else {
+      eof = true;
+    }
+    FragFile tmp;
+    memset(&tmp, 0, sizeof tmp);
+    if (readFragment(&tmp, data + s, l)) out->rows.push_back(tmp);
+  }
+}
+}  // namespace
+
 FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device) {
-  // slurp the rest of the stream; lines are split on '\n' like std::getline
-  std::string data((std::istreambuf_iterator<char>(frags_file)), std::istreambuf_iterator<char>());
+  // slurp the rest of the stream in one read; lines are split on '\n' like std::getline
+  std::string data;
+  {
+    const std::streampos here = frags_file.tellg();
+    frags_file.seekg(0, std::ios::end);
+    const std::streampos fin = frags_file.tellg();
+    if (here != std::streampos(-1) && fin != std::streampos(-1) && fin >= here) {
+      frags_file.seekg(here);
+      data.resize((size_t)(fin - here));
+      frags_file.read(&data[0], (std::streamsize)data.size());
+      data.resize((size_t)frags_file.gcount());
+    } else {  // not seekable
+      frags_file.clear();
+      data.assign((std::istreambuf_iterator<char>(frags_file)), std::istreambuf_iterator<char>());
+    }
+  }
   size_t pos = 0;
   auto next_line = [&](std::string &out) {
     const size_t s = pos;
@@ -96,26 +137,49 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   ctx_ = rk_create(device);
   if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
 
-  // upper bound on rows: number of remaining lines
-  uint64_t lines = 1;
-  for (size_t i = pos; i < data.size(); ++i) lines += data[i] == '\n';
-  cap_ = lines;
+  // The rows are parsed by all host cores: the text is cut at row boundaries into one range per thread, every thread
+  // keeps its accepted rows in file order, and the ranges are concatenated in order — the same records, in the same
+  // order, as the reference's row-by-row loop.
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
+  const size_t body = data.size() - pos;
+  if (nthreads < 1 || body < (1u << 20)) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  std::vector<size_t> cut(nthreads + 1, data.size());
+  cut[0] = pos;
+  for (unsigned t = 1; t < nthreads; ++t) {
+    size_t c = pos + body / nthreads * t;
+    if (c < cut[t - 1]) c = cut[t - 1];
+    while (c < data.size() && data[c - 1] != '\n') ++c;  // move to the start of the next row (c > pos >= 1 here)
+    cut[t] = c;
+  }
+  std::vector<ParsedChunk> chunks(nthreads);
+  bool eof_only = data.empty();  // reference: an empty stream never enters the row loop
+  if (!eof_only) {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; ++t) {
+      const bool last = t + 1 == nthreads;
+      if (!last && cut[t] >= cut[t + 1]) continue;  // empty range
+      pool.emplace_back(parse_range, data.data(), cut[t], cut[t + 1], last, &chunks[t]);
+    }
+    for (auto &th : pool) th.join();
+  }
+  uint64_t accepted = 0;
+  for (const auto &c : chunks) accepted += c.rows.size();
+  if (accepted > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
+  cap_ = accepted ? accepted : 1;
   records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16);
   if (!records_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
-
-  bool eof = data.empty();
-  while (!eof) {  // :92-100; the final getline on an exhausted stream yields one empty line
-    const size_t s = pos;
-    while (pos < data.size() && data[pos] != '\n') ++pos;
-    const size_t l = pos - s;
-    if (pos < data.size()) ++pos;
-    else eof = true;
-    FragFile tmp;
-    memset(&tmp, 0, sizeof tmp);
-    if (!readFragment(&tmp, data.data() + s, l)) continue;
-    records_[count_++] = tmp;
-    if (count_ > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
+  {
+    std::vector<std::thread> pool;
+    uint64_t off = 0;
+    for (auto &c : chunks) {
+      if (!c.rows.empty()) pool.emplace_back([this, off, &c] { memcpy(records_ + off, c.rows.data(), c.rows.size() * sizeof(FragFile)); });
+      off += c.rows.size();
+    }
+    for (auto &th : pool) th.join();
   }
+  count_ = accepted;
 
   const int rc = rk_load_aos(ctx_, records_, count_, seq_manager.get_sequence_by_label(0).len,
                              seq_manager.get_sequence_by_label(1).len, RK_F_TIMING, &load_stats_);

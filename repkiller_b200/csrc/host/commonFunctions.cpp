@@ -168,6 +168,27 @@ void save_frag_pair(std::ostream &out_file, uint64_t, uint64_t, const sequence_m
   for (auto fg : fgl) save_frags_from_group(out_file, *fg, gid++);
 }
 
+// The same file as save_all_frag_pairs, without the detour over an FGList: the lines of the last rk_group on this
+// database are formatted on the device (rk_format_lines, K6) and written chunk by chunk.
+void save_device_text(const std::string &out_file_base_path, const sequence_manager &seq_manager, const FragmentsDatabase &db,
+                      float *ms_format) {
+  std::ofstream out_file(out_file_base_path, std::ofstream::out | std::ofstream::binary);
+  if (!out_file) throw std::runtime_error("Could not open output directory " + out_file_base_path);
+  seq_manager.write_header(out_file);
+  uint64_t kept = db.load_stats().n_kept, done = 0;
+  float ms = 0.f;
+  while (done < kept) {
+    const uint64_t cnt = kept - done < RK_FORMAT_MAX_LINES ? kept - done : RK_FORMAT_MAX_LINES;
+    rk_text t;
+    if (rk_format_lines(db.ctx(), done, cnt, &t) != RK_OK) device_error(db);
+    out_file.write(t.text, (std::streamsize)t.n_bytes);
+    ms += t.ms_device;
+    done += cnt;
+  }
+  out_file.close();
+  if (ms_format) *ms_format = ms;
+}
+
 void save_all_frag_pairs(const std::string &out_file_base_path, const sequence_manager &seq_manager, const FGList &fgl) {
   const uint64_t n_seq = seq_manager.get_number_of_sequences();
   std::ofstream out_file;

@@ -31,4 +31,8 @@ void save_frags_from_group(std::ostream &out_file, FragsGroup &fg, uint64_t gid)
 void save_frag_pair(std::ostream &out_file, uint64_t seq1_label, uint64_t seq2_label, const sequence_manager &seq_mngr,
                     const FGList &fgl);
 void save_all_frag_pairs(const std::string &out_file_base_path, const sequence_manager &seq_manager, const FGList &fgl);
+// The same file for the result of the last rk_group on frags_db, its lines formatted on the device (K6, rk_format_lines):
+// no FGList, no per-line host formatting.  Throws std::runtime_error when the path cannot be opened (like the above).
+void save_device_text(const std::string &out_file_base_path, const sequence_manager &seq_manager, const FragmentsDatabase &frags_db,
+                      float *ms_format = nullptr);
 void free_groups(FGList *fgl);

@@ -4,11 +4,13 @@
 // Parameter pairs are processed in argv order on one device context while the writer thread saves the previous
 // result; every pair writes the same path (as in the reference, repkiller.cpp:95-96), so the last pair's file
 // remains ([survey choice]: the reference's 3-thread pool makes the survivor timing dependent).
-// RK_TIMING=1 prints per-stage device times on stderr; RK_DEVICE selects the GPU.
+// RK_TIMING=1 prints per-stage device times on stderr; RK_DEVICE selects the GPU; RK_LEGACY_WRITER=1 formats the output on
+// the host through FGList + SaverQueue instead of on the device (K6).
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <queue>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -18,14 +20,33 @@
 #include "../commonFunctions.h"
 #include "../structs.h"
 
-static void execWithParams(const FragmentsDatabase &frag_db, std::pair<double, double> param, const std::string &out_path,
-                           SaverQueue &sq, bool timing) {
+static size_t fallback_count = 0;
+
+static void execWithParams(const FragmentsDatabase &frag_db, const sequence_manager &seq_manager, std::pair<double, double> param,
+                           const std::string &out_path, SaverQueue &sq, bool timing, bool legacy_writer) {
   rk_result st;
-  FGList *groups = group_and_sort(frag_db, param.first, param.second, &st);  // repkiller.cpp:83-91 in one device pass
+  if (legacy_writer) {  // RK_LEGACY_WRITER=1: host lists + the host formatter behind the reference's SaverQueue interface
+    FGList *groups = group_and_sort(frag_db, param.first, param.second, &st);  // repkiller.cpp:83-91 in one device pass
+    if (timing)
+      std::cerr << "[rk] len_ratio=" << param.first << " pos_ratio=" << param.second << " groups=" << st.n_groups
+                << " device_ms=" << st.ms_device << " launches=" << st.n_launches << "\n";
+    sq.addRequest(out_path, groups);  // repkiller.cpp:95-96
+    return;
+  }
+  // grouping (K3-K5) and the text of the output file (K6) on the device; the host only writes bytes
+  if (rk_group(frag_db.ctx(), param.first, param.second, RK_F_TIMING, &st) != RK_OK)
+    throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(frag_db.ctx()));
+  float ms_format = 0.f;
+  try {
+    save_device_text(out_path, seq_manager, frag_db, &ms_format);
+  } catch (const std::runtime_error &) {  // reference: SaverQueue.cpp:16-20
+    const std::string default_path = "represults-" + std::to_string(++fallback_count) + ".csv";
+    std::cerr << "Couldn't access " << out_path << ", saving into " << default_path << "\n" << std::flush;
+    save_device_text(default_path, seq_manager, frag_db, &ms_format);
+  }
   if (timing)
     std::cerr << "[rk] len_ratio=" << param.first << " pos_ratio=" << param.second << " groups=" << st.n_groups
-              << " device_ms=" << st.ms_device << " launches=" << st.n_launches << "\n";
-  sq.addRequest(out_path, groups);  // repkiller.cpp:95-96
+              << " device_ms=" << st.ms_device << " launches=" << st.n_launches << " format_ms=" << ms_format << "\n";
 }
 
 int main(int argc, char *argv[]) {
@@ -46,6 +67,7 @@ int main(int argc, char *argv[]) {
                "\n"
             << std::flush;
   const bool timing = getenv("RK_TIMING") != nullptr;
+  const bool legacy_writer = getenv("RK_LEGACY_WRITER") != nullptr;
   const int device = getenv("RK_DEVICE") ? atoi(getenv("RK_DEVICE")) : 0;
 
   sequence_manager seq_manager;
@@ -61,7 +83,7 @@ int main(int argc, char *argv[]) {
   while (!params.empty()) {
     auto param = params.front();
     params.pop();
-    execWithParams(frag_db, param, out_file_base_path, sq, timing);
+    execWithParams(frag_db, seq_manager, param, out_file_base_path, sq, timing, legacy_writer);
   }
   sq.stop();
   std::cout << "Repkiller finished with no errors\n";

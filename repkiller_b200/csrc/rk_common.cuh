@@ -69,7 +69,7 @@ __device__ __forceinline__ u32 absdiff(u32 a, u32 b) { return a > b ? a - b : b 
 // ---- per-kernel timing (CUDA events around every launch; off unless rk_profile_enable) ---------------
 enum KernelId {
   KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
-  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_COUNT
+  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_FORMAT, KID_COUNT
 };
 void prof_begin(int kid, cudaStream_t st, unsigned long long units);
 void prof_end(cudaStream_t st);
@@ -175,6 +175,22 @@ struct OrderArgs {
   float *out_identity;
   u32 *err;
 };
+// K6: the text of output lines first_line .. first_line+n_lines (commonFunctions.cpp:101-115) from the loaded records and
+// the result arrays of the last grouping.
+struct FormatArgs {
+  const u8 *aos;           // the loaded records, file order, 109 bytes each
+  const u32 *order, *gid;  // result arrays (output order)
+  const u8 *repval;
+  const float *identity;
+  u32 first_line, n_lines;
+  char *text;              // out: n_lines lines, back to back
+  u32 *total_bytes;        // out (device): bytes written
+  u32 *line_len, *line_off;  // set by launch_format (carved from its work area)
+};
+u64 format_work_bytes(u32 n_lines);
+constexpr u32 RK_FORMAT_MAX_LINE = 208;  // upper bound of one line in bytes
+int launch_format(FormatArgs a, void *work, cudaStream_t st);
+
 u64 order_scratch_bytes(u64 m);
 void order_carve(OrderArgs &a, void *scratch, u64 m);  // sets packed .. worklist, work_cap
 int launch_order(const OrderArgs &a, cudaStream_t st);

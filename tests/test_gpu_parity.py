@@ -92,6 +92,8 @@ def test_fuzz_golden_bytes(ctx, fuzz_cases, tmp_path):
         outp = tmp_path / "out.csv"
         O.write_output(str(outp), hdr, rec, g)
         assert outp.read_bytes() == c["ref_out"].encode("latin1"), f"fuzz seed {c['seed']}"
+        # K6: the same bytes formatted on the device (the header lines are the host's)
+        assert hdr + ctx.format_lines() == c["ref_out"].encode("latin1"), f"device text, fuzz seed {c['seed']}"
 
 
 @pytest.mark.parametrize("name", ["c1_loose", "c3_small", "dense", "c2_small"])
@@ -104,6 +106,43 @@ def test_medium_golden_md5(ctx, medium_cases, tmp_path, name):
     outp = tmp_path / "out.csv"
     O.write_output(str(outp), make_header(w.lx, w.ly, w.n).encode(), rec, g)
     assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"]
+    text = ctx.format_lines()   # K6: device-side formatter, byte for byte the reference's lines
+    assert hashlib.md5(make_header(w.lx, w.ly, w.n).encode() + text).hexdigest() == c["ref_md5"]
+    # chunked calls return the same bytes
+    k = res.n_kept // 3
+    assert ctx.format_lines(0, k) + ctx.format_lines(k, res.n_kept - k) == text
+
+
+def test_device_text_float_formats(ctx, tmp_path):
+    """printf("%g") of every kind of float the two float columns can hold (similarity is whatever the input carried):
+    denormals, powers of ten and their neighbours, rounding ties, inf, nan, -0; and 20-digit integers."""
+    rng = np.random.default_rng(11)
+    n = 40_000
+    rec = np.zeros(n, FRAG_DTYPE)
+    rec["xStart"] = rng.integers(0, 9_000, n)
+    rec["yStart"] = rng.integers(0, 9_000, n)
+    rec["length"] = rng.integers(0, 400, n)            # length 0: identity is inf or -nan
+    rec["ident"] = rng.integers(0, 400, n)
+    rec["xEnd"] = rng.integers(0, 2 ** 63, n, dtype=np.uint64) * 2 + 1   # 19/20-digit integers
+    rec["yEnd"] = rng.integers(0, 2 ** 40, n)
+    rec["score"] = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    rec["strand"] = rng.choice([b"f", b"r"], n)
+    bits = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    special = np.array([0, 0x80000000, 1, 0x007FFFFF, 0x00800000, 0x7F7FFFFF, 0x7F800000, 0xFF800000, 0x7FC00000, 0xFFC00000,
+                        0x49742400, 0x49742408, 0x497423F8, 0x38D1B717, 0x38D1B716, 0x3A83126F, 0x42AFD70A], dtype=np.uint32)
+    bits[: special.size] = special
+    pct = (rng.integers(0, 10001, n // 2) / np.float32(100)).astype(np.float32)   # "87.92"-like values
+    bits[n // 2:] = pct.view(np.uint32)
+    rec["similarity"] = bits.view(np.float32)
+    res, g = check_against_oracle(ctx, rec, 10_001, 10_001, 0.05, 0.05)
+    g.order, g.out_gid, g.repval, g.identity = res.order, res.gid, res.repval, res.identity
+    outp = tmp_path / "out.csv"
+    O.write_output(str(outp), b"", rec, g)
+    want, got = outp.read_bytes(), ctx.format_lines()
+    if want != got:
+        wl, gl = want.split(b"\n"), got.split(b"\n")
+        bad = [(a, b) for a, b in zip(wl, gl) if a != b][:5]
+        raise AssertionError(f"{len(wl)} vs {len(gl)} lines; first differences: {bad}")
 
 
 def test_edge_inputs(ctx):
