@@ -118,7 +118,8 @@ int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out);
  * byte for byte what the reference writes (integers as ostream << uint64_t, the two floats as printf("%g")),
  * formatted on the device from the loaded records.  At most RK_FORMAT_MAX_LINES lines per call; the caller writes
  * the 16 header lines itself (sequence_manager::write_header) and appends the chunks.  text: pinned host memory owned
- * by the context, valid until the next rk_format_lines / rk_destroy.  The records must still be where rk_load_aos
+ * by the context, valid until the next-but-one rk_format_lines call (two buffers alternate, so that a chunk can be
+ * written to disk while the next one is formatted) or rk_destroy.  The records must still be where rk_load_aos
  * found them when they were given as a DEVICE pointer (host records are kept in the context).  Synchronous. */
 #define RK_FORMAT_MAX_LINES 8000000ull
 typedef struct {

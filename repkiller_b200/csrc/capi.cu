@@ -96,8 +96,9 @@ struct rk_ctx {
   const u8 *aos_dev = nullptr;  // the loaded records on the device (own copy, or the caller's device pointer)
   void *d_text = nullptr;
   u64 d_text_bytes = 0;
-  char *h_text = nullptr;
-  u64 h_text_bytes = 0;
+  char *h_text[2] = {nullptr, nullptr};  // alternating: a chunk stays valid while the next one is produced
+  u64 h_text_bytes[2] = {0, 0};
+  int h_text_next = 0;
 
   bool loaded = false;
   u64 n = 0;
@@ -376,7 +377,7 @@ void rk_destroy(rk_ctx *c) {
   if (c->st_cnt) cudaFree(c->st_cnt);
   if (c->st_scratch) cudaFree(c->st_scratch);
   if (c->d_text) cudaFree(c->d_text);
-  if (c->h_text) cudaFreeHost(c->h_text);
+  for (char *t : c->h_text) if (t) cudaFreeHost(t);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -603,17 +604,19 @@ int rk_format_lines(rk_ctx *ctx, uint64_t first_line, uint64_t n_lines, rk_text 
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   const u64 nbytes = ctx->h_cnt->pad;
-  if (nbytes + 1 > ctx->h_text_bytes) {
-    if (ctx->h_text) cudaFreeHost(ctx->h_text);
-    ctx->h_text = nullptr, ctx->h_text_bytes = 0;
+  const int hb = ctx->h_text_next;
+  ctx->h_text_next ^= 1;
+  if (nbytes + 1 > ctx->h_text_bytes[hb]) {
+    if (ctx->h_text[hb]) cudaFreeHost(ctx->h_text[hb]);
+    ctx->h_text[hb] = nullptr, ctx->h_text_bytes[hb] = 0;
     const u64 cap = align_up(nbytes + nbytes / 8 + 4096, 4096);
-    CK(cudaHostAlloc((void **)&ctx->h_text, cap, cudaHostAllocDefault));
-    ctx->h_text_bytes = cap;
+    CK(cudaHostAlloc((void **)&ctx->h_text[hb], cap, cudaHostAllocDefault));
+    ctx->h_text_bytes[hb] = cap;
   }
-  if (nbytes) CK(cudaMemcpyAsync(ctx->h_text, ctx->d_text, nbytes, cudaMemcpyDeviceToHost, st));
+  if (nbytes) CK(cudaMemcpyAsync(ctx->h_text[hb], ctx->d_text, nbytes, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->ev[1], st));
   CK(cudaStreamSynchronize(st));
-  out->text = ctx->h_text;
+  out->text = ctx->h_text[hb];
   out->n_bytes = nbytes;
   out->ms_device = ev_ms(ctx->ev[0], ctx->ev[1]);
   return RK_OK;

@@ -1,6 +1,7 @@
 #include "FragmentsDatabase.h"
 
 #include <cerrno>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -99,6 +100,14 @@ void parse_range(const char *data, size_t begin, size_t end, bool last_range, Pa
 }  // namespace
 
 FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  // CUDA start-up (a few hundred ms) runs beside the file read and the parse
+  std::thread create_thread([this, device] { ctx_ = rk_create(device); });
+  struct Joiner {
+    std::thread &t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } create_joiner{create_thread};
   // slurp the rest of the stream in one read; lines are split on '\n' like std::getline
   std::string data;
   {
@@ -115,6 +124,7 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
       data.assign((std::istreambuf_iterator<char>(frags_file)), std::istreambuf_iterator<char>());
     }
   }
+  const auto t1 = clk::now();
   size_t pos = 0;
   auto next_line = [&](std::string &out) {
     const size_t s = pos;
@@ -134,9 +144,6 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   seq_manager.read_header(header);
   vsize = 1 + seq_manager.get_sequence_by_label(0).len / 10;  // :84
 
-  ctx_ = rk_create(device);
-  if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
-
   // The rows are parsed by all host cores: the text is cut at row boundaries into one range per thread, every thread
   // keeps its accepted rows in file order, and the ranges are concatenated in order — the same records, in the same
   // order, as the reference's row-by-row loop.
@@ -155,20 +162,29 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   }
   std::vector<ParsedChunk> chunks(nthreads);
   bool eof_only = data.empty();  // reference: an empty stream never enters the row loop
+  // pinned memory for the records (full-speed H2D) is allocated beside the parse, for at most min(T, bytes / 28) records:
+  // a file with more accepted rows than its header announces is an error anyway, and a row that readFragment accepts
+  // has 14 non-empty fields ("Frag" first) and 13 commas, i.e. at least 30 bytes with its line end
+  const uint64_t rows_upper = body / 28 + 1;
+  cap_ = (rows_upper < total_frags ? rows_upper : total_frags) + 2;
+  create_thread.join();
+  if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
+  std::thread alloc_thread([this] { records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16); });
+  Joiner alloc_joiner{alloc_thread};
   if (!eof_only) {
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nthreads; ++t) {
       const bool last = t + 1 == nthreads;
       if (!last && cut[t] >= cut[t + 1]) continue;  // empty range
+      chunks[t].rows.reserve((cut[t + 1] - cut[t]) / 48 + 16);  // GECKO rows are 60..90 bytes
       pool.emplace_back(parse_range, data.data(), cut[t], cut[t + 1], last, &chunks[t]);
     }
     for (auto &th : pool) th.join();
   }
   uint64_t accepted = 0;
   for (const auto &c : chunks) accepted += c.rows.size();
+  alloc_thread.join();
   if (accepted > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
-  cap_ = accepted ? accepted : 1;
-  records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16);
   if (!records_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
   {
     std::vector<std::thread> pool;
@@ -180,10 +196,15 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
     for (auto &th : pool) th.join();
   }
   count_ = accepted;
+  const auto t2 = clk::now();
 
   const int rc = rk_load_aos(ctx_, records_, count_, seq_manager.get_sequence_by_label(0).len,
                              seq_manager.get_sequence_by_label(1).len, RK_F_TIMING, &load_stats_);
   if (rc != RK_OK) throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(ctx_));
+  const auto t3 = clk::now();
+  ms_read_ = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  ms_parse_ = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  ms_device_load_ = std::chrono::duration<double, std::milli>(t3 - t2).count();
 }
 
 FragmentsDatabase::~FragmentsDatabase() {

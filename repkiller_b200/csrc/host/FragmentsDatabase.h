@@ -19,6 +19,7 @@ class FragmentsDatabase {
   rk_ctx *ctx_ = nullptr;
   std::string header;
   rk_load_stats load_stats_{};
+  double ms_read_ = 0, ms_parse_ = 0, ms_device_load_ = 0;  // host wall clock of the three ingest phases
 
  public:
   // Parses the GECKO CSV exactly like the reference (16 header lines, Frag rows, readFragment's accept/pad
@@ -34,4 +35,7 @@ class FragmentsDatabase {
   const FragFile *records() const { return records_; }   // replaces begin()/end(): file order, not buckets
   rk_ctx *ctx() const { return ctx_; }
   const rk_load_stats &load_stats() const { return load_stats_; }
+  double ms_read() const { return ms_read_; }
+  double ms_parse() const { return ms_parse_; }
+  double ms_device_load() const { return ms_device_load_; }
 };

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <stdexcept>
+#include <thread>
 
 void print_help() {
   std::cout << "Repkiller v0.9.b\n";
@@ -175,16 +176,24 @@ void save_device_text(const std::string &out_file_base_path, const sequence_mana
   std::ofstream out_file(out_file_base_path, std::ofstream::out | std::ofstream::binary);
   if (!out_file) throw std::runtime_error("Could not open output directory " + out_file_base_path);
   seq_manager.write_header(out_file);
-  uint64_t kept = db.load_stats().n_kept, done = 0;
+  // chunks of 1M lines: the device formats chunk k+1 (rk_format_lines alternates between two pinned buffers) while
+  // this thread's helper writes chunk k
+  const uint64_t kChunk = 1000000;
+  const uint64_t kept = db.load_stats().n_kept;
+  uint64_t done = 0;
   float ms = 0.f;
+  std::thread writer;
   while (done < kept) {
-    const uint64_t cnt = kept - done < RK_FORMAT_MAX_LINES ? kept - done : RK_FORMAT_MAX_LINES;
+    const uint64_t cnt = kept - done < kChunk ? kept - done : kChunk;
     rk_text t;
-    if (rk_format_lines(db.ctx(), done, cnt, &t) != RK_OK) device_error(db);
-    out_file.write(t.text, (std::streamsize)t.n_bytes);
+    const int rc = rk_format_lines(db.ctx(), done, cnt, &t);
+    if (writer.joinable()) writer.join();  // chunk k-1 is on its way to the file before chunk k+1 may reuse its buffer
+    if (rc != RK_OK) device_error(db);
+    writer = std::thread([&out_file, t] { out_file.write(t.text, (std::streamsize)t.n_bytes); });
     ms += t.ms_device;
     done += cnt;
   }
+  if (writer.joinable()) writer.join();
   out_file.close();
   if (ms_format) *ms_format = ms;
 }

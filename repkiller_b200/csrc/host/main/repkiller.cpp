@@ -6,6 +6,7 @@
 // remains ([survey choice]: the reference's 3-thread pool makes the survivor timing dependent).
 // RK_TIMING=1 prints per-stage device times on stderr; RK_DEVICE selects the GPU; RK_LEGACY_WRITER=1 formats the output on
 // the host through FGList + SaverQueue instead of on the device (K6).
+#include <chrono>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -37,6 +38,7 @@ static void execWithParams(const FragmentsDatabase &frag_db, const sequence_mana
   if (rk_group(frag_db.ctx(), param.first, param.second, RK_F_TIMING, &st) != RK_OK)
     throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(frag_db.ctx()));
   float ms_format = 0.f;
+  const auto tw0 = std::chrono::steady_clock::now();
   try {
     save_device_text(out_path, seq_manager, frag_db, &ms_format);
   } catch (const std::runtime_error &) {  // reference: SaverQueue.cpp:16-20
@@ -46,7 +48,8 @@ static void execWithParams(const FragmentsDatabase &frag_db, const sequence_mana
   }
   if (timing)
     std::cerr << "[rk] len_ratio=" << param.first << " pos_ratio=" << param.second << " groups=" << st.n_groups
-              << " device_ms=" << st.ms_device << " launches=" << st.n_launches << " format_ms=" << ms_format << "\n";
+              << " device_ms=" << st.ms_device << " launches=" << st.n_launches << " format_ms=" << ms_format << " write_call_ms="
+              << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count() << "\n";
 }
 
 int main(int argc, char *argv[]) {
@@ -75,7 +78,8 @@ int main(int argc, char *argv[]) {
   frags_file.close();
   if (timing) {
     const rk_load_stats &ls = frag_db.load_stats();
-    std::cerr << "[rk] loaded=" << ls.n_loaded << " kept=" << ls.n_kept << " device_ms=" << ls.ms_device << "\n";
+    std::cerr << "[rk] loaded=" << ls.n_loaded << " kept=" << ls.n_kept << " device_ms=" << ls.ms_device << " host: read_ms=" << frag_db.ms_read()
+              << " parse_ms=" << frag_db.ms_parse() << " load_call_ms=" << frag_db.ms_device_load() << "\n";
   }
 
   SaverQueue sq(seq_manager);
