@@ -308,3 +308,70 @@ def test_device_generator_matches_host_generator(ctx):
         want = host.view(np.uint8).reshape(-1)
         d = np.nonzero(got != want)[0]
         assert d.size == 0, f"{w.name}: {d.size} bytes differ, first at record {d[0] // 109} byte {d[0] % 109}"
+
+
+def _killer(n):
+    """median-of-three killer (Musser 1997): drives libstdc++'s introsort to its depth limit and into heap sort"""
+    k = n // 2
+    a = np.zeros(n, np.int64)
+    for i in range(1, k + 1):
+        if i % 2:
+            a[i - 1] = i
+            a[i] = k + i
+        a[k + i - 1] = 2 * i
+    return a[:n]
+
+
+def test_group_order_is_libstdcxx_sort_for_every_size_and_pattern(ctx):
+    """K5b alone through rk_st_order: groups of every size class (<= 16 stable, 17..128 and 129..1024 by one warp,
+    > 1024 split in global memory) with keys that are random, heavily tied, constant, sorted, reversed, organ-pipe
+    and median-of-three killers (depth limit -> heap sort) must come out in the order std::sort leaves them
+    (oracle: rko_std_sort_by_key runs the real std::sort)."""
+    import torch
+    from repkiller_b200.dist import CudaStages
+    st = CudaStages(ctx, torch.device("cuda:0"))
+    rng = np.random.default_rng(5)
+    sizes = list(range(1, 40)) + [63, 64, 65, 100, 127, 128, 129, 130, 200, 255, 256, 257, 500, 1000, 1023, 1024, 1025, 1026,
+                                   1500, 2047, 2048, 2049, 3000, 5000, 9000, 20000]
+    patterns = {
+        "random": lambda n: rng.integers(0, 1 << 30, n),
+        "ties8": lambda n: rng.integers(0, 8, n),
+        "ties_sqrt": lambda n: rng.integers(0, max(2, int(n ** 0.5)), n),
+        "constant": lambda n: np.full(n, 7),
+        "sorted": lambda n: np.arange(n),
+        "reversed": lambda n: np.arange(n)[::-1].copy(),
+        "organ": lambda n: np.minimum(np.arange(n), np.arange(n)[::-1]),
+        "killer": _killer,
+        "sorted_ties": lambda n: np.arange(n) // 3,
+    }
+    hs, gids = [], []
+    g = 0
+    for name, fn in patterns.items():
+        for n in sizes:
+            hs.append(np.asarray(fn(n), dtype=np.int64))
+            gids.append(np.full(n, g, np.int64))
+            g += 1
+    h = np.concatenate(hs).astype(np.uint32)
+    gid = np.concatenate(gids).astype(np.uint32)
+    m = h.shape[0]
+    fidx = rng.permutation(m).astype(np.uint32)                 # any payload: it must follow its member
+    ident = rng.random(m, dtype=np.float32)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+    o, og, rep, idn = st.order(t(gid), t(h), t(fidx), t(ident), True)
+    torch.cuda.synchronize()
+    o = o.cpu().numpy().view(np.uint32)
+    og = og.cpu().numpy().view(np.uint32)
+    rep, idn = rep.cpu().numpy(), idn.cpu().numpy()
+    assert_same("gid", og, gid)
+    pos = 0
+    h64 = h.astype(np.uint64)
+    for hh in hs:
+        n = hh.shape[0]
+        idx = np.arange(pos, pos + n, dtype=np.uint32)
+        want = O.std_sort_by_key(idx, h64) if n > 1 else idx
+        msg = first_diff(o[pos:pos + n], fidx[want])
+        assert msg is None, f"group of {n} at {pos}: {msg}"
+        assert np.array_equal(idn[pos:pos + n].view(np.uint32), ident[want].view(np.uint32))
+        assert np.array_equal(rep[pos:pos + n], np.r_[0 if n == 1 else 1, np.full(n - 1, 2)].astype(np.uint8))
+        pos += n
