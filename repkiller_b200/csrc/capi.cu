@@ -122,6 +122,7 @@ struct rk_ctx {
   u32 *ys_r = nullptr, *kx = nullptr, *ky = nullptr;
   u32 *skx = nullptr, *rx = nullptr, *sky = nullptr, *ry = nullptr;
   void *sort_work = nullptr;
+  u32 *prehist = nullptr;  // 4 x [4][256]: digit counts of key0, kx, ky, gid gathered by the kernels that produce them
   u32 *xm_bits = nullptr;
   u32 *parent = nullptr, *gid_rank = nullptr, *h = nullptr, *sgid = nullptr, *srank = nullptr;
   void *forest_work = nullptr;
@@ -183,6 +184,7 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   c->sky = (u32 *)take(n1 * 4);
   c->ry = (u32 *)take(n1 * 4);
   c->sort_work = take(sort_work_bytes(n1));
+  c->prehist = (u32 *)take(4 * 4 * 256 * 4);
   c->parent = (u32 *)take(n1 * 4);
   c->xm_bits = (u32 *)take((n1 + 31) / 32 * 4);
   c->gid_rank = (u32 *)take(n1 * 4);
@@ -439,8 +441,8 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   ctx->link_y_words = lyw;
   ctx->n = n;
   ctx->g = g;
-  ctx->bits_rank = ceil_log2(g.vsize);
-  ctx->bits_x = ceil_log2(2ull * g.nbx);
+  ctx->bits_rank = ceil_log2(g.vsize) < 1 ? 1 : ceil_log2(g.vsize);  // (the sort clamps to >= 1 bit as well)
+  ctx->bits_x = ceil_log2(2ull * g.nbx);                             // >= 2: nbx >= 2
   ctx->bits_y = ceil_log2(2ull * g.nby);
 
   cudaStream_t st = ctx->stream;
@@ -457,11 +459,14 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   CK(cudaMemsetAsync(ctx->link_x, 0, lxw * 4, st));
   CK(cudaMemsetAsync(ctx->link_y, 0, lyw * 4, st));
   u64 launches = 0;
+  CK(cudaMemsetAsync(ctx->prehist, 0, 3 * 4 * 256 * 4, st));
+  auto hist_of = [&](int which, int bits) { return HistOut{ctx->prehist + which * 1024, (bits + 7) / 8, bits}; };
   launches += launch_decode(aos, n, g, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->key0, ctx->link_x, ctx->link_y,
-                            &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st, ctx->rec4);
+                            &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st, ctx->rec4, hist_of(0, ctx->bits_rank));
   CK(cudaEventRecord(ev[2], st));
   // the rank sort does not depend on the number of dropped records: they carry the largest key and sort last
-  launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st, &ctx->d_cnt->err);
+  launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st, &ctx->d_cnt->err,
+                                ctx->prehist);
   CK(cudaEventRecord(ev[3], st));
   CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -473,13 +478,15 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
 
   CK(cudaEventRecord(ev[4], st));
   launches += launch_keys(ctx->fidx_r, m, g, ctx->rec4, ctx->link_x, ctx->link_y, ctx->xl_r, ctx->yl_r, ctx->ys_r, ctx->kx, ctx->ky,
-                          ctx->identity_r, st);
+                          ctx->identity_r, st, hist_of(1, ctx->bits_x), hist_of(2, ctx->bits_y));
   // generate_diagonal_func does not depend on the ratios: h and the per-rank output record are load-time work
   launches += launch_hkey(ctx->k0_r, ctx->ys_r, m, ctx->h, st, ctx->fidx_r, ctx->identity_r, ctx->hfi_r);
   CK(cudaEventRecord(ev[5], st));
-  launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st, &ctx->d_cnt->err);
+  launches += launch_sort_pairs(ctx->kx, nullptr, ctx->skx, ctx->rx, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_x, ctx->sort_work, st, &ctx->d_cnt->err,
+                                ctx->prehist + 1024);
   CK(cudaEventRecord(ev[6], st));
-  launches += launch_sort_pairs(ctx->ky, nullptr, ctx->sky, ctx->ry, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_y, ctx->sort_work, st, &ctx->d_cnt->err);
+  launches += launch_sort_pairs(ctx->ky, nullptr, ctx->sky, ctx->ry, ctx->tmp_k, ctx->tmp_v, m, ctx->bits_y, ctx->sort_work, st, &ctx->d_cnt->err,
+                                ctx->prehist + 2048);
   CK(cudaEventRecord(ev[7], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
@@ -530,12 +537,15 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
   my.work_count = ctx->d_cnt->work_y;
   launches += launch_match(my, st);
   CK(cudaEventRecord(ev[2], st));
-  launches += launch_forest(ctx->parent, m, ctx->gid_rank, &ctx->d_cnt->n_groups, ctx->forest_work, st);
+  const int bits_g = ceil_log2(m) < 1 ? 1 : ceil_log2(m);
+  CK(cudaMemsetAsync(ctx->prehist + 3072, 0, 4 * 256 * 4, st));
+  launches += launch_forest(ctx->parent, m, ctx->gid_rank, &ctx->d_cnt->n_groups, ctx->forest_work, st, 0, 0xFFFFFFFFu,
+                            HistOut{ctx->prehist + 3072, (bits_g + 7) / 8, bits_g});
   CK(cudaEventRecord(ev[3], st));
   CK(cudaEventRecord(ev[4], st));
   // gids are < number of groups <= m; sorting by ceil_log2(m) bits avoids a host round trip for the count
-  launches += launch_sort_pairs(ctx->gid_rank, nullptr, ctx->sgid, ctx->srank, ctx->tmp_k, ctx->tmp_v, m, ceil_log2(m),
-                                ctx->sort_work, st, &ctx->d_cnt->err);
+  launches += launch_sort_pairs(ctx->gid_rank, nullptr, ctx->sgid, ctx->srank, ctx->tmp_k, ctx->tmp_v, m, bits_g,
+                                ctx->sort_work, st, &ctx->d_cnt->err, m ? ctx->prehist + 3072 : nullptr);
   launches += run_order(ctx, flags);
   CK(cudaEventRecord(ev[5], st));
   return finish_group(ctx, flags, out, launches);

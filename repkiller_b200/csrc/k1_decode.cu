@@ -72,10 +72,11 @@ struct DecodeOut {
   u32 *link_x, *link_y;
   u32 *n_dropped;
   u32 *err;
+  HistOut hist;  // digit counts of key0 for the rank sort (ghist == nullptr: off)
 };
 
-__device__ __forceinline__ void emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, u64 ident, u8 strand, const Geometry &g,
-                                              const DecodeOut &o, u32 &dropped, u32 &err) {
+__device__ __forceinline__ u32 emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, u64 ident, u8 strand, const Geometry &g,
+                                             const DecodeOut &o, u32 &dropped, u32 &err) {
   u8 fl = (strand != 'f') ? FL_REVERSE : 0;
   const u64 cx = xs + len / 2, cy = ys + len / 2;
   if ((xs | ys | len | cx | cy) >> 32) {
@@ -125,15 +126,18 @@ __device__ __forceinline__ void emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, 
     o.flags[idx] = fl;
     o.identity[idx] = idv;
   }
+  return key0;
 }
 
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ aos, u64 n, Geometry g, DecodeOut o) {
   extern __shared__ __align__(128) u8 stage_mem[];
   __shared__ __align__(8) u64 full_bar[DEC_STAGES];
   __shared__ u32 s_dropped, s_err;
+  __shared__ u32 s_hist[HIST_PASSES][HIST_RADIX];
 
   const u32 tid = threadIdx.x;
   const u64 full_tiles = n / DEC_TILE;
+  if (o.hist.ghist) hist_zero(s_hist);
   if (tid == 0) {
     for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&full_bar[s], 1);
     s_dropped = 0;
@@ -173,7 +177,8 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
     const u64 len = lds_u64_unaligned(rec_base, off + OFF_LENGTH);
     const u64 ident = lds_u64_unaligned(rec_base, off + OFF_IDENT);
     const u8 strand = rec_base[off + OFF_STRAND];
-    emit_fragment(tile * DEC_TILE + tid, xs, ys, len, ident, strand, g, o, dropped, err);
+    const u32 k0 = emit_fragment(tile * DEC_TILE + tid, xs, ys, len, ident, strand, g, o, dropped, err);
+    if (o.hist.ghist) hist_add(s_hist, k0, true, o.hist);
     __syncthreads();  // every thread is done reading stage s
     if (tid == 0) {
       const u64 nt = tile + (u64)DEC_STAGES * gridDim.x;
@@ -187,11 +192,13 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
   // ragged tail (n % 256 records): plain byte loads, one CTA
   if (blockIdx.x == 0) {
     const u64 idx = full_tiles * DEC_TILE + tid;
+    u32 k0 = 0;
     if (idx < n) {
       const u8 *p = aos + idx * FRAG_BYTES;
-      emit_fragment(idx, ldg_u64_bytes(p + OFF_XSTART), ldg_u64_bytes(p + OFF_YSTART), ldg_u64_bytes(p + OFF_LENGTH),
-                    ldg_u64_bytes(p + OFF_IDENT), p[OFF_STRAND], g, o, dropped, err);
+      k0 = emit_fragment(idx, ldg_u64_bytes(p + OFF_XSTART), ldg_u64_bytes(p + OFF_YSTART), ldg_u64_bytes(p + OFF_LENGTH),
+                         ldg_u64_bytes(p + OFF_IDENT), p[OFF_STRAND], g, o, dropped, err);
     }
+    if (o.hist.ghist) hist_add(s_hist, k0, idx < n, o.hist);
   }
 
   // one atomic per CTA for the dropped count and the error word
@@ -204,6 +211,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
     if (err) atomicOr(&s_err, err);
   }
   __syncthreads();
+  if (o.hist.ghist) hist_flush(s_hist, o.hist);
   if (tid == 0) {
     if (s_dropped) atomicAdd(o.n_dropped, s_dropped);
     if (s_err) atomicOr(o.err, s_err);
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
 }
 
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity, u32 *key0,
-                  u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4) {
+                  u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4, HistOut hist) {
   if (n == 0) return 0;
   static bool attr_set = false;
   const int smem = DEC_STAGES * DEC_TILE_BYTES;
@@ -225,7 +233,7 @@ int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, 
   const u64 full_tiles = n / DEC_TILE;
   u64 grid = (u64)sms * 2;  // two CTAs (2 x 84 KB of staging) per SM, persistent over the tiles
   if (grid > full_tiles) grid = full_tiles ? full_tiles : 1;
-  DecodeOut o{xs, ys, len, rec4, flags, identity, key0, link_x, link_y, n_dropped, err};
+  DecodeOut o{xs, ys, len, rec4, flags, identity, key0, link_x, link_y, n_dropped, err, hist};
   KScope ks(KID_DECODE, st, n);
   k_decode<<<(unsigned)grid, DEC_THREADS, smem, st>>>(aos, n, g, o);
   return 1;

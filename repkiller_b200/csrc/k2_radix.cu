@@ -402,7 +402,7 @@ u64 sort_work_bytes(u64 n) {
 }
 
 static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp, u32 *vals_tmp,
-                           u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word) {
+                           u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word, u32 *prehist) {
   const int passes = (key_bits + 7) / 8;
   const u32 tiles = (u32)((n + OS_TILE - 1) / OS_TILE);
   static bool attr_set = false;
@@ -410,7 +410,7 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
     cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM_BYTES);
     attr_set = true;
   }
-  u32 *ghist = reinterpret_cast<u32 *>(work);          // [4][256]
+  u32 *ghist = reinterpret_cast<u32 *>(work);          // [4][256] (or the producer's counters)
   u32 *counters = ghist + OS_MAX_PASSES * RADIX;          // [4] tile counters, [4] = error word when none was set
   u32 *state = counters + 64;                            // [passes][tiles][256]
   cudaMemsetAsync(work, 0, (OS_MAX_PASSES * RADIX + 64 + (u64)passes * tiles * RADIX) * 4, st);
@@ -418,7 +418,10 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  {
+  if (prehist) {  // the producer of the keys counted the digits (HistOut): only the bin bases are left to do
+    ghist = prehist;
+    k_onesweep_bases<<<passes, RADIX, 0, st>>>(ghist);
+  } else {
     KScope ks(KID_RADIX_HIST, st, n);
     u64 blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (blocks > (u64)sms * 8) blocks = (u64)sms * 8;
@@ -444,12 +447,12 @@ static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out
 }
 
 int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp,
-                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word) {
+                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word, u32 *prehist) {
   if (n == 0) return 0;
   if (key_bits < 1) key_bits = 1;
   if (key_bits > 32) key_bits = 32;
   static const bool force_3k = getenv("RK_SORT_3K") != nullptr;  // tuning switch: histogram + scan + scatter per pass
-  if (n < OS_MAX_N && !force_3k) return launch_onesweep(keys_in, vals_in, keys_out, vals_out, keys_tmp, vals_tmp, n, key_bits, work, st, err_word);
+  if (n < OS_MAX_N && !force_3k) return launch_onesweep(keys_in, vals_in, keys_out, vals_out, keys_tmp, vals_tmp, n, key_bits, work, st, err_word, prehist);
   const int passes = (key_bits + 7) / 8;
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
   u32 *counts = reinterpret_cast<u32 *>(work);

@@ -43,28 +43,58 @@ __device__ __forceinline__ u32 run_start(const u32 *__restrict__ bm, u32 k) {
 __global__ void __launch_bounds__(256)
     k_keys(const u32 *__restrict__ fidx_r, u32 m, Geometry g, const uint4 *__restrict__ rec4, const u32 *__restrict__ link_x,
            const u32 *__restrict__ link_y, uint2 *__restrict__ xl_r, uint2 *__restrict__ yl_r, u32 *__restrict__ ys_r,
-           u32 *__restrict__ kx, u32 *__restrict__ ky, float *__restrict__ identity_r) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  // one 32-byte gather (one sector): {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
-  const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
-  const uint4 rec = src[0];
-  identity_r[i] = __uint_as_float(src[1].x);
-  const u32 x = rec.x, y = rec.y, l = rec.z;
-  const u32 sc = rec.w & FL_REVERSE;
-  const u32 cx = x + l / 2, cy = y + l / 2;  // commonFunctions.cpp:55,59
-  xl_r[i] = make_uint2(cx, l);
-  yl_r[i] = make_uint2(cy, l);
-  ys_r[i] = y;
-  kx[i] = run_start(link_x, sc * g.nbx + cx / DIVISOR);
-  ky[i] = run_start(link_y, sc * g.nby + cy / DIVISOR);
+           u32 *__restrict__ kx, u32 *__restrict__ ky, float *__restrict__ identity_r, HistOut hx, HistOut hy) {
+  // the digit counts of the two sort keys are gathered here (the keys would otherwise be read again by each sort)
+  __shared__ u32 s_hx[HIST_PASSES][HIST_RADIX], s_hy[HIST_PASSES][HIST_RADIX];
+  const bool do_hist = hx.ghist != nullptr;
+  if (do_hist) {
+    hist_zero(s_hx);
+    hist_zero(s_hy);
+    __syncthreads();
+  }
+  // warp-uniform loop bounds: every lane takes part in the votes of hist_add
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < m; base += (u64)gridDim.x * blockDim.x) {
+    const u32 i = (u32)base + threadIdx.x;
+    const bool valid = i < m;
+    u32 kxv = 0, kyv = 0;
+    if (valid) {
+      // one 32-byte gather (one sector): {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
+      const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
+      const uint4 rec = src[0];
+      identity_r[i] = __uint_as_float(src[1].x);
+      const u32 x = rec.x, y = rec.y, l = rec.z;
+      const u32 sc = rec.w & FL_REVERSE;
+      const u32 cx = x + l / 2, cy = y + l / 2;  // commonFunctions.cpp:55,59
+      xl_r[i] = make_uint2(cx, l);
+      yl_r[i] = make_uint2(cy, l);
+      ys_r[i] = y;
+      kxv = run_start(link_x, sc * g.nbx + cx / DIVISOR);
+      kyv = run_start(link_y, sc * g.nby + cy / DIVISOR);
+      kx[i] = kxv;
+      ky[i] = kyv;
+    }
+    if (do_hist) {
+      hist_add(s_hx, kxv, valid, hx);
+      hist_add(s_hy, kyv, valid, hy);
+    }
+  }
+  if (do_hist) {
+    __syncthreads();
+    hist_flush(s_hx, hx);
+    hist_flush(s_hy, hy);
+  }
 }
 
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
-                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st) {
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x, HistOut hist_y) {
   if (m == 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u32 blocks = (m + 255) / 256;
+  if (hist_x.ghist && blocks > (u32)sms * 8) blocks = (u32)sms * 8;  // few CTAs: few histogram flushes
   KScope ks(KID_KEYS, st, m);
-  k_keys<<<(m + 255) / 256, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r);
+  k_keys<<<blocks, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r, hist_x, hist_y);
   return 1;
 }
 

@@ -19,24 +19,42 @@ struct LoadIsRoot {
 
 __global__ void __launch_bounds__(256) k_chase(const u32 *__restrict__ parent, const u32 *__restrict__ gid_of_root, u32 m,
                                                u32 *__restrict__ gid_rank, const u32 *__restrict__ total, u32 *n_groups,
-                                               u32 lo) {
-  // ranks lo .. lo+m-1 are resolved (lo = 0, m = all on a single GPU; a rank's slice in the multi-GPU stages)
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0) *n_groups = *total;
-  if (t >= m) return;
-  const u32 i = lo + t;
-  u32 r = i;
-  for (;;) {
-    const u32 p = parent[r];
-    if (p == RK_NONE32) break;
-    r = p;  // p < r always: terminates
+                                               u32 lo, HistOut ho) {
+  // ranks lo .. lo+m-1 are resolved (lo = 0, m = all on a single GPU; a rank's slice in the multi-GPU stages).
+  // The group ids are the keys of the K5b sort: their digit counts are gathered here.
+  __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
+  const bool do_hist = ho.ghist != nullptr;
+  if (do_hist) {
+    hist_zero(s_h);
+    __syncthreads();
   }
-  gid_rank[t] = gid_of_root[r];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_groups = *total;
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < m; base += (u64)gridDim.x * blockDim.x) {
+    const u32 t = (u32)base + threadIdx.x;
+    const bool valid = t < m;
+    u32 gidv = 0;
+    if (valid) {
+      u32 r = lo + t;
+      for (;;) {
+        const u32 p = parent[r];
+        if (p == RK_NONE32) break;
+        r = p;  // p < r always: terminates
+      }
+      gidv = gid_of_root[r];
+      gid_rank[t] = gidv;
+    }
+    if (do_hist) hist_add(s_h, gidv, valid, ho);
+  }
+  if (do_hist) {
+    __syncthreads();
+    hist_flush(s_h, ho);
+  }
 }
 
 u64 forest_work_bytes(u32 m) { return ((u64)m + scan_work_words(m)) * 4 + 256; }
 
-int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st, u32 lo, u32 cnt) {
+int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st, u32 lo, u32 cnt,
+                  HistOut hist) {
   if (cnt == 0xFFFFFFFFu) cnt = m;
   if (m == 0) {
     cudaMemsetAsync(n_groups, 0, sizeof(u32), st);
@@ -47,7 +65,12 @@ int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *
   int launches = exclusive_scan_u32(LoadIsRoot{parent}, gid_of_root, m, bsum, st);
   const u32 nb = (u32)(((u64)m + SCAN_CHUNK - 1) / SCAN_CHUNK);
   KScope ks(KID_CHASE, st, cnt);
-  k_chase<<<(cnt + 255) / 256 + (cnt == 0), 256, 0, st>>>(parent, gid_of_root, cnt, gid_rank, bsum + nb, n_groups, lo);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u32 blocks = (cnt + 255) / 256 + (cnt == 0);
+  if (hist.ghist && blocks > (u32)sms * 8) blocks = (u32)sms * 8;
+  k_chase<<<blocks, 256, 0, st>>>(parent, gid_of_root, cnt, gid_rank, bsum + nb, n_groups, lo, hist);
   return launches + 1;
 }
 

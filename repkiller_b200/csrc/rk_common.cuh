@@ -66,6 +66,45 @@ __device__ __forceinline__ bool probes_prev(u32 c) { return (c % DIVISOR) <= 1 &
 
 __device__ __forceinline__ u32 absdiff(u32 a, u32 b) { return a > b ? a - b : b - a; }
 
+// ---- digit histograms of a sort key, accumulated by the kernel that PRODUCES the key (saves the sort's own histogram
+// pass: one more read of the keys and a launch).  ghist: [4][256] global counters (zeroed by the caller), or nullptr.
+struct HistOut {
+  u32 *ghist;
+  int passes;    // ceil(key_bits / 8)
+  int key_bits;
+};
+constexpr int HIST_PASSES = 4, HIST_RADIX = 256;
+
+// One key per lane into a CTA's shared-memory histograms.  Every lane of the warp must call it (valid = false for
+// lanes without a key): a digit shared by the whole warp — the top digits of nearly sorted keys — is counted once by
+// lane 0 instead of serialising 32 atomics on one address.
+__device__ __forceinline__ void hist_add(u32 (*h)[HIST_RADIX], u32 key, bool valid, const HistOut &ho) {
+  const u32 last_mask = (1u << (ho.key_bits - 8 * (ho.passes - 1))) - 1;
+  const u32 lane = threadIdx.x & 31;
+#pragma unroll
+  for (int p = 0; p < HIST_PASSES; ++p) {
+    if (p < ho.passes) {
+      const u32 d = (key >> (8 * p)) & (p == ho.passes - 1 ? last_mask : 0xFFu);
+      const u32 d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
+      if (__all_sync(0xFFFFFFFFu, valid && d == d0)) {
+        if (lane == 0) atomicAdd(&h[p][d], 32u);
+      } else if (valid) {
+        atomicAdd(&h[p][d], 1u);
+      }
+    }
+  }
+}
+// all threads of the CTA: zero / flush (blockDim.x >= 256 or any multiple of 32; strided)
+__device__ __forceinline__ void hist_zero(u32 (*h)[HIST_RADIX]) {
+  for (u32 i = threadIdx.x; i < (u32)(HIST_PASSES * HIST_RADIX); i += blockDim.x) (&h[0][0])[i] = 0;
+}
+__device__ __forceinline__ void hist_flush(u32 (*h)[HIST_RADIX], const HistOut &ho) {
+  for (u32 i = threadIdx.x; i < (u32)(ho.passes * HIST_RADIX); i += blockDim.x) {
+    const u32 c = (&h[0][0])[i];
+    if (c) atomicAdd(&ho.ghist[i], c);
+  }
+}
+
 // ---- per-kernel timing (CUDA events around every launch; off unless rk_profile_enable) ---------------
 enum KernelId {
   KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
@@ -87,19 +126,23 @@ int launch_gen(u64 seed, u64 lx, u64 ly, double p_rep, u64 families, u64 ax, u64
 
 // K1: decode n packed records (device, 16-byte aligned) into file-order SoA, raise link bits.
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity,
-                  u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4 = nullptr);
+                  u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4 = nullptr,
+                  HistOut hist = HistOut{nullptr, 0, 0});
 
 // K2: stable LSD radix sort of (key,value) pairs; result in keys_out/vals_out.
 u64 sort_work_bytes(u64 n);
+// prehist: [4][256] digit counts of keys_in already accumulated by the producer of the keys (HistOut), or nullptr
 int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp,
-                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word = nullptr);
+                      u32 *vals_tmp, u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word = nullptr,
+                      u32 *prehist = nullptr);
 
 // K2 keys: rank-order SoA + super-bucket sort keys.
 // rec4: file order, two 16-byte words per record {xStart, yStart, length, flags} {identity bits, 0, 0, 0} (one 32-byte
 // sector per gather); xl_r/yl_r: rank-order {center, length} per axis (one 8-byte gather per fragment in the match
 // kernels); identity_r: rank order
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
-                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st);
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x = HistOut{nullptr, 0, 0},
+                HistOut hist_y = HistOut{nullptr, 0, 0});
 
 int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
                        const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
@@ -138,7 +181,7 @@ int launch_match(const MatchArgs &a, cudaStream_t st);
 u64 forest_work_bytes(u32 m);
 // lo/cnt: resolve only ranks [lo, lo+cnt) of a parent array of m entries (multi-GPU: the rank's own slice)
 int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st, u32 lo = 0,
-                  u32 cnt = 0xFFFFFFFFu);
+                  u32 cnt = 0xFFFFFFFFu, HistOut hist = HistOut{nullptr, 0, 0});
 
 // K5a: h = |yStart - yStart(last fragment of the same xStart/10 bucket)| per rank.
 // With hfi_r: also the packed per-rank record {h, file index, identity bits, 0} K5b/c gathers (h may then be null).
