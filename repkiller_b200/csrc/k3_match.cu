@@ -138,28 +138,48 @@ struct ColPtrs {
   u32 *out[8];
 };
 
-// rows[i][j] = cols[j][i]   (coalesced reads, row-major writes)
-__global__ void __launch_bounds__(256) k_interleave(ColPtrs c, u64 n, int k, u32 *__restrict__ rows) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  for (int j = 0; j < k; ++j) rows[i * k + j] = c.in[j][i];
+// The three row kernels work on tiles of 256 rows, one WORD of the tile per thread and step (word w of the tile is
+// column w % k of row w / k), so that the row side is always touched as contiguous runs of k words and the column
+// side along i.
+constexpr int ROW_TILE = 256;
+__device__ __forceinline__ u32 div_small(u32 w, u32 magic) { return (w * magic) >> 16; }  // w / k for w < 4096, k <= 8
+static inline u32 div_magic(int k) { return (65536u + (u32)k - 1) / (u32)k; }
+
+// rows[i][j] = cols[j][i]
+__global__ void __launch_bounds__(ROW_TILE) k_interleave(ColPtrs c, u64 n, int k, u32 magic, u32 *__restrict__ rows) {
+  const u64 i0 = (u64)blockIdx.x * ROW_TILE;
+  const u32 cnt = (u32)min((u64)ROW_TILE, n - i0);
+  u32 *dst = rows + i0 * k;
+  for (u32 w = threadIdx.x; w < cnt * (u32)k; w += ROW_TILE) {
+    const u32 r = div_small(w, magic), j = w - r * k;
+    dst[w] = c.in[j][i0 + r];
+  }
 }
 // out[i][:] = rows[idx[i]][:]
-__global__ void __launch_bounds__(256) k_gather_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
-                                                     u32 *__restrict__ out) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const u32 *src = rows + (u64)idx[i] * k;
-  for (int j = 0; j < k; ++j) out[i * k + j] = src[j];
+__global__ void __launch_bounds__(ROW_TILE) k_gather_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
+                                                          u32 magic, u32 *__restrict__ out) {
+  const u64 i0 = (u64)blockIdx.x * ROW_TILE;
+  const u32 cnt = (u32)min((u64)ROW_TILE, n - i0);
+  u32 *dst = out + i0 * k;
+  for (u32 w = threadIdx.x; w < cnt * (u32)k; w += ROW_TILE) {
+    const u32 r = div_small(w, magic), j = w - r * k;
+    dst[w] = rows[(u64)idx[i0 + r] * k + j];
+  }
 }
-// cols[j][i] = rows[idx ? idx[i] : i][j]   (row reads, coalesced column writes)
-__global__ void __launch_bounds__(256) k_unpack_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
-                                                     ColPtrs c) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const u32 *src = rows + (u64)(idx ? idx[i] : (u32)i) * k;
-  for (int j = 0; j < k; ++j)
-    if (c.out[j]) c.out[j][i] = src[j];
+// cols[j][i] = rows[idx ? idx[i] : i][j]
+__global__ void __launch_bounds__(ROW_TILE) k_unpack_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
+                                                          u32 magic, ColPtrs c) {
+  __shared__ u32 s[ROW_TILE * 8 + 8];
+  const u64 i0 = (u64)blockIdx.x * ROW_TILE;
+  const u32 cnt = (u32)min((u64)ROW_TILE, n - i0);
+  for (u32 w = threadIdx.x; w < cnt * (u32)k; w += ROW_TILE) {
+    const u32 r = div_small(w, magic), j = w - r * k;
+    s[w + (r >> 5)] = idx ? rows[(u64)idx[i0 + r] * k + j] : rows[i0 * k + w];  // one pad word per 32 rows (even k)
+  }
+  __syncthreads();
+  if (threadIdx.x < cnt)
+    for (int j = 0; j < k; ++j)
+      if (c.out[j]) c.out[j][i0 + threadIdx.x] = s[threadIdx.x * k + j + (threadIdx.x >> 5)];
 }
 // out[idx[i]] = v[i]
 __global__ void __launch_bounds__(256) k_scatter_u32(const u32 *__restrict__ v, const u32 *__restrict__ idx, u64 n,
@@ -172,19 +192,19 @@ int launch_interleave(const u32 *const *cols, u64 n, int k, u32 *rows, cudaStrea
   if (n == 0) return 0;
   ColPtrs c{};
   for (int j = 0; j < k; ++j) c.in[j] = cols[j];
-  k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, n, k, rows);
+  k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, n, k, div_magic(k), rows);
   return 1;
 }
 int launch_gather_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *out, cudaStream_t st) {
   if (n == 0) return 0;
-  k_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, out);
+  k_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, div_magic(k), out);
   return 1;
 }
 int launch_unpack_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *const *cols, cudaStream_t st) {
   if (n == 0) return 0;
   ColPtrs c{};
   for (int j = 0; j < k; ++j) c.out[j] = cols[j];
-  k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, c);
+  k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, div_magic(k), c);
   return 1;
 }
 int launch_scatter_u32(const u32 *v, const u32 *idx, u64 n, u32 *out, cudaStream_t st) {

@@ -32,6 +32,12 @@ import torch.distributed as dist
 NONE = -1  # 0xFFFFFFFF in the int32 bit containers used for all u32 columns
 
 
+def _iota_u32(n: int, start: int, device) -> torch.Tensor:
+    """start, start+1, ... as u32 values in an int32 container (two's complement wrap above 2^31)"""
+    s32 = ((int(start) + 2 ** 31) % 2 ** 32) - 2 ** 31
+    return torch.arange(n, dtype=torch.int32, device=device) + s32
+
+
 def ceil_log2(x: int) -> int:
     """bits needed for values 0 .. x-1 (at least 1)"""
     return max(1, (max(int(x), 1) - 1).bit_length())
@@ -334,7 +340,7 @@ def group_partitioned(st, comm: Comm, aos: torch.Tensor, n_local: int, file_offs
     k0s, lidx = st.sort_pairs(d["key0"], bits0)
     k0s, lidx = k0s[:kept], lidx[:kept]          # the dropped last X bucket carries the largest key: it sorts last
     # one 28-byte row per fragment: build the rows once (coalesced), then ONE row gather into send order
-    gf = torch.arange(file_offset, file_offset + n_local, dtype=torch.int64, device=dev).to(i32)
+    gf = _iota_u32(n_local, file_offset, dev)
     rows = st.pack([d["key0"], gf, d["xs"], d["ys"], d["len"], d["flags"].to(i32), d["identity"].view(i32)], lidx)
     recv, _ = comm.exchange(rows, comm.range_partition(k0s, bits0))
     (rkeys,) = st.unpack(recv, None, [0])
@@ -344,7 +350,7 @@ def group_partitioned(st, comm: Comm, aos: torch.Tensor, n_local: int, file_offs
     m = k0_r.shape[0]
     counts = comm.all_gather_ints(m, dev)
     off, m_total = sum(counts[: comm.rank]), sum(counts)
-    grank = (torch.arange(m, dtype=torch.int64, device=dev) + off).to(i32)
+    grank = _iota_u32(m, off, dev)
 
     mark("redistribute:rank")
     # -- K2 keys
