@@ -99,6 +99,37 @@ void parse_range(const char *data, size_t begin, size_t end, bool last_range, Pa
 }
 }  // namespace
 
+// The data rows of text[pos, size) parsed by nthreads threads: the text is cut at row boundaries into one range per
+// thread, every thread keeps its accepted rows in file order, and the ranges are returned in order — the same
+// records, in the same order, as the reference's row-by-row loop (FragmentsDatabase.cpp:92-100).
+std::vector<std::vector<FragFile>> parse_rows_parallel(const std::string &data, size_t pos, unsigned nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  const size_t body = data.size() - pos;
+  std::vector<size_t> cut(nthreads + 1, data.size());
+  cut[0] = pos;
+  for (unsigned t = 1; t < nthreads; ++t) {
+    size_t c = pos + body / nthreads * t;
+    if (c < cut[t - 1]) c = cut[t - 1];
+    while (c > 0 && c < data.size() && data[c - 1] != '\n') ++c;  // move to the start of the next row
+    cut[t] = c;
+  }
+  std::vector<ParsedChunk> chunks(nthreads);
+  if (!data.empty()) {  // reference: an empty stream never enters the row loop
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; ++t) {
+      const bool last = t + 1 == nthreads;
+      if (!last && cut[t] >= cut[t + 1]) continue;  // empty range
+      chunks[t].rows.reserve((cut[t + 1] - cut[t]) / 48 + 16);  // GECKO rows are 60..90 bytes
+      pool.emplace_back(parse_range, data.data(), cut[t], cut[t + 1], last, &chunks[t]);
+    }
+    for (auto &th : pool) th.join();
+  }
+  std::vector<std::vector<FragFile>> out(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t) out[t].swap(chunks[t].rows);
+  return out;
+}
+
 FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device) {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
@@ -144,24 +175,11 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   seq_manager.read_header(header);
   vsize = 1 + seq_manager.get_sequence_by_label(0).len / 10;  // :84
 
-  // The rows are parsed by all host cores: the text is cut at row boundaries into one range per thread, every thread
-  // keeps its accepted rows in file order, and the ranges are concatenated in order — the same records, in the same
-  // order, as the reference's row-by-row loop.
+  // the rows are parsed by all host cores (RK_PARSE_THREADS overrides the count)
   unsigned nthreads = std::thread::hardware_concurrency();
-  if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
   const size_t body = data.size() - pos;
   if (nthreads < 1 || body < (1u << 20)) nthreads = 1;
-  if (nthreads > 64) nthreads = 64;
-  std::vector<size_t> cut(nthreads + 1, data.size());
-  cut[0] = pos;
-  for (unsigned t = 1; t < nthreads; ++t) {
-    size_t c = pos + body / nthreads * t;
-    if (c < cut[t - 1]) c = cut[t - 1];
-    while (c < data.size() && data[c - 1] != '\n') ++c;  // move to the start of the next row (c > pos >= 1 here)
-    cut[t] = c;
-  }
-  std::vector<ParsedChunk> chunks(nthreads);
-  bool eof_only = data.empty();  // reference: an empty stream never enters the row loop
+  if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
   // pinned memory for the records (full-speed H2D) is allocated beside the parse, for at most min(T, bytes / 28) records:
   // a file with more accepted rows than its header announces is an error anyway, and a row that readFragment accepts
   // has 14 non-empty fields ("Frag" first) and 13 commas, i.e. at least 30 bytes with its line end
@@ -171,18 +189,9 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
   std::thread alloc_thread([this] { records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16); });
   Joiner alloc_joiner{alloc_thread};
-  if (!eof_only) {
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < nthreads; ++t) {
-      const bool last = t + 1 == nthreads;
-      if (!last && cut[t] >= cut[t + 1]) continue;  // empty range
-      chunks[t].rows.reserve((cut[t + 1] - cut[t]) / 48 + 16);  // GECKO rows are 60..90 bytes
-      pool.emplace_back(parse_range, data.data(), cut[t], cut[t + 1], last, &chunks[t]);
-    }
-    for (auto &th : pool) th.join();
-  }
+  std::vector<std::vector<FragFile>> chunks = parse_rows_parallel(data, pos, nthreads);
   uint64_t accepted = 0;
-  for (const auto &c : chunks) accepted += c.rows.size();
+  for (const auto &c : chunks) accepted += c.size();
   alloc_thread.join();
   if (accepted > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
   if (!records_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
@@ -190,8 +199,8 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
     std::vector<std::thread> pool;
     uint64_t off = 0;
     for (auto &c : chunks) {
-      if (!c.rows.empty()) pool.emplace_back([this, off, &c] { memcpy(records_ + off, c.rows.data(), c.rows.size() * sizeof(FragFile)); });
-      off += c.rows.size();
+      if (!c.empty()) pool.emplace_back([this, off, &c] { memcpy(records_ + off, c.data(), c.size() * sizeof(FragFile)); });
+      off += c.size();
     }
     for (auto &th : pool) th.join();
   }

@@ -6,11 +6,14 @@
 #include <cstdint>
 #include <fstream>
 #include <string>
+#include <vector>
 
 #include "rk_b200.h"
 #include "structs.h"
 
 bool readFragment(FragFile *frag, const char *line, size_t len);  // reference: FragmentsDatabase.cpp:17-50
+// data rows of text[pos, size) parsed by nthreads threads; the accepted records of consecutive ranges, in file order
+std::vector<std::vector<FragFile>> parse_rows_parallel(const std::string &text, size_t pos, unsigned nthreads);
 
 class FragmentsDatabase {
   FragFile *records_ = nullptr;  // file order, pinned

@@ -1,5 +1,7 @@
 // Test helper for the host side of the drop-in.
-//   rk_hostcheck parse <in.csv> <out.bin>     readFragment over every data row: accepted records, 109 B each (no GPU)
+//   rk_hostcheck parse <in.csv> <out.bin> [threads]
+//                                             readFragment over every data row: accepted records, 109 B each (no GPU);
+//                                             with a thread count: through parse_rows_parallel, the database's parser
 //   rk_hostcheck write <in.csv> <out.csv>     writer format: parses, then writes every accepted record as its own
 //                                             singleton group in file order (no GPU)
 //   rk_hostcheck steps <in.csv> <out.csv> <len_ratio> <pos_ratio>
@@ -7,6 +9,7 @@
 //                                             generate_fragment_groups -> generate_diagonal_func -> sort_groups ->
 //                                             save_all_frag_pairs, each through its own facade (GPU)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -45,7 +48,19 @@ int main(int argc, char **argv) {
   if (argc < 4) return 2;
   const std::string mode = argv[1];
   if (mode == "parse") {
-    auto recs = parse_rows(argv[2], nullptr);
+    std::vector<FragFile> recs;
+    if (argc >= 5) {  // the multi-threaded parser of FragmentsDatabase
+      std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+      std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+      size_t pos = 0;
+      for (int ln = 0; ln < 16; ++ln) {
+        while (pos < data.size() && data[pos] != '\n') ++pos;
+        if (pos < data.size()) ++pos;
+      }
+      for (auto &c : parse_rows_parallel(data, pos, (unsigned)atoi(argv[4]))) recs.insert(recs.end(), c.begin(), c.end());
+    } else {
+      recs = parse_rows(argv[2], nullptr);
+    }
     FILE *f = fopen(argv[3], "wb");
     if (!f) return 3;
     if (!recs.empty()) fwrite(recs.data(), sizeof(FragFile), recs.size(), f);

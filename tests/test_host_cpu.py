@@ -24,6 +24,20 @@ def test_csv_parser_matches_oracle_on_fuzz(tmp_path, fuzz_cases):
         assert got.tobytes() == want.tobytes(), f"fuzz seed {c['seed']}"
 
 
+def test_parallel_parser_matches_oracle_for_any_thread_count(tmp_path, fuzz_cases):
+    """FragmentsDatabase parses the rows with all host cores (ranges cut at row boundaries, concatenated in order): the
+    records must be those of the row-by-row loop for every thread count, also when there are more threads than rows."""
+    for c in fuzz_cases[::3]:
+        inp = tmp_path / "in.csv"
+        inp.write_text(c["csv"], newline="")
+        want, _, _, _ = O.load_csv(str(inp))
+        for threads in (1, 2, 3, 7, 16, 64):
+            out = tmp_path / "recs.bin"
+            subprocess.check_call([HOSTCHECK, "parse", str(inp), str(out), str(threads)])
+            got = np.fromfile(out, dtype=FRAG_DTYPE)
+            assert got.tobytes() == want.tobytes(), f"fuzz seed {c['seed']}, {threads} threads"
+
+
 def test_writer_line_format_matches_reference(tmp_path, fuzz_cases):
     """Every line the reference wrote for a singleton group (repval 0) must be reproduced byte for byte by the
     host writer from the same record (float formatting of similarity and identity, '-nan', strand bytes)."""
