@@ -8,7 +8,8 @@
 // 16) is staged into shared memory with one cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) per tile, three
 // tiles in flight per CTA behind mbarriers; each thread then pulls its record's fields out of shared memory
 // with aligned 32-bit reads + funnel shifts (record stride 27.25 words: near conflict-free) and the SoA is
-// written fully coalesced.  HBM-bound: 109 B read + 21 B written per fragment.
+// written fully coalesced.  HBM-bound: 109 B read + 36 B written per fragment (a 32-byte record + the sort key); the
+// digit counts of the key are gathered on the way for the rank sort (HistOut).
 #include "rk_common.cuh"
 
 namespace rk {

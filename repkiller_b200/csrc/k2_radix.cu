@@ -6,11 +6,14 @@
 // one list per center/100).  Stability is what carries the reference's visiting order (file order inside an
 // X bucket, processing order inside an occupation bucket).
 //
-// Per digit pass: (1) per-tile digit histogram, (2) exclusive scan of the [digit][tile] count matrix,
-// (3) scatter: a 4096-key tile is ranked stably inside the CTA (warp-level match_any multisplit + per-warp
-// digit counters), reordered through shared memory so that each digit's run leaves as one contiguous,
-// coalesced store, and placed at the scanned global offset.  HBM traffic per pass and key: 4 B (histogram)
-// + 8 B read + 8 B written.
+// One-sweep passes (the path every call below 2^30 elements takes): the digit counts of all passes come from the
+// kernel that produced the keys (HistOut in rk_common.cuh) or from k_onesweep_hist; then one kernel per digit: a
+// 4096-key tile is ranked stably inside the CTA (ballot multisplit + per-warp digit counters), reordered through
+// shared memory so that each digit's run leaves as one contiguous store, and placed at the offset its tile obtains
+// by decoupled look-back over the preceding tiles' counts.  Algorithmic traffic per pass and key: 8 B read + 8 B
+// written (served by the 126 MB L2 for the 10M-element sorts of config 2).
+// The three-kernel variant (per-tile histogram, scan of the [digit][tile] matrix, scatter) is kept for n >= 2^30 and
+// as a tuning reference (RK_SORT_3K).
 #include <cstdlib>
 
 #include "rk_common.cuh"

@@ -13,8 +13,9 @@
 // the link bits raised by K1).  Fragments arrive here stably sorted by (strand class, first bucket of their
 // run): every run is a contiguous segment in processing order and segments are independent of one another.
 //
-//   tier 1: segments of <= 32 fragments (the typical segment holds 3): candidate masks for every fragment in
-//           parallel, then the head's thread replays the segment with bit operations (see k_match_small).
+//   tier 1: segments of <= 32 fragments (the typical segment holds 3; a repeat family about a dozen): independent
+//           warps on 64-position windows — candidate masks from a pair-balanced search, then the insertion status of
+//           every member in a few ballot rounds, then the owners (see k_match_small).
 //   tier 2: one warp per longer segment: 32 queries at a time are scored against the entry list (uniform
 //           loads, each lane its own query), then the insertions inside the chunk are replayed in order with
 //           ballots; work per query is O(entries), not O(segment).

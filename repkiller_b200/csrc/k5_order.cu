@@ -11,7 +11,10 @@
 // so the member order of a group is whatever libstdc++'s introsort does with that input; K5b therefore runs
 // the same algorithm (bits/stl_algo.h: __introsort_loop with the median-of-three to *first, unguarded
 // partition, depth limit 2*lg(n) with heap-sort fallback, threshold 16, final insertion sort) on
-// (h << 32 | rank) words, comparing the high halves only.
+// (h << 32 | index) words, comparing the high halves only — in parallel: groups of <= 16 by a stable rank per member,
+// larger ones by a warp whose partition step is computed from ballot masks (see warp_partition), the largest split
+// across warps after the top of the recursion.  Only __partial_sort (the heap-sort fallback at the depth limit) runs on
+// one lane.
 #include "rk_common.cuh"
 
 namespace rk {
@@ -71,7 +74,7 @@ int launch_diag_table(const u32 *k0_r, const u32 *ys_r, u32 m, u32 vsize, u64 *d
   return 1;
 }
 
-// ---- K5b: libstdc++ std::sort, restated over an indexable array of packed (h,rank) words ----------------
+// ---- K5b: pieces of libstdc++'s std::sort over an indexable array of packed (h, index) words ---------------
 
 __device__ __forceinline__ bool hless(u64 a, u64 b) { return (u32)(a >> 32) < (u32)(b >> 32); }
 
@@ -132,99 +135,10 @@ __device__ void dev_heap_sort(P a, int len) {
   }
 }
 
-template <class P>
-__device__ __forceinline__ void dev_unguarded_linear_insert(P a, int last) {
-  const u64 val = a[last];
-  int next = last - 1;
-  while (hless(val, a[next])) {
-    a[last] = a[next];
-    last = next;
-    --next;
-  }
-  a[last] = val;
-}
-
-template <class P>
-__device__ void dev_insertion_sort(P a, int first, int last) {
-  if (first == last) return;
-  for (int i = first + 1; i != last; ++i) {
-    if (hless(a[i], a[first])) {
-      const u64 val = a[i];
-      for (int k = i; k > first; --k) a[k] = a[k - 1];  // move_backward
-      a[first] = val;
-    } else {
-      dev_unguarded_linear_insert(a, i);
-    }
-  }
-}
-
 struct SubArray {  // a[first..] view so the heap code can stay zero-based
   u64 *p;
   __device__ __forceinline__ u64 &operator[](int i) const { return p[i]; }
 };
-
-template <class P>
-__device__ void dev_std_sort(P a, int n) {
-  if (n <= 1) return;
-  if (n > 16) {
-    int lg = 0;
-    for (int t = n; t > 1; t >>= 1) ++lg;
-    // __introsort_loop; the two sides of a partition are independent, so the recursion order is free: keep
-    // iterating on the smaller side and stack the larger one (stack depth <= lg n).
-    int st_first[40], st_last[40], st_depth[40];
-    int sp = 0;
-    st_first[0] = 0, st_last[0] = n, st_depth[0] = 2 * lg;
-    sp = 1;
-    while (sp > 0) {
-      --sp;
-      int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
-      while (last - first > 16) {
-        if (depth == 0) {
-          SubArray sub{&a[first]};
-          dev_heap_sort(sub, last - first);
-          break;
-        }
-        --depth;
-        // __unguarded_partition_pivot: median of (first+1, mid, last-1) moved to first
-        const int mid = first + (last - first) / 2;
-        {
-          const int x = first + 1, y = mid, z = last - 1;
-          if (hless(a[x], a[y])) {
-            if (hless(a[y], a[z])) swp(a, first, y);
-            else if (hless(a[x], a[z])) swp(a, first, z);
-            else swp(a, first, x);
-          } else if (hless(a[x], a[z])) swp(a, first, x);
-          else if (hless(a[y], a[z])) swp(a, first, z);
-          else swp(a, first, y);
-        }
-        int lo = first + 1, hi = last;
-        const u64 pivot = a[first];
-        for (;;) {
-          while (hless(a[lo], pivot)) ++lo;
-          --hi;
-          while (hless(pivot, a[hi])) --hi;
-          if (!(lo < hi)) break;
-          swp(a, lo, hi);
-          ++lo;
-        }
-        const int cut = lo;
-        // left = [first, cut), right = [cut, last), both continue with `depth`
-        if (cut - first < last - cut) {
-          if (sp < 40) { st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; ++sp; }
-          last = cut;
-        } else {
-          if (sp < 40) { st_first[sp] = first; st_last[sp] = cut; st_depth[sp] = depth; ++sp; }
-          first = cut;
-        }
-      }
-    }
-    // __final_insertion_sort
-    dev_insertion_sort(a, 0, 16);
-    for (int i = 16; i != n; ++i) dev_unguarded_linear_insert(a, i);
-  } else {
-    dev_insertion_sort(a, 0, n);
-  }
-}
 
 constexpr int GS_STABLE = 16;        // std::sort of <= 16 elements is one insertion sort == a stable sort by h
 constexpr int GS_WARP_CAP0 = 128;    // groups of 17..128 members: one warp each, 2 KB of shared memory per warp

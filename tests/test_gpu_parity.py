@@ -375,3 +375,18 @@ def test_group_order_is_libstdcxx_sort_for_every_size_and_pattern(ctx):
         assert np.array_equal(idn[pos:pos + n].view(np.uint32), ident[want].view(np.uint32))
         assert np.array_equal(rep[pos:pos + n], np.r_[0 if n == 1 else 1, np.full(n - 1, 2)].astype(np.uint8))
         pos += n
+
+
+def test_two_giant_families_small_input(ctx):
+    """60k fragments, 90 % of them in two repeat families: segments and groups of tens of thousands of members on a
+    small input (tier 2 of K3, the giant-group path of K5b) — every stage against the oracle, and the device text."""
+    from dataclasses import replace
+    w = replace(gen.scaled(gen.WORKLOADS["c3"], 60_000), families=2)
+    rec = gen.generate(w)
+    res, g = check_against_oracle(ctx, rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
+    assert np.bincount(res.gid).max() > 1024
+    g.order, g.out_gid, g.repval, g.identity = res.order, res.gid, res.repval, res.identity
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        O.write_output(os.path.join(d, "o.csv"), b"", rec, g)
+        assert open(os.path.join(d, "o.csv"), "rb").read() == ctx.format_lines()
