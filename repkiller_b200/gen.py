@@ -54,6 +54,11 @@ WORKLOADS = {
     "c1": Workload("c1", 100_000, 5_000_000, 5_000_000, 0.3, 500, seed=1),
     "c2": Workload("c2", 10_000_000, 150_000_000, 150_000_000, 0.3, 50_000, seed=2),
     "c3": Workload("c3", 10_000_000, 150_000_000, 150_000_000, 0.9, 200, tandem_every=2, seed=3),
+    # config 4 (5,000-contig draft assembly vs a 150 Mbp reference, 50M fragments).  The reference reads every row as
+    # sequence pair (0, 1) — seqX/seqY are hard-coded, FragmentsDatabase.cpp:41-42 — so a multi-contig file is ONE
+    # comparison over the concatenated X coordinates: contigs with log-uniform lengths 2 kbp..2 Mbp add up to about
+    # 1.45 Gbp, fragments land on a contig in proportion to its length, i.e. uniformly on the concatenated axis.
+    "c4": Workload("c4", 50_000_000, 1_450_000_000, 150_000_000, 0.3, 250_000, seed=4),
     "c5": Workload("c5", 1_000_000_000, 3_000_000_000, 3_000_000_000, 0.3, 5_000_000, seed=5),
 }
 

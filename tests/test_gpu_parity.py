@@ -390,3 +390,11 @@ def test_two_giant_families_small_input(ctx):
     with tempfile.TemporaryDirectory() as d:
         O.write_output(os.path.join(d, "o.csv"), b"", rec, g)
         assert open(os.path.join(d, "o.csv"), "rb").read() == ctx.format_lines()
+
+
+def test_config4_shape_dense_y_axis(ctx):
+    """BASELINE config 4 at 1/50 of its size (same densities): a 1.45 Gbp concatenation of contigs against a 150 Mbp
+    sequence puts ~17 fragments per strand into every Y bucket, so most Y segments exceed 32 fragments (tier 2)."""
+    w = gen.scaled(gen.WORKLOADS["c4"], 1_000_000)
+    rec = gen.generate(w)
+    check_against_oracle(ctx, rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
