@@ -557,20 +557,21 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
         if (qp == 0 || (ql == 2 && qp == 2)) return 0.0;
         return deviation(ec, el, c, len, tl.t, tp.t);
       };
-      // phase A: entries inserted before this chunk, newest first (uniform loads)
-      if (__any_sync(0xFFFFFFFFu, needq)) {
-        for (u32 t = n_ent; t-- > 0;) {
-          const u32 er = e_rank[t];
-          if (er == RK_NONE32) continue;  // retired duplicate (uniform branch)
-          const u32 ec = e_c[t], el = e_len[t];
-          if (needq) {
-            bool own;
-            const double sc = score(ec, el, own);
-            if (sc > best_sc || (sc == best_sc && best != RK_NONE32 && own && !best_own)) {
-              best_sc = sc;
-              best = er;
-              best_own = own;
-            }
+      // phase A: entries inserted before this chunk, newest first (uniform loads).  Every lane scores its query and,
+      // because any lane may become an entry in phase B, notes the live entry with its own (center, length).
+      u32 dup_idx = RK_NONE32;
+      for (u32 t = n_ent; t-- > 0;) {
+        const u32 er = e_rank[t];
+        if (er == RK_NONE32) continue;  // retired duplicate (uniform branch)
+        const u32 ec = e_c[t], el = e_len[t];
+        if (ec == c && el == len) dup_idx = t;  // at most one entry per (center, length) is live
+        if (needq) {
+          bool own;
+          const double sc = score(ec, el, own);
+          if (sc > best_sc || (sc == best_sc && best != RK_NONE32 && own && !best_own)) {
+            best_sc = sc;
+            best = er;
+            best_own = own;
           }
         }
       }
@@ -583,22 +584,17 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
         const u32 Lc = __shfl_sync(0xFFFFFFFFu, c, L);
         const u32 Ll = __shfl_sync(0xFFFFFFFFu, len, L);
         const u32 Lr = __shfl_sync(0xFFFFFFFFu, r, L);
-        // retire the live entry with the same (center, length), if any (at most one is live)
-        for (u32 t0 = 0; t0 < n_ent; t0 += 32) {
-          const u32 t = t0 + lane;
-          const bool dup = t < n_ent && e_c[t] == Lc && e_len[t] == Ll && e_rank[t] != RK_NONE32;
-          const u32 hit = __ballot_sync(0xFFFFFFFFu, dup);
-          if (hit) {
-            if (dup) e_rank[t] = RK_NONE32;
-            ++n_dead;
-            break;
-          }
-        }
+        // retire the live entry with the same (center, length), if any: the one phase A found, or the one an earlier
+        // lane of this chunk has appended since (every lane tracks the live entry of its own pair)
+        const u32 kill = __shfl_sync(0xFFFFFFFFu, dup_idx, L);
+        if (kill != RK_NONE32) ++n_dead;
         if ((int)lane == L) {
+          if (kill != RK_NONE32) e_rank[kill] = RK_NONE32;
           e_rank[n_ent] = r;
           e_c[n_ent] = c;
           e_len[n_ent] = len;
         }
+        if (c == Lc && len == Ll) dup_idx = n_ent;
         ++n_ent;
         if ((int)lane > L && needq) {
           // the new entry is the newest: it is scanned before every older entry of its bucket class
@@ -611,7 +607,6 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
           }
         }
         pending &= ~((2u << L) - 1u);  // lanes <= L are final
-        __syncwarp();                  // the entry stores are read by the duplicate search of the next insertion
       }
       if (valid && !xm) {
         if (best != RK_NONE32) store_owner(a, q, r, best);
