@@ -543,37 +543,59 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
       double best_sc = 0.0;
       u32 best = RK_NONE32;
       bool best_own = false;
-      // score of entry (ec, el) for this lane's query, 0 when it is not a candidate
-      auto score = [&](u32 ec, u32 el, bool &own) -> double {
+      u32 best_dl = 0, best_dc = 0;  // the two differences of the best entry so far
+      // Exact scores cost two fp64 divisions; most of them are avoidable.  For one query the score is a function of
+      // (dl, dc) that falls STRICTLY when either difference grows (every rounding step is monotone, and with
+      // t = length*ratio < 2^30 one unit of difference moves a term by far more than an ulp).  So an entry whose
+      // differences are both >= the best's is either the same pair of differences — the same score, only the tie rule
+      // speaks — or strictly worse, and nothing has to be computed.
+      const bool prune_ok = tl.t < 0x1p30 && tp.t < 0x1p30;
+      // is entry (ec, el) a candidate (deviation > 0) of this lane's query?
+      auto candidate = [&](u32 ec, u32 el, bool &own, u32 &dl, u32 &dc) -> bool {
         const u32 bk = ec / DIVISOR;
         own = bk == b;
-        if (!own && bk != nbk) return 0.0;
-        const u32 dl = len > el ? len - el : el - len;
-        const u32 dc = c > ec ? c - ec : ec - c;
-        if (dl > tl.rej || dc > tp.rej) return 0.0;
+        if (!own && bk != nbk) return false;
+        dl = len > el ? len - el : el - len;
+        dc = c > ec ? c - ec : ec - c;
+        if (dl > tl.rej || dc > tp.rej) return false;
         const int ql = quotient_vs_one(dl, tl);
-        if (ql == 0) return 0.0;
+        if (ql == 0) return false;
         const int qp = quotient_vs_one(dc, tp);
-        if (qp == 0 || (ql == 2 && qp == 2)) return 0.0;
-        return deviation(ec, el, c, len, tl.t, tp.t);
+        return !(qp == 0 || (ql == 2 && qp == 2));
       };
       // phase A: entries inserted before this chunk, newest first (uniform loads).  Every lane scores its query and,
       // because any lane may become an entry in phase B, notes the live entry with its own (center, length).
+      // The list is read 32 entries at a time, one entry per lane (coalesced), and handed round with shuffles: the
+      // inner loop then waits for no memory at all (a uniform load per entry cost two dependent cache round trips).
       u32 dup_idx = RK_NONE32;
-      for (u32 t = n_ent; t-- > 0;) {
-        const u32 er = e_rank[t];
-        if (er == RK_NONE32) continue;  // retired duplicate (uniform branch)
-        const u32 ec = e_c[t], el = e_len[t];
-        if (ec == c && el == len) dup_idx = t;  // at most one entry per (center, length) is live
-        if (needq) {
-          bool own;
-          const double sc = score(ec, el, own);
-          if (sc > best_sc || (sc == best_sc && best != RK_NONE32 && own && !best_own)) {
-            best_sc = sc;
-            best = er;
-            best_own = own;
+      for (u32 hi = n_ent; hi > 0;) {
+        const u32 cnt = hi < 32 ? hi : 32, base_t = hi - cnt;
+        u32 er_l = RK_NONE32, ec_l = 0, el_l = 0;
+        if (lane < cnt) er_l = e_rank[base_t + lane], ec_l = e_c[base_t + lane], el_l = e_len[base_t + lane];
+        u32 live = __ballot_sync(0xFFFFFFFFu, er_l != RK_NONE32);  // retired duplicates are skipped
+        while (live) {
+          const int j = 31 - __clz(live);  // newest first
+          live &= ~(1u << j);
+          const u32 t = base_t + (u32)j;
+          const u32 er = __shfl_sync(0xFFFFFFFFu, er_l, j), ec = __shfl_sync(0xFFFFFFFFu, ec_l, j), el = __shfl_sync(0xFFFFFFFFu, el_l, j);
+          if (ec == c && el == len) dup_idx = t;  // at most one entry per (center, length) is live
+          if (needq) {
+            bool own;
+            u32 dl, dc;
+            if (candidate(ec, el, own, dl, dc)) {
+              if (prune_ok && best != RK_NONE32 && dl >= best_dl && dc >= best_dc) {
+                // same differences: same score, an older entry only wins with the own-bucket rule; else strictly worse
+                if (dl == best_dl && dc == best_dc && own && !best_own) best = er, best_own = true;
+              } else {
+                const double sc = deviation(ec, el, c, len, tl.t, tp.t);
+                if (sc > best_sc || (sc == best_sc && best != RK_NONE32 && own && !best_own)) {
+                  best_sc = sc, best = er, best_own = own, best_dl = dl, best_dc = dc;
+                }
+              }
+            }
           }
         }
+        hi = base_t;
       }
       // phase B: replay the insertions of this chunk in order
       u32 pending = __ballot_sync(0xFFFFFFFFu, valid);
@@ -599,11 +621,16 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
         if ((int)lane > L && needq) {
           // the new entry is the newest: it is scanned before every older entry of its bucket class
           bool own;
-          const double sc = score(Lc, Ll, own);
-          if (sc > best_sc || (sc == best_sc && sc > 0.0 && (own || !best_own))) {
-            best_sc = sc;
-            best = Lr;
-            best_own = own;
+          u32 dl, dc;
+          if (candidate(Lc, Ll, own, dl, dc)) {
+            if (prune_ok && best != RK_NONE32 && dl >= best_dl && dc >= best_dc) {
+              if (dl == best_dl && dc == best_dc && (own || !best_own)) best = Lr, best_own = own;  // same score, newer
+            } else {
+              const double sc = deviation(Lc, Ll, c, len, tl.t, tp.t);
+              if (sc > best_sc || (sc == best_sc && sc > 0.0 && (own || !best_own))) {
+                best_sc = sc, best = Lr, best_own = own, best_dl = dl, best_dc = dc;
+              }
+            }
           }
         }
         pending &= ~((2u << L) - 1u);  // lanes <= L are final
