@@ -32,7 +32,7 @@ UNIT = "fragments/s"
 CPU_SAMPLE_N = 1_000_000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {  # profiles/r01b_ncu_full_top_kernels.json (C2, 10M fragments), mean over the launches of a step
-    "k_match_small": 470000000, "k_radix_scatter": 98000000, "k_order_tile": 425000000, "k_keys": 1427000000,
+    "k_match_small": 472000000, "k_radix_scatter": 98000000, "k_keys": 1429000000, "k_decode": 1430000000,
 }
 
 
