@@ -378,7 +378,10 @@ def ours(args):
             "checksum": checksum,
             "e2e": {"value": e2e_value if do_e2e else None, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(lines * 13 + 40),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(sum(v[0] for v in prof.values())) if prof else None,
+            # kernels of this library launched inside timed region 1 (the C ABI counts them per call); the partitioned
+            # path reports its timed launch groups (torch's own kernels and NCCL are not counted)
+            "gpu_launches": (int((st.n_launches + res.n_launches) * args.steps) if not partitioned
+                             else (int(sum(v[0] for v in prof.values())) if prof else None)),
             "clocks": clocks,
             "roofline": roofline,
             "pipeline_alg_bytes_per_fragment": round(total_alg / args.steps / n, 1),
