@@ -4,6 +4,8 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
+#include <memory>
 #include <stdexcept>
 #include <thread>
 #include <vector>
@@ -16,6 +18,55 @@
 //  * a trailing ',' produces one empty token (row rejected);
 //  * field 0 must be "Frag" (:29); numeric fields through atoll; similarity AND ident from stof(field 10)
 //    (:39-40; field 9 is ignored); a row whose similarity does not parse is rejected (:46-48).
+namespace {
+// atoll / strtof are what the reference calls; the two helpers below return the same values for the plain tokens a GECKO
+// file is made of (all digits; digits[.digits]) without the copy, the locale machinery and the errno round trip, and
+// say "no" for everything else (signs, blanks, exponents, overlong tokens), which then takes the library call.
+inline bool plain_u64(const char *p, size_t n, uint64_t &v) {  // 1..18 digits: below 2^63, atoll returns the same
+  if (n == 0 || n > 18) return false;
+  uint64_t x = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const unsigned c = (unsigned char)p[i] - '0';
+    if (c > 9) return false;
+    x = x * 10 + c;
+  }
+  v = x;
+  return true;
+}
+// digits[.digits] with an integer mantissa below 2^53 and at most 22 fraction digits: mantissa and power of ten are
+// exact doubles, their quotient is the correctly rounded double, and narrowing it gives the correctly rounded float
+// (what strtof returns) unless the double sits on the midpoint of two floats — then the library decides.
+inline bool plain_float(const char *p, size_t n, float &out) {
+  static const double P10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  uint64_t m = 0;
+  int digits = 0, frac = 0;
+  bool dot = false;
+  for (size_t i = 0; i < n; ++i) {
+    const unsigned c = (unsigned char)p[i] - '0';
+    if (c <= 9) {
+      if (++digits > 18) return false;
+      m = m * 10 + c;
+      frac += dot;
+    } else if (p[i] == '.' && !dot) {
+      dot = true;
+    } else {
+      return false;
+    }
+  }
+  if (digits == 0 || frac > 22 || m >= (1ull << 53)) return false;
+  const double d = (double)m / P10[frac];
+  uint64_t bits;
+  memcpy(&bits, &d, sizeof bits);
+  const uint32_t low = (uint32_t)(bits & 0x1FFFFFFFu);  // the 29 bits a float drops
+  if (low >= 0x0FFFFFFFu && low <= 0x10000001u) return false;
+  out = (float)d;
+  return true;
+}
+}  // namespace
+
+bool parse_plain_float(const char *p, size_t n, float *out) { return plain_float(p, n, *out); }
+
 bool readFragment(FragFile *frag, const char *line, size_t len) {
   const char *tok[14];
   size_t tlen[14];
@@ -44,20 +95,27 @@ bool readFragment(FragFile *frag, const char *line, size_t len) {
     buf[l] = 0;
     return buf;
   };
-  frag->xStart = (uint64_t)atoll(cstr(1));
-  frag->yStart = (uint64_t)atoll(cstr(2));
+  auto num = [&](int i) -> long long {
+    uint64_t v;
+    return plain_u64(tok[i], tlen[i], v) ? (long long)v : atoll(cstr(i));
+  };
+  frag->xStart = (uint64_t)num(1);
+  frag->yStart = (uint64_t)num(2);
   frag->diag = (int64_t)frag->xStart - (int64_t)frag->yStart;
-  frag->xEnd = (uint64_t)atoll(cstr(3));
-  frag->yEnd = (uint64_t)atoll(cstr(4));
+  frag->xEnd = (uint64_t)num(3);
+  frag->yEnd = (uint64_t)num(4);
   frag->strand = tok[5][0];
-  frag->block = atoll(cstr(6));
-  frag->length = (uint64_t)atoll(cstr(7));
-  frag->score = (uint64_t)atoll(cstr(8));
-  const char *s = cstr(10);
-  char *endp = nullptr;
-  errno = 0;
-  const float sim = strtof(s, &endp);  // std::stof: invalid_argument when nothing converts, out_of_range on ERANGE
-  if (endp == s || errno == ERANGE) return false;
+  frag->block = num(6);
+  frag->length = (uint64_t)num(7);
+  frag->score = (uint64_t)num(8);
+  float sim;
+  if (!plain_float(tok[10], tlen[10], sim)) {
+    const char *s = cstr(10);
+    char *endp = nullptr;
+    errno = 0;
+    sim = strtof(s, &endp);  // std::stof: invalid_argument when nothing converts, out_of_range on ERANGE
+    if (endp == s || errno == ERANGE) return false;
+  }
   frag->ident = (uint64_t)sim;
   frag->similarity = sim;
   frag->seqX = 0;
@@ -102,26 +160,26 @@ void parse_range(const char *data, size_t begin, size_t end, bool last_range, Pa
 // The data rows of text[pos, size) parsed by nthreads threads: the text is cut at row boundaries into one range per
 // thread, every thread keeps its accepted rows in file order, and the ranges are returned in order — the same
 // records, in the same order, as the reference's row-by-row loop (FragmentsDatabase.cpp:92-100).
-std::vector<std::vector<FragFile>> parse_rows_parallel(const std::string &data, size_t pos, unsigned nthreads) {
+std::vector<std::vector<FragFile>> parse_rows_parallel(const char *data, size_t size, size_t pos, unsigned nthreads) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 64) nthreads = 64;
-  const size_t body = data.size() - pos;
-  std::vector<size_t> cut(nthreads + 1, data.size());
+  const size_t body = size - pos;
+  std::vector<size_t> cut(nthreads + 1, size);
   cut[0] = pos;
   for (unsigned t = 1; t < nthreads; ++t) {
     size_t c = pos + body / nthreads * t;
     if (c < cut[t - 1]) c = cut[t - 1];
-    while (c > 0 && c < data.size() && data[c - 1] != '\n') ++c;  // move to the start of the next row
+    while (c > 0 && c < size && data[c - 1] != '\n') ++c;  // move to the start of the next row
     cut[t] = c;
   }
   std::vector<ParsedChunk> chunks(nthreads);
-  if (!data.empty()) {  // reference: an empty stream never enters the row loop
+  if (size != 0) {  // reference: an empty stream never enters the row loop
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nthreads; ++t) {
       const bool last = t + 1 == nthreads;
       if (!last && cut[t] >= cut[t + 1]) continue;  // empty range
       chunks[t].rows.reserve((cut[t + 1] - cut[t]) / 48 + 16);  // GECKO rows are 60..90 bytes
-      pool.emplace_back(parse_range, data.data(), cut[t], cut[t + 1], last, &chunks[t]);
+      pool.emplace_back(parse_range, data, cut[t], cut[t + 1], last, &chunks[t]);
     }
     for (auto &th : pool) th.join();
   }
@@ -140,28 +198,35 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
     ~Joiner() { if (t.joinable()) t.join(); }
   } create_joiner{create_thread};
   // slurp the rest of the stream in one read; lines are split on '\n' like std::getline
-  std::string data;
+  std::unique_ptr<char[]> raw;  // (not a std::string: resize() would zero-fill ~1 GB first)
+  std::string fallback;
+  const char *data = nullptr;
+  size_t size = 0;
   {
     const std::streampos here = frags_file.tellg();
     frags_file.seekg(0, std::ios::end);
     const std::streampos fin = frags_file.tellg();
     if (here != std::streampos(-1) && fin != std::streampos(-1) && fin >= here) {
       frags_file.seekg(here);
-      data.resize((size_t)(fin - here));
-      frags_file.read(&data[0], (std::streamsize)data.size());
-      data.resize((size_t)frags_file.gcount());
+      const size_t want = (size_t)(fin - here);
+      raw.reset(new char[want + 1]);
+      frags_file.read(raw.get(), (std::streamsize)want);
+      size = (size_t)frags_file.gcount();
+      data = raw.get();
     } else {  // not seekable
       frags_file.clear();
-      data.assign((std::istreambuf_iterator<char>(frags_file)), std::istreambuf_iterator<char>());
+      fallback.assign((std::istreambuf_iterator<char>(frags_file)), std::istreambuf_iterator<char>());
+      data = fallback.data();
+      size = fallback.size();
     }
   }
   const auto t1 = clk::now();
   size_t pos = 0;
   auto next_line = [&](std::string &out) {
     const size_t s = pos;
-    while (pos < data.size() && data[pos] != '\n') ++pos;
-    out.assign(data, s, pos - s);
-    if (pos < data.size()) ++pos;
+    while (pos < size && data[pos] != '\n') ++pos;
+    out.assign(data + s, pos - s);
+    if (pos < size) ++pos;
   };
   std::string line;
   uint64_t total_frags = 0;
@@ -177,7 +242,7 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
 
   // the rows are parsed by all host cores (RK_PARSE_THREADS overrides the count)
   unsigned nthreads = std::thread::hardware_concurrency();
-  const size_t body = data.size() - pos;
+  const size_t body = size - pos;
   if (nthreads < 1 || body < (1u << 20)) nthreads = 1;
   if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
   // pinned memory for the records (full-speed H2D) is allocated beside the parse, for at most min(T, bytes / 28) records:
@@ -189,7 +254,7 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
   std::thread alloc_thread([this] { records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16); });
   Joiner alloc_joiner{alloc_thread};
-  std::vector<std::vector<FragFile>> chunks = parse_rows_parallel(data, pos, nthreads);
+  std::vector<std::vector<FragFile>> chunks = parse_rows_parallel(data, size, pos, nthreads);
   uint64_t accepted = 0;
   for (const auto &c : chunks) accepted += c.size();
   alloc_thread.join();

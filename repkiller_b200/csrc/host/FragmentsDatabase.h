@@ -12,8 +12,10 @@
 #include "structs.h"
 
 bool readFragment(FragFile *frag, const char *line, size_t len);  // reference: FragmentsDatabase.cpp:17-50
+// the strtof fast path of readFragment (digits[.digits]): true and the correctly rounded float, or false = ask strtof
+bool parse_plain_float(const char *p, size_t n, float *out);
 // data rows of text[pos, size) parsed by nthreads threads; the accepted records of consecutive ranges, in file order
-std::vector<std::vector<FragFile>> parse_rows_parallel(const std::string &text, size_t pos, unsigned nthreads);
+std::vector<std::vector<FragFile>> parse_rows_parallel(const char *text, size_t size, size_t pos, unsigned nthreads);
 
 class FragmentsDatabase {
   FragFile *records_ = nullptr;  // file order, pinned

@@ -2,6 +2,7 @@
 //   rk_hostcheck parse <in.csv> <out.bin> [threads]
 //                                             readFragment over every data row: accepted records, 109 B each (no GPU);
 //                                             with a thread count: through parse_rows_parallel, the database's parser
+//   rk_hostcheck floatcheck <n> <seed>        the float fast path of the parser against strtof on n generated tokens (no GPU)
 //   rk_hostcheck write <in.csv> <out.csv>     writer format: parses, then writes every accepted record as its own
 //                                             singleton group in file order (no GPU)
 //   rk_hostcheck steps <in.csv> <out.csv> <len_ratio> <pos_ratio>
@@ -57,7 +58,7 @@ int main(int argc, char **argv) {
         while (pos < data.size() && data[pos] != '\n') ++pos;
         if (pos < data.size()) ++pos;
       }
-      for (auto &c : parse_rows_parallel(data, pos, (unsigned)atoi(argv[4]))) recs.insert(recs.end(), c.begin(), c.end());
+      for (auto &c : parse_rows_parallel(data.data(), data.size(), pos, (unsigned)atoi(argv[4]))) recs.insert(recs.end(), c.begin(), c.end());
     } else {
       recs = parse_rows(argv[2], nullptr);
     }
@@ -66,6 +67,32 @@ int main(int argc, char **argv) {
     if (!recs.empty()) fwrite(recs.data(), sizeof(FragFile), recs.size(), f);
     fclose(f);
     return 0;
+  }
+  if (mode == "floatcheck") {
+    uint64_t rng = 88172645463325252ull ^ (uint64_t)atoll(argv[3]);
+    auto nx = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    long bad = 0, fast = 0, total = 0;
+    char t[64];
+    for (long i = 0, n = atol(argv[2]); i < n; ++i) {
+      const int kind = (int)(nx() % 4);
+      if (kind == 0) snprintf(t, sizeof t, "%.9g", (double)(float)((nx() % 1000000) / 10000.0));   // what gen.py writes
+      else if (kind == 1) snprintf(t, sizeof t, "%llu.%0*llu", (unsigned long long)(nx() % 1000), (int)(1 + nx() % 15), (unsigned long long)(nx() % 100000000));
+      else if (kind == 2) snprintf(t, sizeof t, "%.17g", (double)(nx() % (1ull << 40)) / (double)(1 + nx() % 100000));
+      else snprintf(t, sizeof t, "%llu", (unsigned long long)(nx() % (1ull << 54)));
+      if (strchr(t, 'e')) continue;
+      float f;
+      ++total;
+      if (parse_plain_float(t, strlen(t), &f)) {
+        ++fast;
+        const float w = strtof(t, nullptr);
+        if (memcmp(&f, &w, 4) != 0) {
+          if (bad < 10) printf("MISMATCH %s fast=%.9g strtof=%.9g\n", t, f, w);
+          ++bad;
+        }
+      }
+    }
+    printf("%ld tokens, %ld fast, %ld mismatches\n", total, fast, bad);
+    return bad != 0;
   }
   if (mode == "write") {
     std::string header;

@@ -38,6 +38,14 @@ def test_parallel_parser_matches_oracle_for_any_thread_count(tmp_path, fuzz_case
             assert got.tobytes() == want.tobytes(), f"fuzz seed {c['seed']}, {threads} threads"
 
 
+def test_float_fast_path_equals_strtof():
+    """readFragment parses plain `digits[.digits]` similarity tokens without strtof; the result must be strtof's
+    (correctly rounded float) on every token the fast path accepts."""
+    p = subprocess.run([HOSTCHECK, "floatcheck", "3000000", "7"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-1500:]
+    assert " 0 mismatches" in p.stdout
+
+
 def test_writer_line_format_matches_reference(tmp_path, fuzz_cases):
     """Every line the reference wrote for a singleton group (repval 0) must be reproduced byte for byte by the
     host writer from the same record (float formatting of similarity and identity, '-nan', strand bytes)."""
