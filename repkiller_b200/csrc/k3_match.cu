@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256)
     if (valid) {
       // one 32-byte gather (one sector): {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
       const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
-      const uint4 rec = src[0];
-      identity_r[i] = __uint_as_float(src[1].x);
+      const uint4 rec = ldg_gather_u4(src), rec1 = ldg_gather_u4(src + 1);
+      identity_r[i] = __uint_as_float(rec1.x);
       const u32 x = rec.x, y = rec.y, l = rec.z;
       const u32 sc = rec.w & FL_REVERSE;
       const u32 cx = x + l / 2, cy = y + l / 2;  // commonFunctions.cpp:55,59

@@ -49,6 +49,15 @@ __device__ __forceinline__ u32 lanemask_lt() {
   return m;
 }
 
+// Random gathers of one sector: ask L2 for a 64-byte fill instead of the default promotion to the whole 128-byte line
+// (ncu showed ~108 B of DRAM traffic per 32-byte gather).  Measured: k_keys 0.270 -> 0.258 ms; no gain for the 8- and
+// 16-byte gathers of K3 and K5, which keep plain loads.
+__device__ __forceinline__ uint4 ldg_gather_u4(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // streaming loads/stores: data touched once should not displace the gather targets in L1
 __device__ __forceinline__ u32 ld_stream(const u32 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(u32 *p, u32 v) { __stcs(p, v); }
