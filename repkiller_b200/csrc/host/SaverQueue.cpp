@@ -2,54 +2,55 @@
 
 #include <iostream>
 #include <stdexcept>
+#include <utility>
 
-void SaverQueue::run() {
-  for (;;) {
-    SaveRequest sr;
-    {
-      std::unique_lock<std::mutex> lck(mutex_);
-      cond_.wait(lck, [&] { return !queue_.empty() || !running_; });
-      if (queue_.empty()) return;  // stopped and drained
-      sr = queue_.front();
-      queue_.pop();
-    }
-    try {
-      save_all_frag_pairs(sr.path, seq_mngr, *sr.fgl);
-    } catch (const std::runtime_error &) {  // reference: SaverQueue.cpp:16-20
-      const std::string default_path = "represults-" + std::to_string(++count_) + ".csv";
-      std::cerr << "Couldn't access " << sr.path << ", saving into " << default_path << "\n" << std::flush;
-      save_all_frag_pairs(default_path, seq_mngr, *sr.fgl);
-    }
-    free_groups(sr.fgl);
+void SaverQueue::write_job(const Job &job) {
+  try {
+    save_all_frag_pairs(job.out_path, sequences_, *job.groups);
+  } catch (const std::runtime_error &) {  // reference: SaverQueue.cpp:16-20
+    const std::string fallback = "represults-" + std::to_string(++fallback_files_) + ".csv";
+    std::cerr << "Couldn't access " << job.out_path << ", saving into " << fallback << "\n" << std::flush;
+    save_all_frag_pairs(fallback, sequences_, *job.groups);
   }
+  free_groups(job.groups);
 }
 
-SaverQueue::~SaverQueue() {
-  if (running_) stop();
+void SaverQueue::work() {
+  std::unique_lock<std::mutex> hold(lock_);
+  for (;;) {
+    wake_.wait(hold, [this] { return !fifo_.empty() || phase_ == Phase::draining; });
+    if (fifo_.empty()) return;  // draining and nothing left
+    Job job = std::move(fifo_.front());
+    fifo_.pop_front();
+    hold.unlock();
+    write_job(job);
+    hold.lock();
+  }
 }
 
 void SaverQueue::start() {
-  std::lock_guard<std::mutex> lck(mutex_);
-  if (!running_) {
-    running_ = true;
-    thread_ptr_.reset(new std::thread(&SaverQueue::run, this));
-  }
+  std::lock_guard<std::mutex> hold(lock_);
+  if (phase_ != Phase::idle) return;
+  phase_ = Phase::accepting;
+  worker_ = std::thread(&SaverQueue::work, this);
 }
 
 void SaverQueue::stop() {
   {
-    std::lock_guard<std::mutex> lck(mutex_);
-    if (!running_) return;
-    running_ = false;
+    std::lock_guard<std::mutex> hold(lock_);
+    if (phase_ != Phase::accepting) return;
+    phase_ = Phase::draining;
   }
-  cond_.notify_all();
-  thread_ptr_->join();
+  wake_.notify_all();
+  worker_.join();
+  std::lock_guard<std::mutex> hold(lock_);
+  phase_ = Phase::idle;
 }
 
 void SaverQueue::addRequest(const std::string &path, FGList *fgl) {
   {
-    std::lock_guard<std::mutex> lck(mutex_);
-    queue_.push(SaveRequest{path, fgl});
+    std::lock_guard<std::mutex> hold(lock_);
+    fifo_.push_back(Job{path, fgl});
   }
-  cond_.notify_all();
+  wake_.notify_one();
 }

@@ -1,12 +1,14 @@
-// Host-side consumer of device results, same interface as /root/reference/src/SaverQueue.h:16-42.  The two
-// defects of the reference are not reproduced: front() on an empty queue when woken by stop()
-// (SaverQueue.cpp:7-12) and the leak of every FragsGroup (SaverQueue.cpp:21).
+// Host-side consumer of grouping results with the interface the reference's callers use
+// (/root/reference/src/SaverQueue.h:16-42: construct with the sequence manager, start(), addRequest(path, list),
+// stop()).  One worker thread drains a FIFO of jobs and writes each list with save_all_frag_pairs; an unwritable
+// path falls back to represults-<n>.csv like the reference (SaverQueue.cpp:16-20).  Two defects of the reference are
+// not reproduced: front() on an empty queue when the worker is woken by stop() (SaverQueue.cpp:7-12) and the leak of
+// every FragsGroup (SaverQueue.cpp:21).
 #pragma once
 
 #include <condition_variable>
-#include <memory>
+#include <deque>
 #include <mutex>
-#include <queue>
 #include <string>
 #include <thread>
 
@@ -14,23 +16,31 @@
 #include "structs.h"
 
 class SaverQueue {
-  struct SaveRequest {
-    std::string path;
-    FGList *fgl;
-  };
-  size_t count_ = 0;
-  bool running_ = false;
-  const sequence_manager &seq_mngr;
-  std::mutex mutex_;
-  std::condition_variable cond_;
-  std::queue<SaveRequest> queue_;
-  std::unique_ptr<std::thread> thread_ptr_;
-  void run();
-
  public:
-  explicit SaverQueue(const sequence_manager &seq_mngr) : seq_mngr(seq_mngr) {}
-  ~SaverQueue();
-  void start();
-  void stop();  // drains the queue, then joins
-  void addRequest(const std::string &path, FGList *fgl);  // takes ownership of fgl and its groups
+  explicit SaverQueue(const sequence_manager &sequences) : sequences_(sequences) {}
+  ~SaverQueue() { stop(); }
+  SaverQueue(const SaverQueue &) = delete;
+  SaverQueue &operator=(const SaverQueue &) = delete;
+
+  void start();                                           // idempotent
+  void stop();                                            // drains the FIFO, then joins; idempotent
+  void addRequest(const std::string &path, FGList *fgl);  // takes ownership of fgl and of its groups
+
+ private:
+  struct Job {
+    std::string out_path;
+    FGList *groups;
+  };
+  enum class Phase { idle, accepting, draining };
+
+  void work();
+  void write_job(const Job &job);
+
+  const sequence_manager &sequences_;
+  std::mutex lock_;
+  std::condition_variable wake_;
+  std::deque<Job> fifo_;
+  std::thread worker_;
+  Phase phase_ = Phase::idle;
+  size_t fallback_files_ = 0;
 };

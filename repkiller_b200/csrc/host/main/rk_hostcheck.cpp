@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../FragmentsDatabase.h"
+#include "../SaverQueue.h"
 #include "../commonFunctions.h"
 
 static std::vector<FragFile> parse_rows(const char *path, std::string *header) {
@@ -101,9 +102,12 @@ int main(int argc, char **argv) {
     sm.sequences.emplace_back(0, 0);
     sm.sequences.emplace_back(1, 0);
     sm.read_header(header);
-    FGList fgl;
-    for (auto &r : recs) fgl.push_back(new FragsGroup{&r});
-    save_all_frag_pairs(argv[3], sm, fgl);
+    FGList *fgl = new FGList;
+    for (auto &r : recs) fgl->push_back(new FragsGroup{&r});
+    SaverQueue sq(sm);  // the writer thread of the drop-in: start, one request, drain
+    sq.start();
+    sq.addRequest(argv[3], fgl);
+    sq.stop();
     return 0;
   }
   if (mode == "steps" && argc >= 6) {
