@@ -11,6 +11,7 @@
 //
 // usage: repkiller_ref <in.csv> <out.csv> <len_ratio> <pos_ratio>
 //   env RK_REF_NOSAVE=1  skip save_all_frag_pairs (timing runs)
+//   env RK_REF_REPEAT=K  repeat the timed calls K times on the once-loaded database (one JSON line each)
 // prints one JSON line with per-phase milliseconds on stderr.
 #include <chrono>
 #include <cstdio>
@@ -40,31 +41,42 @@ int main(int argc, char **argv) {
   in.close();
   const double load_ms = ms_since(t0);
 
-  FGList *groups = new FGList;
-  t0 = std::chrono::steady_clock::now();
-  generate_fragment_groups(db, *groups, sm, len_ratio, pos_ratio);
-  const double group_ms = ms_since(t0);
-
-  t0 = std::chrono::steady_clock::now();
-  size_t *diag_func = new size_t[db.getA()];
-  generate_diagonal_func(db, diag_func);
-  const double diag_ms = ms_since(t0);
-
-  t0 = std::chrono::steady_clock::now();
-  sort_groups(*groups, diag_func);
-  const double sort_ms = ms_since(t0);
-  delete[] diag_func;
-
-  double save_ms = 0.0;
-  if (!getenv("RK_REF_NOSAVE")) {
+  // RK_REF_REPEAT=K (bench.py --impl reference): the database is loaded once and the timed calls are repeated K
+  // times, one JSON line per repetition; RK_REF_BUDGET_S stops the loop early once that much wall time is spent.
+  const int repeat = getenv("RK_REF_REPEAT") ? atoi(getenv("RK_REF_REPEAT")) : 1;
+  const double budget_ms = getenv("RK_REF_BUDGET_S") ? 1e3 * atof(getenv("RK_REF_BUDGET_S")) : 0.0;
+  const auto t_start = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeat; ++rep) {
+    FGList *groups = new FGList;
     t0 = std::chrono::steady_clock::now();
-    save_all_frag_pairs(out_path, sm, *groups);
-    save_ms = ms_since(t0);
+    generate_fragment_groups(db, *groups, sm, len_ratio, pos_ratio);
+    const double group_ms = ms_since(t0);
+
+    t0 = std::chrono::steady_clock::now();
+    size_t *diag_func = new size_t[db.getA()];
+    generate_diagonal_func(db, diag_func);
+    const double diag_ms = ms_since(t0);
+
+    t0 = std::chrono::steady_clock::now();
+    sort_groups(*groups, diag_func);
+    const double sort_ms = ms_since(t0);
+    delete[] diag_func;
+
+    double save_ms = 0.0;
+    if (!getenv("RK_REF_NOSAVE") && rep == repeat - 1) {
+      t0 = std::chrono::steady_clock::now();
+      save_all_frag_pairs(out_path, sm, *groups);
+      save_ms = ms_since(t0);
+    }
+    fprintf(stderr,
+            "{\"n_frags\": %llu, \"n_groups\": %zu, \"load_ms\": %.3f, \"group_ms\": %.3f, "
+            "\"diag_ms\": %.3f, \"sort_ms\": %.3f, \"save_ms\": %.3f}\n",
+            (unsigned long long)db.getTotalFrags(), groups->size(), load_ms, group_ms, diag_ms,
+            sort_ms, save_ms);
+    fflush(stderr);
+    for (FragsGroup *g : *groups) delete g;  // (the reference's saver leaks them; a repeat loop cannot)
+    delete groups;
+    if (budget_ms > 0 && ms_since(t_start) > budget_ms) break;
   }
-  fprintf(stderr,
-          "{\"n_frags\": %llu, \"n_groups\": %zu, \"load_ms\": %.3f, \"group_ms\": %.3f, "
-          "\"diag_ms\": %.3f, \"sort_ms\": %.3f, \"save_ms\": %.3f}\n",
-          (unsigned long long)db.getTotalFrags(), groups->size(), load_ms, group_ms, diag_ms,
-          sort_ms, save_ms);
   return 0;
 }

@@ -6,7 +6,7 @@
  *
  * Pinning: the reference ships no golden vectors.  This restatement is pinned against the
  * reference itself: oracle/_ref/repkiller_ref (the unmodified reference sources + oracle/ref_driver.cpp)
- * on the fuzz classes and workloads of tests/golden/make_golden.py; see tests/test_oracle_vs_ref.py.
+ * on the fuzz classes and workloads of tests/golden/make_golden.py; see tests/test_oracle_golden.py.
  */
 #ifndef RK_ORACLE_H
 #define RK_ORACLE_H

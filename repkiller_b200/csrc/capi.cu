@@ -1,157 +1,35 @@
 // C ABI of librk_b200.so (include/rk_b200.h): context, device workspace, and the launch sequences that stand
 // in for FragmentsDatabase's constructor (rk_load_aos) and for generate_fragment_groups +
 // generate_diagonal_func + sort_groups (rk_group).  Reference call sites: /root/reference/src/repkiller.cpp:52,84-91.
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
-#include "../../include/rk_b200.h"
-#include "rk_common.cuh"
+#include "rk_ctx.cuh"
 
 using namespace rk;
 
 namespace {
 
-std::string g_create_error;
-
-inline u64 align_up(u64 x, u64 a) { return (x + a - 1) / a * a; }
-inline int ceil_log2(u64 x) {  // bits needed to represent values 0 .. x-1
-  int b = 0;
-  while (b < 63 && (1ull << b) < x) ++b;
-  return b;
+std::mutex g_create_mu;        // rk_create may run on several threads (one context per GPU)
+std::string g_create_error;   // guarded by g_create_mu; rk_create_error() returns a per-thread copy
+thread_local std::string tl_create_error;
+void set_create_error(const std::string &s) {
+  std::lock_guard<std::mutex> lk(g_create_mu);
+  g_create_error = s;
 }
 
 const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan", "k_radix_scatter", "k_keys", "k_match_small",
                                              "k_match_long", "k_chase", "k_hkey", "k_pack", "k_order_tile",
                                              "k_groupsort_large", "k_finalize", "k_diag_table", "k_groupsort_warp", "k_format"};
 
-// CUDA-event pair around every launch group; folded into per-kernel totals after each synchronisation
-struct Profiler {
-  bool on = false;
-  struct Rec { int kid; cudaEvent_t a, b; u64 units; };
-  std::vector<Rec> open_recs;
-  std::vector<cudaEvent_t> pool;
-  double ms[KID_COUNT] = {0};
-  u64 launches[KID_COUNT] = {0};
-  u64 units[KID_COUNT] = {0};
-  cudaEvent_t get() {
-    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    return e;
-  }
-  void fold() {  // call after the stream was synchronised
-    for (auto &r : open_recs) {
-      float t = 0.f;
-      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; launches[r.kid] += 1; units[r.kid] += r.units; }
-      else cudaGetLastError();
-      pool.push_back(r.a);
-      pool.push_back(r.b);
-    }
-    open_recs.clear();
-  }
-};
 thread_local Profiler *tl_prof = nullptr;
-
-struct Counters {  // small device block, mirrored in pinned host memory
-  u32 n_dropped;
-  u32 err;
-  u32 n_groups;
-  u32 pad;
-  u32 work_x[2];
-  u32 work_y[2];
-  u32 work_g[8];
-};
 
 }  // namespace
 
-struct rk_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  std::string err;
-
-  // device workspace (one allocation, carved by carve())
-  void *arena = nullptr;
-  u64 arena_bytes = 0;
-  u64 cap_n = 0;  // records the workspace was carved for
-
-  // pinned host result buffers
-  void *h_res = nullptr;
-  u64 h_res_cap = 0;
-  Counters *h_cnt = nullptr;
-
-  cudaEvent_t ev[RK_NSTAGES + 2];
-  Profiler prof;
-
-  // multi-GPU stage calls (rk_st_*): own counters and a grow-only scratch area
-  Counters *st_cnt = nullptr;
-  void *st_scratch = nullptr;
-  u64 st_scratch_bytes = 0;
-
-  // K6 text output: device text + work area (grow-only), pinned host mirror
-  const u8 *aos_dev = nullptr;  // the loaded records on the device (own copy, or the caller's device pointer)
-  void *d_text = nullptr;
-  u64 d_text_bytes = 0;
-  char *h_text[2] = {nullptr, nullptr};  // alternating: a chunk stays valid while the next one is produced
-  u64 h_text_bytes[2] = {0, 0};
-  int h_text_next = 0;
-
-  bool loaded = false;
-  u64 n = 0;
-  u32 m = 0;
-  Geometry g{};
-  int bits_rank = 1, bits_x = 1, bits_y = 1;
-  bool have_group = false;
-
-  // carved pointers
-  u8 *d_aos = nullptr;
-  uint4 *rec4 = nullptr;  // file order, two words per record: {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
-  float *identity_r = nullptr;  // rank order
-  uint4 *hfi_r = nullptr;       // rank order {h, file index, identity bits, 0}
-  u32 *key0 = nullptr;
-  u32 *link_x = nullptr, *link_y = nullptr;
-  u64 link_x_words = 0, link_y_words = 0;
-  Counters *d_cnt = nullptr;
-  u32 *k0_r = nullptr, *fidx_r = nullptr;
-  u32 *tmp_k = nullptr, *tmp_v = nullptr;
-  uint2 *xl_r = nullptr, *yl_r = nullptr;  // rank order {center, length} per axis
-  u32 *ys_r = nullptr, *kx = nullptr, *ky = nullptr;
-  u32 *skx = nullptr, *rx = nullptr, *sky = nullptr, *ry = nullptr;
-  void *sort_work = nullptr;
-  u32 *prehist = nullptr;  // 4 x [4][256]: digit counts of key0, kx, ky, gid gathered by the kernels that produce them
-  u32 *xm_bits = nullptr;
-  u32 *parent = nullptr, *gid_rank = nullptr, *h = nullptr, *sgid = nullptr, *srank = nullptr;
-  void *forest_work = nullptr;
-  void *order_scratch = nullptr;
-  u32 *worklist = nullptr;
-  u32 work_cap = 0;
-  u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr;
-  u32 *out_order = nullptr, *out_gid = nullptr;
-  u8 *out_repval = nullptr;
-  float *out_identity = nullptr;
-};
-
 namespace {
-
-int fail(rk_ctx *c, int code, const char *fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  c->err = buf;
-  return code;
-}
-
-#define CK(call)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e_ = (call);                                                                          \
-    if (e_ != cudaSuccess) return fail(ctx, RK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));    \
-  } while (0)
 
 // carve the workspace for n records; returns bytes needed.  With base == nullptr only sizes are computed.
 u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
@@ -205,6 +83,9 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   return off;
 }
 
+}  // namespace
+
+namespace rk {
 Geometry make_geometry(u64 seqx_len, u64 seqy_len) {
   Geometry g{};
   g.lx = seqx_len;
@@ -235,9 +116,7 @@ const char *err_bits_text(u32 e) {
   return "unknown device error";
 }
 
-}  // namespace
-
-namespace rk {
+void prof_route(Profiler *p) { tl_prof = p; }
 void prof_begin(int kid, cudaStream_t st, unsigned long long units) {
   if (!tl_prof) return;
   Profiler::Rec r{kid, tl_prof->get(), tl_prof->get(), (u64)units};
@@ -250,19 +129,6 @@ void prof_end(cudaStream_t st) {
 }
 }  // namespace rk
 
-namespace {
-struct ProfGuard {  // routes the launchers' KScope events to this context for the duration of one API call
-  rk_ctx *c;
-  explicit ProfGuard(rk_ctx *ctx) : c(ctx) { tl_prof = ctx->prof.on ? &ctx->prof : nullptr; }
-  ~ProfGuard() {
-    if (tl_prof) {
-      cudaStreamSynchronize(c->stream);
-      tl_prof->fold();
-    }
-    tl_prof = nullptr;
-  }
-};
-}  // namespace
 
 namespace {
 // K5b tail + K5c on the state the last rk_group left on the device
@@ -342,25 +208,29 @@ int finish_group(rk_ctx *ctx, unsigned flags, rk_result *out, u64 launches) {
 extern "C" {
 
 const char *rk_version(void) { return "repkiller-b200 0.1 (sm_100a)"; }
-const char *rk_create_error(void) { return g_create_error.c_str(); }
+const char *rk_create_error(void) {
+  std::lock_guard<std::mutex> lk(g_create_mu);
+  tl_create_error = g_create_error;
+  return tl_create_error.c_str();
+}
 
 rk_ctx *rk_create(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
-    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+    set_create_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
     cudaGetLastError();
     return nullptr;
   }
   if (device < 0 || device >= count) {
-    g_create_error = "device index out of range";
+    set_create_error("device index out of range");
     return nullptr;
   }
   rk_ctx *c = new rk_ctx;
   c->device = device;
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaHostAlloc((void **)&c->h_cnt, sizeof(Counters), cudaHostAllocDefault)) != cudaSuccess) {
-    g_create_error = cudaGetErrorString(e);
+    set_create_error(cudaGetErrorString(e));
     delete c;
     return nullptr;
   }
@@ -368,6 +238,13 @@ rk_ctx *rk_create(int device) {
   if (const char *gr = getenv("RK_L2_GRAN")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));  // tuning switch
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   if (cudaMalloc((void **)&c->st_cnt, sizeof(Counters)) != cudaSuccess) c->st_cnt = nullptr;
+  // function attributes are per device: every context sets them for its own device (a process-wide flag would leave
+  // the second device of a process without the shared-memory opt-in)
+  if ((e = decode_init_device()) != cudaSuccess || (e = sort_init_device()) != cudaSuccess || (e = order_init_device()) != cudaSuccess) {
+    set_create_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    rk_destroy(c);
+    return nullptr;
+  }
   return c;
 }
 
@@ -387,7 +264,7 @@ void rk_destroy(rk_ctx *c) {
   delete c;
 }
 
-const char *rk_last_error(const rk_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+const char *rk_last_error(const rk_ctx *c) { return c ? c->err.c_str() : rk_create_error(); }
 
 int rk_set_stream(rk_ctx *ctx, void *cuda_stream) {
   if (!ctx) return RK_ERR_ARG;

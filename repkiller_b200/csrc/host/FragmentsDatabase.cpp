@@ -245,9 +245,10 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   const size_t body = size - pos;
   if (nthreads < 1 || body < (1u << 20)) nthreads = 1;
   if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
-  // pinned memory for the records (full-speed H2D) is allocated beside the parse, for at most min(T, bytes / 28) records:
-  // a file with more accepted rows than its header announces is an error anyway, and a row that readFragment accepts
-  // has 14 non-empty fields ("Frag" first) and 13 commas, i.e. at least 30 bytes with its line end
+  // pinned memory for the records (full-speed H2D) is allocated beside the parse, for min(T, bytes / 28) records: a
+  // full GECKO row has 14 non-empty fields and 13 commas, i.e. at least 30 bytes with its line end.  This is only a
+  // guess: readFragment's short-row padding also accepts rows like "Frag,5" (7 bytes), so the count is checked after
+  // the parse and the buffer is re-allocated for exactly `accepted` records when the guess was too small.
   const uint64_t rows_upper = body / 28 + 1;
   cap_ = (rows_upper < total_frags ? rows_upper : total_frags) + 2;
   create_thread.join();
@@ -259,6 +260,14 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   for (const auto &c : chunks) accepted += c.size();
   alloc_thread.join();
   if (accepted > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
+  if (records_ && accepted > cap_) {  // short rows: more records than bytes / 28
+    rk_host_free(records_);
+    records_ = nullptr;
+  }
+  if (!records_ && accepted > cap_) {
+    cap_ = accepted;
+    records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16);
+  }
   if (!records_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
   {
     std::vector<std::thread> pool;

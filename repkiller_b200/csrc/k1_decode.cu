@@ -219,15 +219,15 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
   }
 }
 
+// per-device opt-in to the 84 KB of dynamic shared memory (called by rk_create for the context's device)
+cudaError_t decode_init_device() {
+  return cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES);
+}
+
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity, u32 *key0,
                   u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4, HistOut hist) {
   if (n == 0) return 0;
-  static bool attr_set = false;
   const int smem = DEC_STAGES * DEC_TILE_BYTES;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -404,15 +404,14 @@ u64 sort_work_bytes(u64 n) {
   return three_kernel > onesweep ? three_kernel : onesweep;
 }
 
+cudaError_t sort_init_device() {
+  return cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM_BYTES);
+}
+
 static int launch_onesweep(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out, u32 *keys_tmp, u32 *vals_tmp,
                            u64 n, int key_bits, void *work, cudaStream_t st, u32 *err_word, u32 *prehist) {
   const int passes = (key_bits + 7) / 8;
   const u32 tiles = (u32)((n + OS_TILE - 1) / OS_TILE);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM_BYTES);
-    attr_set = true;
-  }
   u32 *ghist = reinterpret_cast<u32 *>(work);          // [4][256] (or the producer's counters)
   u32 *counters = ghist + OS_MAX_PASSES * RADIX;          // [4] tile counters, [4] = error word when none was set
   u32 *state = counters + 64;                            // [passes][tiles][256]

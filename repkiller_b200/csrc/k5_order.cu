@@ -598,6 +598,13 @@ void order_carve(OrderArgs &a, void *scratch, u64 m) {
   a.worklist[2] = (u32 *)p;
 }
 
+cudaError_t order_init_device() {
+  const int smem1 = GW1_WARPS * (int)sizeof(WarpSortMem<GS_WARP_CAP>);
+  cudaError_t e = cudaFuncSetAttribute(k_groupsort_warp<GS_WARP_CAP, GW1_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_rangesort_warp<GS_WARP_CAP, GW1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+}
+
 int launch_order(const OrderArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
   const u32 m = a.m;
@@ -610,12 +617,6 @@ int launch_order(const OrderArgs &a, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int smem0 = GW0_WARPS * (int)sizeof(WarpSortMem<GS_WARP_CAP0>), smem1 = GW1_WARPS * (int)sizeof(WarpSortMem<GS_WARP_CAP>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_groupsort_warp<GS_WARP_CAP, GW1_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    cudaFuncSetAttribute(k_rangesort_warp<GS_WARP_CAP, GW1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    attr_set = true;
-  }
   {
     KScope ks(KID_GSORT_WARP, st, 0);
     k_groupsort_warp<GS_WARP_CAP0, GW0_WARPS, 0><<<sms * 6, GW0_WARPS * 32, smem0, st>>>(a);

@@ -127,6 +127,11 @@ struct KScope {
   ~KScope() { prof_end(st); }
 };
 
+// per-device kernel attributes (dynamic shared memory opt-ins); rk_create calls these for the context's device
+cudaError_t decode_init_device();
+cudaError_t sort_init_device();
+cudaError_t order_init_device();
+
 // ---- launchers (each returns the number of kernels it launched) -------------------------------------
 
 // tooling: synthetic workload on the device, identical to repkiller_b200/gen.py
