@@ -197,6 +197,62 @@ int rk_st_hkey(rk_ctx *ctx, const uint32_t *k0_r, const uint32_t *ys_r, uint64_t
 int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *sh, const uint32_t *sfidx, const float *sident,
                 int do_sort, uint32_t *out_order, uint32_t *out_gid, uint8_t *out_repval, float *out_identity);
 
+/* ---- one comparison partitioned over several GPUs ---------------------------------------------
+ * The reference is one process on one host (src/repkiller.cpp); these entry points run the same
+ * FragmentsDatabase -> generate_fragment_groups -> generate_diagonal_func -> sort_groups sequence on ONE fragment file
+ * whose records are spread over the GPUs of a box, with output bit-identical to rk_load_aos + rk_group on one GPU.
+ * Fragments are range-partitioned by xStart/10 (processing order), the X pass runs at home with a halo of the fragments
+ * whose center crosses a cut, the Y pass on the owners of the Y ranges, group ids come from per-GPU root counts plus parent
+ * chains followed through peer memory (NVLink), and rank r ends up with the r-th range of output lines.
+ *
+ * (a) one process per GPU (torchrun, MPI): rank 0 calls rk_dist_unique_id and broadcasts the RK_DIST_ID_BYTES bytes; every rank
+ *     calls rk_dist_init, rk_dist_export, all-gathers the RK_DIST_BLOB_BYTES blobs (any transport the application has),
+ *     rk_dist_import, then rk_dist_load_aos / rk_dist_group.  These calls are collective: every rank must make them.
+ * (b) one process, several GPUs: rk_create_multi and rk_multi_*; the library runs one host thread per GPU. */
+#define RK_DIST_ID_BYTES 128u
+#define RK_DIST_BLOB_BYTES 128u
+typedef struct {
+  int rank, world;
+  uint64_t total_loaded;  /* records of the whole file */
+  uint64_t total_kept;    /* fragments the reference iterates, all ranks */
+  uint64_t total_groups;
+  uint64_t line_offset;   /* index of this rank's first output line in the whole output */
+  uint64_t n_lines;       /* output lines this rank holds (== rk_result.n_kept of rk_dist_group) */
+  uint64_t rank_offset;   /* first processing rank this GPU owns */
+  uint64_t n_ranked;      /* fragments this GPU owns in processing order */
+  uint64_t n_halo_in, n_halo_out; /* X-pass halo fragments received from lower / sent to higher GPUs */
+  uint64_t n_y;           /* fragments this GPU owns in the Y pass */
+  uint64_t bytes_sent;    /* payload this rank sent to other ranks during the call */
+} rk_dist_info;
+int rk_dist_unique_id(void *id128);
+/* cap_per_rank: rows of workspace per GPU (the same on every rank; about 1.3 x the fragments per GPU) */
+int rk_dist_init(rk_ctx *ctx, int rank, int nranks, const void *id128, uint64_t cap_per_rank);
+int rk_dist_export(rk_ctx *ctx, void *blob);
+int rk_dist_import(rk_ctx *ctx, const void *blobs /* nranks x RK_DIST_BLOB_BYTES, in rank order */);
+/* frags: this rank's contiguous slice of the file (host or 16-byte aligned device memory), file_offset = index of its first
+ * record; slices in rank order make up the file.  Replaces FragmentsDatabase::FragmentsDatabase like rk_load_aos. */
+int rk_dist_load_aos(rk_ctx *ctx, const void *frags, uint64_t n_local, uint64_t file_offset, uint64_t seqx_len, uint64_t seqy_len,
+                     unsigned flags, rk_load_stats *stats);
+/* out: THIS RANK's range of output lines (order = file indices of the whole file, gid = global group ids); n_groups is
+ * the global count.  info may be NULL. */
+int rk_dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk_result *out, rk_dist_info *info);
+
+typedef struct rk_multi rk_multi;
+/* One context per listed device.  Distinct devices talk over NCCL; a device listed twice (tests on a one-GPU box) makes
+ * the ranks exchange through device copies.  NULL on failure (rk_create_error). */
+rk_multi *rk_create_multi(const int *devices, int ndev);
+void rk_destroy_multi(rk_multi *m);
+const char *rk_multi_last_error(const rk_multi *m);
+int rk_multi_ranks(const rk_multi *m);
+rk_ctx *rk_multi_ctx(rk_multi *m, int rank);
+const char *rk_multi_transport(const rk_multi *m); /* "nccl" or "local" */
+/* frags: the whole file in HOST memory; the ranks take consecutive slices. */
+int rk_multi_load_aos(rk_multi *m, const void *frags, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags,
+                      rk_load_stats *stats);
+/* out: the whole result in pinned host memory owned by m (device pointers are NULL), valid until the next call. */
+int rk_multi_group(rk_multi *m, double len_ratio, double pos_ratio, unsigned flags, rk_result *out);
+int rk_multi_info(const rk_multi *m, int rank, rk_dist_info *info);
+
 /* Tooling: records start .. start+count of the synthetic workload of repkiller_b200/gen.py, generated on the device
  * (lx, ly are the header values, i.e. loaded length - 1). */
 int rk_gen_workload(rk_ctx *ctx, uint64_t seed, uint64_t lx, uint64_t ly, double p_rep, uint64_t families, uint64_t ax, uint64_t ay,

@@ -25,7 +25,12 @@ SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_se
            "rk_diagonal_func", "rk_format_lines", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
            # multi-GPU stage entry points (bound in repkiller_b200/dist.py)
            "rk_st_link_words", "rk_st_decode", "rk_st_or_words", "rk_st_keys", "rk_st_match", "rk_st_forest", "rk_st_hkey",
-           "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter", "rk_gen_workload"]
+           "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter", "rk_gen_workload",
+           # one comparison over several GPUs
+           "rk_dist_unique_id", "rk_dist_init", "rk_dist_export", "rk_dist_import", "rk_dist_load_aos", "rk_dist_group",
+           "rk_create_multi", "rk_destroy_multi", "rk_multi_last_error", "rk_multi_ranks", "rk_multi_ctx", "rk_multi_transport",
+           "rk_multi_load_aos", "rk_multi_group", "rk_multi_info"]
+DIST_ID_BYTES, DIST_BLOB_BYTES = 128, 128
 
 
 class RkError(RuntimeError):
@@ -49,6 +54,16 @@ class _Result(C.Structure):
                 ("identity", C.POINTER(C.c_float)),
                 ("d_order", C.c_void_p), ("d_gid", C.c_void_p), ("d_repval", C.c_void_p), ("d_identity", C.c_void_p),
                 ("ms_stage", C.c_float * NSTAGES), ("ms_device", C.c_float), ("n_launches", C.c_uint64)]
+
+
+class _DistInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int)] + [(k, C.c_uint64) for k in (
+        "total_loaded", "total_kept", "total_groups", "line_offset", "n_lines", "rank_offset", "n_ranked", "n_halo_in",
+        "n_halo_out", "n_y", "bytes_sent")]
+
+
+def _info_dict(i: "_DistInfo") -> dict:
+    return {k: int(getattr(i, k)) for k, _ in _DistInfo._fields_}
 
 
 _lib = None
@@ -81,6 +96,25 @@ def load_library():
     L.rk_format_lines.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(_Text)]
     L.rk_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.rk_profile_read.argtypes = [C.c_void_p, C.POINTER(_KernelTime), C.c_int, C.c_int]
+    L.rk_dist_unique_id.argtypes = [C.c_void_p]
+    L.rk_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    L.rk_dist_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.rk_dist_import.argtypes = [C.c_void_p, C.c_void_p]
+    L.rk_dist_load_aos.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(_LoadStats)]
+    L.rk_dist_group.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint, C.POINTER(_Result), C.POINTER(_DistInfo)]
+    L.rk_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int]
+    L.rk_create_multi.restype = C.c_void_p
+    L.rk_destroy_multi.argtypes = [C.c_void_p]
+    L.rk_multi_last_error.argtypes = [C.c_void_p]
+    L.rk_multi_last_error.restype = C.c_char_p
+    L.rk_multi_ranks.argtypes = [C.c_void_p]
+    L.rk_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.rk_multi_ctx.restype = C.c_void_p
+    L.rk_multi_transport.argtypes = [C.c_void_p]
+    L.rk_multi_transport.restype = C.c_char_p
+    L.rk_multi_load_aos.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(_LoadStats)]
+    L.rk_multi_group.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint, C.POINTER(_Result)]
+    L.rk_multi_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(_DistInfo)]
     _lib = L
     return L
 
@@ -250,3 +284,111 @@ class Context:
 
     def sort_pairs_work_bytes(self, n: int) -> int:
         return int(self._L.rk_sort_pairs_work_bytes(n))
+
+    # ---- one comparison over several GPUs, one process per GPU (rk_dist_*; collective calls) ----
+    def dist_init(self, rank: int, world: int, unique_id: bytes, cap_per_rank: int):
+        assert len(unique_id) == DIST_ID_BYTES
+        self._check(self._L.rk_dist_init(self._h, rank, world, C.c_char_p(unique_id), cap_per_rank))
+
+    def dist_export(self) -> bytes:
+        buf = C.create_string_buffer(DIST_BLOB_BYTES)
+        self._check(self._L.rk_dist_export(self._h, buf))
+        return buf.raw
+
+    def dist_import(self, blobs: bytes):
+        self._check(self._L.rk_dist_import(self._h, C.c_char_p(blobs)))
+
+    def dist_load(self, ptr: int, n_local: int, file_offset: int, seqx_len: int, seqy_len: int, timing: bool = False) -> LoadStats:
+        st = _LoadStats()
+        self._check(self._L.rk_dist_load_aos(self._h, C.c_void_p(ptr), n_local, file_offset, seqx_len, seqy_len,
+                                             F_TIMING if timing else 0, C.byref(st)))
+        return LoadStats(st.n_loaded, st.n_kept, st.vsize, {STAGES[i]: st.ms_stage[i] for i in range(NSTAGES)}, st.ms_device,
+                         st.n_launches)
+
+    def dist_group(self, len_ratio: float, pos_ratio: float, host_result: bool = True, sort: bool = True, timing: bool = False,
+                   copy: bool = True):
+        """(Groups of THIS rank's range of output lines, info dict)"""
+        flags = (F_HOST_RESULT if host_result else 0) | (0 if sort else F_NO_SORT) | (F_TIMING if timing else 0)
+        r, info = _Result(), _DistInfo()
+        self._check(self._L.rk_dist_group(self._h, len_ratio, pos_ratio, flags, C.byref(r), C.byref(info)))
+        return _groups_of(r, host_result, copy), _info_dict(info)
+
+
+def _groups_of(r: "_Result", host_result: bool, copy: bool) -> Groups:
+    m = r.n_kept
+
+    def arr(p, dt):
+        if not host_result:
+            return None
+        if m == 0:
+            return np.zeros(0, dt)
+        v = np.ctypeslib.as_array(p, shape=(m,))
+        return v.copy() if copy else v
+
+    return Groups(m, r.n_groups, arr(r.order, np.uint32), arr(r.gid, np.uint32), arr(r.repval, np.uint8), arr(r.identity, np.float32),
+                  {"order": r.d_order, "gid": r.d_gid, "repval": r.d_repval, "identity": r.d_identity},
+                  {STAGES[i]: r.ms_stage[i] for i in range(NSTAGES)}, r.ms_device, r.n_launches)
+
+
+def dist_unique_id() -> bytes:
+    """rank 0: the NCCL unique id every rank hands to Context.dist_init (broadcast it with whatever the application has)"""
+    L = load_library()
+    buf = C.create_string_buffer(DIST_ID_BYTES)
+    rc = L.rk_dist_unique_id(buf)
+    if rc:
+        raise RkError(rc, "NCCL is not available")
+    return buf.raw
+
+
+class Multi:
+    """One comparison over several GPUs of one process (rk_create_multi): the library runs one host thread per GPU."""
+
+    def __init__(self, devices):
+        self._L = load_library()
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = self._L.rk_create_multi(arr, len(devices))
+        if not self._h:
+            raise RkError(-1, self._L.rk_create_error().decode())
+        self.n = len(devices)
+
+    @property
+    def transport(self) -> str:
+        return self._L.rk_multi_transport(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rk_destroy_multi(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RkError(rc, self._L.rk_multi_last_error(self._h).decode())
+
+    def load(self, records: np.ndarray, seqx_len: int, seqy_len: int) -> LoadStats:
+        rec = np.ascontiguousarray(records)
+        self._keep = rec
+        st = _LoadStats()
+        self._check(self._L.rk_multi_load_aos(self._h, C.c_void_p(rec.ctypes.data), rec.nbytes // 109, seqx_len, seqy_len, 0, C.byref(st)))
+        return LoadStats(st.n_loaded, st.n_kept, st.vsize, {}, st.ms_device, st.n_launches)
+
+    def group(self, len_ratio: float, pos_ratio: float, sort: bool = True) -> Groups:
+        r = _Result()
+        self._check(self._L.rk_multi_group(self._h, len_ratio, pos_ratio, 0 if sort else F_NO_SORT, C.byref(r)))
+        return _groups_of(r, True, True)
+
+    def info(self, rank: int) -> dict:
+        i = _DistInfo()
+        self._check(self._L.rk_multi_info(self._h, rank, C.byref(i)))
+        return _info_dict(i)

@@ -23,7 +23,8 @@ void set_create_error(const std::string &s) {
 
 const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan", "k_radix_scatter", "k_keys", "k_match_small",
                                              "k_match_long", "k_chase", "k_hkey", "k_pack", "k_order_tile",
-                                             "k_groupsort_large", "k_finalize", "k_diag_table", "k_groupsort_warp", "k_format"};
+                                             "k_groupsort_large", "k_finalize", "k_diag_table", "k_groupsort_warp", "k_format", "k_dist_rows",
+                                             "k_group_stats"};
 
 thread_local Profiler *tl_prof = nullptr;
 
@@ -252,6 +253,7 @@ void rk_destroy(rk_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  dist_destroy(c);
   if (c->arena) cudaFree(c->arena);
   if (c->st_cnt) cudaFree(c->st_cnt);
   if (c->st_scratch) cudaFree(c->st_scratch);

@@ -65,7 +65,7 @@ __device__ __forceinline__ u64 ldg_u64_bytes(const u8 *p) {
 
 struct DecodeOut {
   u32 *xs, *ys, *len;
-  uint4 *rec4;  // when set: two 16-byte words per record {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
+  uint4 *rec4;  // when set: two 16-byte words per record {xStart, yStart, length, flags} {identity bits, file index, 0, 0}
                 // instead of the five arrays (one 32-byte sector per gather in k_keys)
   u8 *flags;
   float *identity;
@@ -74,6 +74,7 @@ struct DecodeOut {
   u32 *n_dropped;
   u32 *err;
   HistOut hist;  // digit counts of key0 for the rank sort (ghist == nullptr: off)
+  u32 fidx_base; // file index of record 0 of this slice (multi-GPU: a rank decodes a slice of the file)
 };
 
 __device__ __forceinline__ u32 emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, u64 ident, u8 strand, const Geometry &g,
@@ -119,7 +120,7 @@ __device__ __forceinline__ u32 emit_fragment(u64 idx, u64 xs, u64 ys, u64 len, u
   o.key0[idx] = key0;
   if (o.rec4) {
     o.rec4[2 * idx] = make_uint4((u32)xs, (u32)ys, (u32)len, fl);
-    o.rec4[2 * idx + 1] = make_uint4(__float_as_uint(idv), 0u, 0u, 0u);
+    o.rec4[2 * idx + 1] = make_uint4(__float_as_uint(idv), o.fidx_base + (u32)idx, 0u, 0u);
   } else {
     o.xs[idx] = (u32)xs;
     o.ys[idx] = (u32)ys;
@@ -225,7 +226,7 @@ cudaError_t decode_init_device() {
 }
 
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity, u32 *key0,
-                  u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4, HistOut hist) {
+                  u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4, HistOut hist, u32 fidx_base) {
   if (n == 0) return 0;
   const int smem = DEC_STAGES * DEC_TILE_BYTES;
   int dev = 0, sms = 148;
@@ -234,7 +235,7 @@ int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, 
   const u64 full_tiles = n / DEC_TILE;
   u64 grid = (u64)sms * 2;  // two CTAs (2 x 84 KB of staging) per SM, persistent over the tiles
   if (grid > full_tiles) grid = full_tiles ? full_tiles : 1;
-  DecodeOut o{xs, ys, len, rec4, flags, identity, key0, link_x, link_y, n_dropped, err, hist};
+  DecodeOut o{xs, ys, len, rec4, flags, identity, key0, link_x, link_y, n_dropped, err, hist, fidx_base};
   KScope ks(KID_DECODE, st, n);
   k_decode<<<(unsigned)grid, DEC_THREADS, smem, st>>>(aos, n, g, o);
   return 1;

@@ -28,23 +28,11 @@ namespace rk {
 constexpr int T1_MAX = 32;
 constexpr u32 NO_BUCKET = 0xFFFFFFFFu;
 
-__device__ __forceinline__ u32 run_start(const u32 *__restrict__ bm, u32 k) {
-  // largest k' <= k whose link bit is clear (bit 0 of every strand class is never set)
-  u32 w = k >> 5;
-  u32 m = 0xFFFFFFFFu >> (31 - (k & 31));
-  for (;;) {
-    const u32 z = ~bm[w] & m;
-    if (z) return (w << 5) + (31 - __clz(z));
-    if (w == 0) return 0;
-    --w;
-    m = 0xFFFFFFFFu;
-  }
-}
-
 __global__ void __launch_bounds__(256)
     k_keys(const u32 *__restrict__ fidx_r, u32 m, Geometry g, const uint4 *__restrict__ rec4, const u32 *__restrict__ link_x,
            const u32 *__restrict__ link_y, uint2 *__restrict__ xl_r, uint2 *__restrict__ yl_r, u32 *__restrict__ ys_r,
-           u32 *__restrict__ kx, u32 *__restrict__ ky, float *__restrict__ identity_r, HistOut hx, HistOut hy) {
+           u32 *__restrict__ kx, u32 *__restrict__ ky, float *__restrict__ identity_r, HistOut hx, HistOut hy,
+           u32 *__restrict__ gfidx_r, u32 own_bit) {
   // the digit counts of the two sort keys are gathered here (the keys would otherwise be read again by each sort)
   __shared__ u32 s_hx[HIST_PASSES][HIST_RADIX], s_hy[HIST_PASSES][HIST_RADIX];
   const bool do_hist = hx.ghist != nullptr;
@@ -63,6 +51,7 @@ __global__ void __launch_bounds__(256)
       const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
       const uint4 rec = ldg_gather_u4(src), rec1 = ldg_gather_u4(src + 1);
       identity_r[i] = __uint_as_float(rec1.x);
+      if (gfidx_r) gfidx_r[i] = rec1.y;
       const u32 x = rec.x, y = rec.y, l = rec.z;
       const u32 sc = rec.w & FL_REVERSE;
       const u32 cx = x + l / 2, cy = y + l / 2;  // commonFunctions.cpp:55,59
@@ -71,7 +60,7 @@ __global__ void __launch_bounds__(256)
       ys_r[i] = y;
       kxv = run_start(link_x, sc * g.nbx + cx / DIVISOR);
       kyv = run_start(link_y, sc * g.nby + cy / DIVISOR);
-      kx[i] = kxv;
+      kx[i] = own_bit ? 2 * kxv + 1 : kxv;
       ky[i] = kyv;
     }
     if (do_hist) {
@@ -87,7 +76,8 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
-                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x, HistOut hist_y) {
+                uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x, HistOut hist_y,
+                u32 *gfidx_r, u32 own_bit) {
   if (m == 0) return 0;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -95,7 +85,7 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u
   u32 blocks = (m + 255) / 256;
   if (hist_x.ghist && blocks > (u32)sms * 8) blocks = (u32)sms * 8;  // few CTAs: few histogram flushes
   KScope ks(KID_KEYS, st, m);
-  k_keys<<<blocks, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r, hist_x, hist_y);
+  k_keys<<<blocks, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r, hist_x, hist_y, gfidx_r, own_bit);
   return 1;
 }
 
@@ -285,7 +275,7 @@ __device__ __forceinline__ void load_elem(const MatchArgs &a, u32 pos, u32 &r, u
     len = cl.y;
     // X-matched: Y-insert without a query (commonFunctions.cpp:59); one bit per rank, set by the X pass (the 1.25 MB
     // map of 10M fragments stays in L2, a gather of parent[r] would cost a DRAM sector)
-    xm = a.is_y && ((a.xm_bits[r >> 5] >> (r & 31)) & 1u);
+    xm = a.is_y && (a.xm_bytes ? a.xm_bytes[r] != 0 : (((a.xm_bits[r >> 5] >> (r & 31)) & 1u) != 0));
   }
 }
 __device__ __forceinline__ void store_owner(const MatchArgs &a, u32 pos, u32 r, u32 v) {
@@ -385,7 +375,7 @@ __global__ void __launch_bounds__(MT_HEADS, RK_MT_MINB) k_match_small(MatchArgs 
     if (e < count) {
       u32 r, c, len;
       bool xm;
-      key = a.skey[bs + e];
+      key = a.skey[bs + e] >> a.key_shift;
       load_elem(a, bs + e, r, c, len, xm);
       s_rank[e] = r;
       s_cl[e] = make_uint2(c, len);
@@ -396,7 +386,7 @@ __global__ void __launch_bounds__(MT_HEADS, RK_MT_MINB) k_match_small(MatchArgs 
     }
     s_key[1 + e] = key;
   }
-  if (tid == 0) s_key[0] = bs ? a.skey[bs - 1] : 0xFFFFFFFEu;  // a segment running in from the previous tile is that CTA's
+  if (tid == 0) s_key[0] = bs ? a.skey[bs - 1] >> a.key_shift : 0xFFFFFFFEu;  // a segment running in from the previous tile is that CTA's
   __syncthreads();
 
   // phase 0
@@ -519,11 +509,11 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
     seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
     if (seg >= nseg) return;
     const u32 start = a.worklist[seg];
-    const u32 key = a.skey[start];
+    const u32 key = a.skey[start] >> a.key_shift;
     u32 end = start;
     for (;;) {
       const u32 idx = end + lane;
-      const bool same = idx < a.m && a.skey[idx] == key;
+      const bool same = idx < a.m && (a.skey[idx] >> a.key_shift) == key;
       const u32 bal = __ballot_sync(0xFFFFFFFFu, same);
       end += __popc(bal);  // sorted keys: the matching lanes are a prefix
       if (bal != 0xFFFFFFFFu) break;

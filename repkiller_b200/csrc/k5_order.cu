@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(OT_TILE) k_order_tile(OrderArgs a) {
   if (mine) {
     const u32 src = s_perm[e], j = bs + e;
     a.out_order[j] = s_fidx[src];
-    a.out_gid[j] = gid;
+    a.out_gid[j] = gid + a.gid_base;
     a.out_repval[j] = (u8)(n == 1 ? 0 : (e == start ? 1 : 2));  // commonFunctions.cpp:106-115
     a.out_identity[j] = __uint_as_float(s_ident[src]);
   }
@@ -426,7 +426,7 @@ __device__ __forceinline__ void emit_sorted(const OrderArgs &a, const u64 *sorte
     load_member(a, gstart + (u32)sorted[t], r, h, fidx, ident);
     const u32 j = gstart + first + t;
     a.out_order[j] = fidx;
-    a.out_gid[j] = g;
+    a.out_gid[j] = g + a.gid_base;
     a.out_repval[j] = (u8)(first + t == 0 ? 1 : 2);  // commonFunctions.cpp:106-115
     a.out_identity[j] = __uint_as_float(ident);
   }

@@ -1,0 +1,420 @@
+// K7 — the kernels of ONE comparison partitioned over several GPUs (multi.cu drives them).
+//
+// The reference is single-process (no distributed backend); what has to be preserved is the order its
+// greedy loop visits fragments in (/root/reference/src/commonFunctions.cpp:51-77) and the reach of one
+// get_associated_group query (/root/reference/src/SequenceOcupationList.cpp:47-89: the own center/100 bucket and at
+// most one neighbour).  Every routing decision below is a function of key VALUES (cuts), never of a GPU id, and ties are
+// always broken by the global processing rank, so the result is bit-identical for any number of GPUs:
+//   * exchange 1: fragments go to the GPU that owns their xStart/10 range (processing order, generate_diagonal_func buckets);
+//   * X pass at home: the X super-bucket of a fragment starts at or after its xStart/100 bucket, so only fragments whose
+//     center reaches past the next cut travel ("halo", to higher GPUs only), and their owners travel back;
+//   * Y pass: fragments are regrouped by Y super-bucket ranges; only the 1-byte "matched in X" flags and the 4-byte
+//     owners move per (len_ratio, pos_ratio) pair;
+//   * forest: parents always have a smaller global rank; a chain that leaves the GPU is followed through the peers'
+//     parent arrays over NVLink (peer loads), group ids = per-GPU root scan + the root counts of the lower GPUs;
+//   * output: fragments go to the GPU that owns their group-id range for sort_groups.
+#include "rk_common.cuh"
+#include "rk_scan.cuh"
+
+namespace rk {
+
+// ---- cuts: contiguous key ranges of about equal population ---------------------------------------------------------
+
+// bin = key >> shift (at most DIST_BINS bins); keys equal to drop_key are not counted (the never-visited last X bucket)
+__global__ void __launch_bounds__(256) k_coarse_hist(const u32 *__restrict__ keys, u32 n, int shift, int pre_shift, u32 drop_key,
+                                                     u32 *__restrict__ hist) {
+  __shared__ u32 s_h[DIST_BINS];
+  for (u32 i = threadIdx.x; i < (u32)DIST_BINS; i += blockDim.x) s_h[i] = 0;
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u32 k = keys[i] >> pre_shift;
+    if (k != drop_key) atomicAdd(&s_h[min(k >> shift, (u32)DIST_BINS - 1)], 1u);
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < (u32)DIST_BINS; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
+}
+
+// one CTA of 1024 threads: hist_all[nr][DIST_BINS] summed over the ranks, cuts[r] = first bin boundary (as a key value)
+// at which the cumulative count reaches total*r/nr; cuts[0] = 0, cuts[nr] = 0xFFFFFFFF.  Identical on every rank.
+__global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__ hist_all, int nr, int shift, u32 *__restrict__ cuts) {
+  __shared__ unsigned long long s_cum[DIST_BINS + 1];
+  __shared__ unsigned long long s_part[1024];
+  constexpr int PER = DIST_BINS / 1024;
+  unsigned long long v[PER], sum = 0;
+  for (int j = 0; j < PER; ++j) {
+    const u32 b = threadIdx.x * PER + j;
+    unsigned long long c = 0;
+    for (int r = 0; r < nr; ++r) c += hist_all[(u64)r * DIST_BINS + b];
+    v[j] = c;
+    sum += c;
+  }
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int t = 0; t < 1024; ++t) {
+      const unsigned long long c = s_part[t];
+      s_part[t] = run;
+      run += c;
+    }
+    s_cum[DIST_BINS] = run;
+  }
+  __syncthreads();
+  unsigned long long run = s_part[threadIdx.x];
+  for (int j = 0; j < PER; ++j) {
+    s_cum[threadIdx.x * PER + j] = run;  // exclusive
+    run += v[j];
+  }
+  if (threadIdx.x <= (u32)nr) cuts[threadIdx.x] = threadIdx.x == (u32)nr ? 0xFFFFFFFFu : 0u;
+  __syncthreads();
+  const unsigned long long total = s_cum[DIST_BINS];
+  for (int j = 0; j < PER; ++j) {
+    const u32 b = threadIdx.x * PER + j;
+    const unsigned long long lo = s_cum[b], hi = s_cum[b + 1];
+    for (int r = 1; r < nr; ++r) {
+      const unsigned long long target = total * (unsigned long long)r / (unsigned long long)nr;
+      if (lo < target && target <= hi) {
+        const unsigned long long key = ((unsigned long long)b + 1) << shift;
+        cuts[r] = key > 0xFFFFFFFEull ? 0xFFFFFFFEu : (u32)key;
+      }
+    }
+  }
+}
+
+// group-id cuts: cuts[r] = floor(total_groups * r / nr) from the all-gathered root counts; also the total
+__global__ void k_cuts_gid(const u32 *__restrict__ nroots_all, int nr, u32 *__restrict__ cuts, u32 *__restrict__ total_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long total = 0;
+    for (int r = 0; r < nr; ++r) total += nroots_all[r];
+    for (int r = 0; r < nr; ++r) cuts[r] = (u32)(total * (unsigned long long)r / (unsigned long long)nr);
+    cuts[nr] = 0xFFFFFFFFu;
+    *total_out = (u32)total;
+  }
+}
+
+// X cuts: the first super-bucket (per strand class) a rank owns = run start of the bucket its xStart/10 range begins in
+__global__ void k_cuts_x(const u32 *__restrict__ cuts0, int nr, Geometry g, const u32 *__restrict__ link_x, u32 *__restrict__ cuts_x) {
+  const int t = threadIdx.x;
+  if (t >= 2 * nr) return;
+  const int s = t / nr, r = t % nr;
+  u32 b = 0;
+  if (r > 0) {
+    const u32 c = cuts0[r];
+    b = min(c / (DIVISOR / XBUCKET), g.nbx - 1);
+  }
+  // bit 0 of every strand class is never set (nothing links bucket 0 to a predecessor), so run_start stays in class s
+  cuts_x[t] = r == 0 ? (u32)s * g.nbx : run_start(link_x, (u32)s * g.nbx + b);
+}
+
+// ---- routing: destination rank of every element + per-destination counts ------------------------------------------
+// dest = largest r with cuts[r] <= key; elements with key == drop_key get dest nr ("nowhere"; they sort last).
+// MODE 0: plain keys against cuts[nr+1].  MODE 1 (X halo): key = keys[i] >> 1 against the per-strand table cuts[2][nr],
+// strand class = key >= nbx; elements that stay on this rank get dest nr as well (only the travellers are packed).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_route(const u32 *__restrict__ keys, u32 n, const u32 *__restrict__ cuts, int nr, u32 drop_key,
+                                               u32 nbx, int me, u32 *__restrict__ dest, u32 *__restrict__ counts) {
+  __shared__ u32 s_cuts[2 * DIST_MAX_RANKS + 2];
+  __shared__ u32 s_cnt[DIST_MAX_RANKS + 1];
+  const int ncut = MODE == 1 ? 2 * nr : nr + 1;
+  if (threadIdx.x < (u32)ncut) s_cuts[threadIdx.x] = cuts[threadIdx.x];
+  if (threadIdx.x <= (u32)nr) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // warp-uniform loop bounds: the per-destination counts are taken from ballots (lane r accumulates destination r)
+  const u32 lane = threadIdx.x & 31;
+  u32 acc = 0;
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 i = base + threadIdx.x;
+    int d = -1;
+    if (i < n) {
+      u32 k = keys[i];
+      if (MODE == 1) {
+        k >>= 1;
+        const u32 *c = s_cuts + (k >= nbx ? nr : 0);
+        d = 0;
+        for (int r = 1; r < nr; ++r) d = c[r] <= k ? r : d;
+        if (d == me) d = nr;
+      } else if (k == drop_key) {
+        d = nr;
+      } else {
+        d = 0;
+        for (int r = 1; r < nr; ++r) d = s_cuts[r] <= k ? r : d;
+      }
+      dest[i] = (u32)d;
+    }
+    for (int r = 0; r <= nr; ++r) {
+      const u32 b = __ballot_sync(0xFFFFFFFFu, d == r);
+      if (lane == (u32)r) acc += __popc(b);
+    }
+  }
+  if (lane <= (u32)nr && acc) atomicAdd(&s_cnt[lane], acc);
+  __syncthreads();
+  if (threadIdx.x <= (u32)nr && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// ---- row movers ----------------------------------------------------------------------------------------------------
+
+// out[t] = rec[perm[t]] (32-byte records, two uint4 each), t < n
+__global__ void __launch_bounds__(256) k_gather_rec32(const uint4 *__restrict__ rec, const u32 *__restrict__ perm, u32 n,
+                                                      uint4 *__restrict__ out) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint4 *src = rec + 2 * (u64)perm[t];
+  const uint4 a = src[0], b = src[1];
+  out[2 * (u64)t] = a;
+  out[2 * (u64)t + 1] = b;
+}
+
+// key0 = xStart / 10 of the arrived records (the sort key of the processing order)
+__global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ rec, u32 n, u32 *__restrict__ key0) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key0[i] = rec[2 * (u64)i].x / XBUCKET;
+}
+
+// rows of one axis pass: {key, center, length, global rank} of element perm[t]
+__global__ void __launch_bounds__(256) k_pack_axis_rows(const u32 *__restrict__ keys, const uint2 *__restrict__ cl, const u32 *__restrict__ perm,
+                                                        u32 n, u32 rank_off, u32 key_and, uint4 *__restrict__ rows) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const u32 i = perm[t];
+  const uint2 c = cl[i];
+  rows[t] = make_uint4(keys[i] & key_and, c.x, c.y, rank_off + i);
+}
+// ... and their arrival: keys[j], cl[j], grank[j] of row j
+__global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restrict__ rows, u32 n, u32 *__restrict__ keys,
+                                                          uint2 *__restrict__ cl, u32 *__restrict__ grank) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint4 r = rows[j];
+  keys[j] = r.x;
+  cl[j] = make_uint2(r.y, r.z);
+  grank[j] = r.w;
+}
+
+// rows of the output exchange: {h, file index, identity bits, gid} of rank perm[t]
+__global__ void __launch_bounds__(256) k_pack_gid_rows(const uint4 *__restrict__ hfi_r, const u32 *__restrict__ gid_rank,
+                                                       const u32 *__restrict__ perm, u32 n, uint4 *__restrict__ rows) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const u32 i = perm[t];
+  uint4 v = hfi_r[i];
+  v.w = gid_rank[i];
+  rows[t] = v;
+}
+__global__ void __launch_bounds__(256) k_gid_keys(const uint4 *__restrict__ rows, u32 n, u32 gid_base, u32 *__restrict__ keys) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) keys[j] = rows[j].w - gid_base;
+}
+
+// ---- owners: from indices of a rank's working list to global ranks ---------------------------------------------------
+
+// X pass: the working list is [own fragments 0..m) ++ [halo m..m+nh).  parent_x[i] = list index of the owner or NONE.
+//   own i  -> parent[i] (global rank) ; halo j -> halo_res[j] (travels back to the fragment's home rank)
+__global__ void __launch_bounds__(256) k_x_owners(const u32 *__restrict__ parent_x, u32 m, u32 nh, u32 rank_off,
+                                                  const u32 *__restrict__ halo_grank, u32 *__restrict__ parent, u32 *__restrict__ halo_res) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m + nh) return;
+  u32 o = parent_x[i];
+  if (o != RK_NONE32) o = o < m ? rank_off + o : halo_grank[o - m];
+  if (i < m) parent[i] = o;
+  else halo_res[i - m] = o;
+}
+// the owners of the fragments this rank sent away come back in send order: away_perm[t] = local rank of the t-th
+__global__ void __launch_bounds__(256) k_apply_away(const u32 *__restrict__ away_res, const u32 *__restrict__ away_perm, u32 n,
+                                                    u32 *__restrict__ parent) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) parent[away_perm[t]] = away_res[t];
+}
+// "matched in the X pass" flags in the order the Y rows were sent
+__global__ void __launch_bounds__(256) k_pack_xm(const u32 *__restrict__ parent, const u32 *__restrict__ perm, u32 n, u8 *__restrict__ xm) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) xm[t] = parent[perm[t]] != RK_NONE32 ? 1 : 0;
+}
+// Y pass: parent_y[j] = arrival index of the owner or NONE -> its global rank
+__global__ void __launch_bounds__(256) k_y_owners(const u32 *__restrict__ parent_y, const u32 *__restrict__ grank, u32 n, u32 *__restrict__ out) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const u32 o = parent_y[j];
+  out[j] = o == RK_NONE32 ? RK_NONE32 : grank[o];
+}
+// the Y owners come back in send order; a fragment matched in X keeps its X owner (commonFunctions.cpp:56-61)
+__global__ void __launch_bounds__(256) k_merge_y(const u32 *__restrict__ yo_back, const u32 *__restrict__ perm, u32 n, u32 *__restrict__ parent) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const u32 i = perm[t];
+  if (parent[i] == RK_NONE32) parent[i] = yo_back[t];
+}
+
+// ---- forest over peer memory ---------------------------------------------------------------------------------------
+struct LoadIsRootD {
+  const u32 *parent;
+  __device__ __forceinline__ u32 operator()(u64 i) const { return parent[i] == RK_NONE32 ? 1u : 0u; }
+};
+__global__ void k_store_total(const u32 *total, u32 *out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *out = *total;
+}
+
+// gid of local rank i: follow the parents to the root — through the peers' arrays when the chain leaves this GPU (peer
+// loads over NVLink; parents always have a smaller global rank, so chains only ever run towards lower GPUs) — then
+// gid(root) = roots of lower GPUs + roots before it on its own GPU.
+__global__ void __launch_bounds__(256) k_chase_peers(PeerTable pt, const u32 *__restrict__ nroots_all, u32 m, u32 *__restrict__ gid_rank) {
+  __shared__ u32 s_groot[DIST_MAX_RANKS];
+  if (threadIdx.x == 0) {
+    u32 run = 0;
+    for (int r = 0; r < pt.nr; ++r) {
+      s_groot[r] = run;
+      run += nroots_all[r];
+    }
+  }
+  __syncthreads();
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int s = pt.me;
+  u32 loc = i;  // (s, loc): the node the walk stands on
+  for (;;) {
+    const u32 p = pt.parent[s][loc];
+    if (p == RK_NONE32) break;
+    while (p < pt.roff[s]) --s;  // global rank p lives on the last rank whose offset is <= p
+    loc = p - pt.roff[s];
+  }
+  gid_rank[i] = s_groot[s] + pt.gidscan[s][loc];
+}
+
+// ---- small helpers ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_or_rows(const u32 *__restrict__ all, int nr, u64 words, u32 *__restrict__ out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= words) return;
+  u32 v = 0;
+  for (int r = 0; r < nr; ++r) v |= all[(u64)r * words + i];
+  out[i] = v;
+}
+
+static inline unsigned blocks_for(u64 n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+static inline int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_key, u32 *hist, cudaStream_t st) {
+  cudaMemsetAsync(hist, 0, DIST_BINS * sizeof(u32), st);
+  if (n == 0) return 0;
+  unsigned b = blocks_for(n, 256 * 8);
+  const unsigned cap = (unsigned)sm_count() * 4;
+  k_coarse_hist<<<b > cap ? cap : b, 256, 0, st>>>(keys, n, shift, pre_shift, drop_key, hist);
+  return 1;
+}
+int dist_cuts_from_hist(const u32 *hist_all, int nr, int shift, u32 *cuts, cudaStream_t st) {
+  k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, nr, shift, cuts);
+  return 1;
+}
+int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st) {
+  k_cuts_gid<<<1, 32, 0, st>>>(nroots_all, nr, cuts, total);
+  return 1;
+}
+int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st) {
+  k_cuts_x<<<1, 64, 0, st>>>(cuts0, nr, g, link_x, cuts_x);
+  return 1;
+}
+int dist_route(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *dest, u32 *counts, cudaStream_t st) {
+  cudaMemsetAsync(counts, 0, (nr + 1) * sizeof(u32), st);
+  if (n == 0) return 0;
+  unsigned b = blocks_for(n, 256 * 4);
+  const unsigned cap = (unsigned)sm_count() * 8;
+  k_route<0><<<b > cap ? cap : b, 256, 0, st>>>(keys, n, cuts, nr, drop_key, 0, 0, dest, counts);
+  return 1;
+}
+int dist_route_x(const u32 *keys2, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 *dest, u32 *counts, cudaStream_t st) {
+  cudaMemsetAsync(counts, 0, (nr + 1) * sizeof(u32), st);
+  if (n == 0) return 0;
+  unsigned b = blocks_for(n, 256 * 4);
+  const unsigned cap = (unsigned)sm_count() * 8;
+  k_route<1><<<b > cap ? cap : b, 256, 0, st>>>(keys2, n, cuts_x, nr, 0xFFFFFFFFu, nbx, me, dest, counts);
+  return 1;
+}
+int dist_gather_rec32(const uint4 *rec, const u32 *perm, u32 n, uint4 *out, cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_gather_rec32<<<blocks_for(n), 256, 0, st>>>(rec, perm, n, out);
+  return 1;
+}
+int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_key0_of_rec<<<blocks_for(n), 256, 0, st>>>(rec, n, key0);
+  return 1;
+}
+int dist_pack_axis_rows(const u32 *keys, const uint2 *cl, const u32 *perm, u32 n, u32 rank_off, u32 key_and, uint4 *rows, cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_pack_axis_rows<<<blocks_for(n), 256, 0, st>>>(keys, cl, perm, n, rank_off, key_and, rows);
+  return 1;
+}
+int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_unpack_axis_rows<<<blocks_for(n), 256, 0, st>>>(rows, n, keys, cl, grank);
+  return 1;
+}
+int dist_pack_gid_rows(const uint4 *hfi_r, const u32 *gid_rank, const u32 *perm, u32 n, uint4 *rows, cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_pack_gid_rows<<<blocks_for(n), 256, 0, st>>>(hfi_r, gid_rank, perm, n, rows);
+  return 1;
+}
+int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_gid_keys<<<blocks_for(n), 256, 0, st>>>(rows, n, gid_base, keys);
+  return 1;
+}
+int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, u32 *halo_res, cudaStream_t st) {
+  if (m + nh == 0) return 0;
+  k_x_owners<<<blocks_for((u64)m + nh), 256, 0, st>>>(parent_x, m, nh, rank_off, halo_grank, parent, halo_res);
+  return 1;
+}
+int dist_apply_away(const u32 *away_res, const u32 *away_perm, u32 n, u32 *parent, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_apply_away<<<blocks_for(n), 256, 0, st>>>(away_res, away_perm, n, parent);
+  return 1;
+}
+int dist_pack_xm(const u32 *parent, const u32 *perm, u32 n, u8 *xm, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_pack_xm<<<blocks_for(n), 256, 0, st>>>(parent, perm, n, xm);
+  return 1;
+}
+int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_y_owners<<<blocks_for(n), 256, 0, st>>>(parent_y, grank, n, out);
+  return 1;
+}
+int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_merge_y<<<blocks_for(n), 256, 0, st>>>(yo_back, perm, n, parent);
+  return 1;
+}
+u64 dist_scan_work_bytes(u32 m) { return scan_work_words(m ? m : 1) * 4 + 256; }
+// gidscan[i] = roots among local ranks < i; *nroots = roots on this rank
+int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *work, cudaStream_t st) {
+  if (m == 0) {
+    cudaMemsetAsync(nroots, 0, sizeof(u32), st);
+    return 0;
+  }
+  u32 *bsum = (u32 *)work;
+  const int l = exclusive_scan_u32(LoadIsRootD{parent}, gidscan, m, bsum, st);
+  const u32 nb = (u32)(((u64)m + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  k_store_total<<<1, 32, 0, st>>>(bsum + nb, nroots);
+  return l + 1;
+}
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, u32 *gid_rank, cudaStream_t st) {
+  if (m == 0) return 0;
+  KScope ks(KID_CHASE, st, m);
+  k_chase_peers<<<blocks_for(m), 256, 0, st>>>(pt, nroots_all, m, gid_rank);
+  return 1;
+}
+int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st) {
+  if (words == 0) return 0;
+  k_or_rows<<<blocks_for(words), 256, 0, st>>>(all, nr, words, out);
+  return 1;
+}
+
+}  // namespace rk

@@ -75,6 +75,21 @@ __device__ __forceinline__ bool probes_prev(u32 c) { return (c % DIVISOR) <= 1 &
 
 __device__ __forceinline__ u32 absdiff(u32 a, u32 b) { return a > b ? a - b : b - a; }
 
+// first bucket of the run of linked buckets that bucket k belongs to (link bit k: k is processed together with k-1)
+__device__ __forceinline__ u32 run_start(const u32 *__restrict__ bm, u32 k) {
+  // largest k' <= k whose link bit is clear (bit 0 of every strand class is never set)
+  u32 w = k >> 5;
+  u32 m = 0xFFFFFFFFu >> (31 - (k & 31));
+  for (;;) {
+    const u32 z = ~bm[w] & m;
+    if (z) return (w << 5) + (31 - __clz(z));
+    if (w == 0) return 0;
+    --w;
+    m = 0xFFFFFFFFu;
+  }
+}
+
+
 // ---- digit histograms of a sort key, accumulated by the kernel that PRODUCES the key (saves the sort's own histogram
 // pass: one more read of the keys and a launch).  ghist: [4][256] global counters (zeroed by the caller), or nullptr.
 struct HistOut {
@@ -117,7 +132,8 @@ __device__ __forceinline__ void hist_flush(u32 (*h)[HIST_RADIX], const HistOut &
 // ---- per-kernel timing (CUDA events around every launch; off unless rk_profile_enable) ---------------
 enum KernelId {
   KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
-  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_FORMAT, KID_COUNT
+  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_FORMAT, KID_DIST_ROWS, KID_STATS,
+  KID_COUNT
 };
 void prof_begin(int kid, cudaStream_t st, unsigned long long units);
 void prof_end(cudaStream_t st);
@@ -141,7 +157,7 @@ int launch_gen(u64 seed, u64 lx, u64 ly, double p_rep, u64 families, u64 ax, u64
 // K1: decode n packed records (device, 16-byte aligned) into file-order SoA, raise link bits.
 int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, u8 *flags, float *identity,
                   u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4 = nullptr,
-                  HistOut hist = HistOut{nullptr, 0, 0});
+                  HistOut hist = HistOut{nullptr, 0, 0}, u32 fidx_base = 0);
 
 // K2: stable LSD radix sort of (key,value) pairs; result in keys_out/vals_out.
 u64 sort_work_bytes(u64 n);
@@ -153,10 +169,11 @@ int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32
 // K2 keys: rank-order SoA + super-bucket sort keys.
 // rec4: file order, two 16-byte words per record {xStart, yStart, length, flags} {identity bits, 0, 0, 0} (one 32-byte
 // sector per gather); xl_r/yl_r: rank-order {center, length} per axis (one 8-byte gather per fragment in the match
-// kernels); identity_r: rank order
+// kernels); identity_r: rank order.  Multi-GPU: gfidx_r = the record's global file index (second word of rec4), and with
+// own_bit the X key is written as 2*key+1 so that halo entries (2*key) of the same super-bucket sort before the rank's own
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
                 uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x = HistOut{nullptr, 0, 0},
-                HistOut hist_y = HistOut{nullptr, 0, 0});
+                HistOut hist_y = HistOut{nullptr, 0, 0}, u32 *gfidx_r = nullptr, u32 own_bit = 0);
 
 int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
                        const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
@@ -183,6 +200,8 @@ struct MatchArgs {
   u32 work_cap;
   u32 *ent_rank, *ent_c, *ent_len;  // scratch of m entries each for long segments
   u32 *err;
+  int key_shift;       // segments are runs of equal (skey >> key_shift); multi-GPU X pass: bit 0 = "own fragment, not halo"
+  const u8 *xm_bytes;  // Y pass, when set: one byte per rank instead of the xm_bits map (multi-GPU: the flags travel as bytes)
   // direct layout (multi-GPU stages): inputs already in sorted order, result per sorted position
   int direct;
   const u32 *sc, *slen;
@@ -222,6 +241,7 @@ struct OrderArgs {
   u32 range_cap;
   u32 m;
   int do_sort;
+  u32 gid_base;  // added to sgid for out_gid (multi-GPU: a rank sorts its range of groups by gid - first gid of the range)
   // start positions of the groups of more than 16 / 128 / 1024 members; work_count[2*i] = entries of list i,
   // work_count[2*i+1] = its pop cursor; work_count[6], [7]: the same for `ranges`
   u32 *worklist[3];
@@ -247,6 +267,37 @@ struct FormatArgs {
 u64 format_work_bytes(u32 n_lines);
 constexpr u32 RK_FORMAT_MAX_LINE = 208;  // upper bound of one line in bytes
 int launch_format(FormatArgs a, void *work, cudaStream_t st);
+
+// K7 (k7_dist.cu): one comparison partitioned over several GPUs — cuts, routing, row movers, forest over peer memory
+constexpr int DIST_BINS = 4096;       // coarse histogram bins a range partition is cut on
+constexpr int DIST_MAX_RANKS = 16;
+struct PeerTable {                    // what a rank needs to follow a parent chain across GPUs
+  const u32 *parent[DIST_MAX_RANKS];  // every rank's parent array (global ranks), mapped peer memory
+  const u32 *gidscan[DIST_MAX_RANKS]; // every rank's exclusive scan of root flags
+  u32 roff[DIST_MAX_RANKS + 1];       // first global rank of every rank
+  int nr, me;
+};
+int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_key, u32 *hist, cudaStream_t st);
+int dist_cuts_from_hist(const u32 *hist_all, int nr, int shift, u32 *cuts, cudaStream_t st);
+int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st);
+int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st);
+int dist_route(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *dest, u32 *counts, cudaStream_t st);
+int dist_route_x(const u32 *keys2, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 *dest, u32 *counts, cudaStream_t st);
+int dist_gather_rec32(const uint4 *rec, const u32 *perm, u32 n, uint4 *out, cudaStream_t st);
+int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, cudaStream_t st);
+int dist_pack_axis_rows(const u32 *keys, const uint2 *cl, const u32 *perm, u32 n, u32 rank_off, u32 key_and, uint4 *rows, cudaStream_t st);
+int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, cudaStream_t st);
+int dist_pack_gid_rows(const uint4 *hfi_r, const u32 *gid_rank, const u32 *perm, u32 n, uint4 *rows, cudaStream_t st);
+int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, cudaStream_t st);
+int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, u32 *halo_res, cudaStream_t st);
+int dist_apply_away(const u32 *away_res, const u32 *away_perm, u32 n, u32 *parent, cudaStream_t st);
+int dist_pack_xm(const u32 *parent, const u32 *perm, u32 n, u8 *xm, cudaStream_t st);
+int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaStream_t st);
+int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st);
+u64 dist_scan_work_bytes(u32 m);
+int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *work, cudaStream_t st);
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, u32 *gid_rank, cudaStream_t st);
+int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st);
 
 u64 order_scratch_bytes(u64 m);
 void order_carve(OrderArgs &a, void *scratch, u64 m);  // sets packed .. worklist, work_cap
