@@ -7,9 +7,11 @@ K5 diag/sort/labels) for len_ratio = pos_ratio = 0.05.
   value : records already resident in HBM, result left in HBM; CUDA events on the launching stream.
   e2e   : the same step through the C ABI with HOST buffers: pinned records -> H2D -> kernels -> D2H of
           order/gid/repval/identity into pinned host arrays.
-N > 1: one process per GPU (torchrun).  Default: ONE comparison of N x the per-GPU size, range-partitioned over
-the GPUs with three all-to-all redistributions and a parent all-gather over NCCL (repkiller_b200/dist.py; weak
-scaling: per-GPU fragments fixed).  --multi independent: one independent sequence-pair comparison per GPU.
+N > 1: one process per GPU (torchrun).  Default: ONE comparison of N x the per-GPU size, partitioned over the GPUs inside
+the library (rk_dist_*: range partition by xStart/10, X pass at home with a halo, Y exchange, forest over peer memory,
+output exchange; NCCL over NVLink; weak scaling: per-GPU fragments fixed).  Its checksum is printed next to the checksum
+of the SAME comparison grouped on one GPU (outside the timed region).  --multi independent: one independent
+sequence-pair comparison per GPU.
 `--impl reference` times the reference's own CPU code (oracle/_ref, built from /root/reference) on host cores.
 """
 from __future__ import annotations
@@ -47,8 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--total-n", type=float, default=0, help="partitioned mode: total fragments of the one comparison (e.g. 1e9)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (very large slices)")
-    ap.add_argument("--checksum", type=int, default=0, help="also print a position-dependent checksum of the whole output")
-    ap.add_argument("--sections", type=int, default=0, help="partitioned mode: CUDA-event time per section (adds syncs)")
+    ap.add_argument("--checksum", type=int, default=1, help="position-dependent checksum of the whole output; N > 1: also of the same comparison on one GPU")
     ap.add_argument("--multi", default="partitioned", choices=["partitioned", "independent"],
                     help="N > 1: one comparison range-partitioned over the GPUs (default) or one independent comparison per GPU")
     ap.add_argument("--profile-kernels", type=int, default=1, help="CUDA-event pairs around every kernel launch in the timed region")
@@ -257,8 +258,7 @@ def ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from repkiller_b200 import capi, gen
-    from repkiller_b200.dist import Comm, CudaStages, group_partitioned
+    from repkiller_b200 import capi, gen, multi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,8 +276,7 @@ def ours(args):
         # ONE comparison, range-partitioned over the GPUs: world x the per-GPU size of the named shape (same density;
         # weak scaling), or with --total-n exactly that many fragments in all (config 5: --workload c5 --total-n 1e9)
         w = gen.scaled(base, args.total_n) if args.total_n else gen.scaled(base, base.n * world)
-        lo, hi = w.n * rank // world, w.n * (rank + 1) // world
-        lo, hi = lo - lo % 16, (hi - hi % 16 if rank + 1 < world else hi)   # slices start on a 16-record boundary
+        lo, hi = multi.slice_bounds(w.n, rank, world)
         n_total = w.n
     else:
         w = workload(args, rank)   # rank r: its own sequence pair of the same shape
@@ -308,35 +307,25 @@ def ours(args):
 
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    stages, comm = CudaStages(ctx, device), Comm()
-    dev2 = torch.empty(n * 109, dtype=torch.uint8, device=device) if partitioned and do_e2e else None
-    pinned_out = {}
+    if partitioned:
+        multi.bootstrap(ctx, multi.default_capacity(n_total // world + 16))   # NCCL id + peer-memory handles, once
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    section_ms = {}
-
     def step_resident():
         if partitioned:
-            return group_partitioned(stages, comm, dev, n, lo, lx1, ly1, w.len_ratio, w.pos_ratio,
-                                     timings=section_ms if args.sections else None)
+            st = ctx.dist_load(dev.data_ptr(), n, lo, lx1, ly1)
+            return st, ctx.dist_group(w.len_ratio, w.pos_ratio, host_result=False, timing=True)
         st = ctx.load(dev.data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=False)
 
-    def step_e2e():
+    def step_e2e():   # pinned host records in, pinned host result out, through the same two C-ABI calls
         if partitioned:
-            dev2.copy_(host, non_blocking=True)
-            r = group_partitioned(stages, comm, dev2, n, lo, lx1, ly1, w.len_ratio, w.pos_ratio)
-            for name in ("order", "gid", "repval", "identity"):
-                t = getattr(r, name)
-                if name not in pinned_out or pinned_out[name].numel() < t.numel():
-                    pinned_out[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype).pin_memory()
-                pinned_out[name][: t.numel()].copy_(t, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return r
+            st = ctx.dist_load(host.data_ptr(), n, lo, lx1, ly1)
+            return st, ctx.dist_group(w.len_ratio, w.pos_ratio, host_result=True, copy=False, timing=True)
         st = ctx.load(host.data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=True, copy=False)   # pinned result buffers, as a C caller sees them
 
@@ -385,39 +374,45 @@ def ours(args):
     else:
         ms_e2e = float("nan")
 
-    checksum = None
+    # Checksum of the whole output (position-dependent, 64 bit), outside the timed regions.  N > 1: the sum over the ranks'
+    # ranges of lines, and beside it the checksum of the SAME comparison grouped by rank 0 alone on its one GPU
+    # (rk_load_aos + rk_group on all N x per-GPU fragments): the two must be equal.
+    checksum = checksum_1gpu = None
     if args.checksum:
-        # position-dependent 64-bit checksum of the whole output (sum over ranks): equal for any number of GPUs
         with torch.cuda.stream(stream):
             if partitioned:
-                o, g_, rp, idn = last.order, last.gid, last.repval, last.identity
-                lines_all = comm.all_gather_ints(int(o.shape[0]), device)
-                off = sum(lines_all[:rank])
+                st_h = ctx.dist_load(dev.data_ptr(), n, lo, lx1, ly1)
+                res_h, info_h = ctx.dist_group(w.len_ratio, w.pos_ratio, host_result=True)
+                cs_local = multi.output_checksum(res_h.order, res_h.gid, res_h.repval, res_h.identity, info_h["line_offset"])
+                halves = torch.tensor([cs_local & 0xFFFFFFFF, cs_local >> 32], dtype=torch.int64, device=device)
+                dist.all_reduce(halves)
+                lo32, hi32 = int(halves[0].item()), int(halves[1].item())
+                checksum = (lo32 + (hi32 << 32)) & ((1 << 64) - 1)
+                if rank == 0 and n_total * 450 < 150e9:   # the whole comparison fits one B200
+                    ctx1 = capi.Context(local)
+                    whole = torch.empty(n_total * 109 + 16, dtype=torch.uint8, device=device)
+                    ctx1.generate_device(w, 0, n_total, whole.data_ptr())
+                    ctx1.load(whole.data_ptr(), lx1, ly1, n=n_total)
+                    r1 = ctx1.group(w.len_ratio, w.pos_ratio, host_result=True)
+                    checksum_1gpu = multi.output_checksum(r1.order, r1.gid, r1.repval, r1.identity)
+                    ctx1.close()
+                    del whole, r1
             else:
                 res_h = ctx.group(w.len_ratio, w.pos_ratio, host_result=True)
-                o, g_, rp, idn = (torch.from_numpy(a).to(device) for a in (res_h.order.view(np.int32), res_h.gid.view(np.int32),
-                                                                           res_h.repval, res_h.identity))
-                off = 0
-            pos = torch.arange(off, off + o.shape[0], dtype=torch.int64, device=device)
-            mix = (pos + 1) * 0x1E3779B97F4A7C15   # int64 arithmetic wraps
-            word = (o.to(torch.int64) & 0xFFFFFFFF) * 1000003 + (g_.to(torch.int64) & 0xFFFFFFFF) * 10007 + rp.to(torch.int64) * 101 \
-                + (idn.view(torch.int32).to(torch.int64) & 0xFFFFFFFF)
-            cs = ((word ^ mix) * 0x2545F4914F6CDD1D).sum().reshape(1)
-            if world > 1 and partitioned:
-                dist.all_reduce(cs)
-            checksum = int(cs.item()) & ((1 << 64) - 1)
+                checksum = multi.output_checksum(res_h.order, res_h.gid, res_h.repval, res_h.identity)
 
     value = n_total * args.steps / (ms_total / 1e3)
     e2e_value = n_total * args.steps / (ms_e2e / 1e3)
+    st, res_info = last
     if partitioned:
-        kept, groups, lines = last.n_kept, last.n_groups, last.n_local_lines
-        stage_ms = {}
-        exchanged = last.bytes_exchanged // max(1, args.warmup + args.steps)
+        res, info = res_info
+        kept, groups, lines = info["total_kept"], res.n_groups, info["n_lines"]
+        exchanged = info["bytes_sent"]
     else:
-        st, res = last
+        res = res_info
         kept, groups, lines = res.n_kept, res.n_groups, res.n_kept
-        stage_ms = {k: round(v, 4) for k, v in {**st.ms_stage, **{k2: v2 for k2, v2 in res.ms_stage.items() if v2}}.items() if v}
         exchanged = 0
+    stage_ms = {k: round(v, 4) for k, v in {**st.ms_stage, **{k2: v2 for k2, v2 in res.ms_stage.items() if v2}}.items() if v}
 
     line = None
     if rank == 0:
@@ -445,21 +440,23 @@ def ours(args):
             "dtype": "u32+f64", "data": "synthetic",
             "config": {"workload": workload_text(w), "per_gpu_fragments": n, "kept": int(kept), "groups": int(groups),
                        "l2": "inputs larger than L2 (1.09 GB of records per GPU and step vs 126 MB)" if n * 109 > 200e6 else "inputs smaller than L2 (reduced --n run)",
-                       "multi_gpu": ("one comparison range-partitioned over the GPUs: 3 all-to-all redistributions + parent all-gather over NCCL, "
-                                     f"{exchanged / 1e6:.0f} MB sent per GPU and step" if partitioned else
+                       "multi_gpu": ("one comparison partitioned over the GPUs inside librk_b200 (rk_dist_*): records to the owner of their "
+                                     "xStart/10 range, X pass at home with a halo, Y exchange, forest over peer memory, output exchange; "
+                                     f"NCCL send/recv, {exchanged / 1e6:.0f} MB sent by rank 0 in the grouping call of a step" if partitioned else
                                      "independent sequence pairs per rank, no data-path collective") if world > 1 else "single GPU"},
-            "checksum": checksum,
+            "checksum": checksum, "checksum_same_comparison_on_1_gpu": checksum_1gpu,
+            "checksum_match": (checksum == checksum_1gpu) if checksum_1gpu is not None else None,
             "e2e": {"value": e2e_value if do_e2e else None, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(lines * 13 + 40),
                     "ms_per_step": ms_e2e / args.steps},
             # kernels of this library launched inside timed region 1 (the C ABI counts them per call); the partitioned
             # path reports its timed launch groups (torch's own kernels and NCCL are not counted)
-            "gpu_launches": (int((st.n_launches + res.n_launches) * args.steps) if not partitioned
-                             else (int(sum(v[0] for v in prof.values())) if prof else None)),
+            # (partitioned: rank 0's kernels; NCCL's own kernels are not counted)
+            "gpu_launches": int((st.n_launches + res.n_launches) * args.steps),
             "clocks": clocks,
             "roofline": roofline,
             "pipeline_alg_bytes_per_fragment": round(total_alg / args.steps / n, 1),
             "pipeline_hbm_frac": round(total_alg / (ms_total / 1e3) / 1e9 / peak_gbs, 4),
-            "stage_ms": stage_ms if not partitioned else {k: round(statistics.median(v[-args.steps:]), 3) for k, v in section_ms.items()},
+            "stage_ms": stage_ms,
             "kernels": kernels,
         }
     if world > 1:
