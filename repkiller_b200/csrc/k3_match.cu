@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256)
       ys_r[i] = y;
       kxv = run_start(link_x, sc * g.nbx + cx / DIVISOR);
       kyv = run_start(link_y, sc * g.nby + cy / DIVISOR);
-      kx[i] = own_bit ? 2 * kxv + 1 : kxv;
+      if (own_bit) kxv = 2 * kxv + 1;
+      kx[i] = kxv;
       ky[i] = kyv;
     }
     if (do_hist) {

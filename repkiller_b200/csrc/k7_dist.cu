@@ -107,103 +107,217 @@ __global__ void k_cuts_x(const u32 *__restrict__ cuts0, int nr, Geometry g, cons
   cuts_x[t] = r == 0 ? (u32)s * g.nbx : run_start(link_x, (u32)s * g.nbx + b);
 }
 
-// ---- routing: destination rank of every element + per-destination counts ------------------------------------------
-// dest = largest r with cuts[r] <= key; elements with key == drop_key get dest nr ("nowhere"; they sort last).
+// ---- routing: a stable split of the local elements by destination rank, fused with the packing of the rows ----------
+// dest(key) = largest r with cuts[r] <= key; key == drop_key -> nr ("nowhere": the never-visited last X bucket).
 // MODE 0: plain keys against cuts[nr+1].  MODE 1 (X halo): key = keys[i] >> 1 against the per-strand table cuts[2][nr],
 // strand class = key >= nbx; elements that stay on this rank get dest nr as well (only the travellers are packed).
+// Three launches: per-tile counts -> exclusive offsets (per destination over the tiles) -> every tile writes its rows at
+// their final place in the send buffer, reading its inputs coalesced.  Stable: inside a destination the elements keep
+// their order (file order / processing order), which is what carries the reference's visiting order across GPUs.
+struct RouteArgs {
+  const u32 *keys;
+  u32 n;
+  const u32 *cuts;
+  int nr, me;
+  u32 drop_key, nbx;
+  u32 out_cap;  // rows the send buffer holds: nothing is written past it (the host checks the counts afterwards)
+};
+constexpr int SPLIT_ROUNDS = 8;
+constexpr int SPLIT_TILE = 256 * SPLIT_ROUNDS;
+constexpr int NRP = DIST_MAX_RANKS + 1;
+
 template <int MODE>
-__global__ void __launch_bounds__(256) k_route(const u32 *__restrict__ keys, u32 n, const u32 *__restrict__ cuts, int nr, u32 drop_key,
-                                               u32 nbx, int me, u32 *__restrict__ dest, u32 *__restrict__ counts) {
+__device__ __forceinline__ int route_of(u32 k, const u32 *s_cuts, const RouteArgs &a) {
+  int d = 0;
+  if (MODE == 1) {
+    k >>= 1;
+    const u32 *c = s_cuts + (k >= a.nbx ? a.nr : 0);
+    for (int r = 1; r < a.nr; ++r) d = c[r] <= k ? r : d;
+    if (d == a.me) d = a.nr;
+  } else if (k == a.drop_key) {
+    d = a.nr;
+  } else {
+    for (int r = 1; r < a.nr; ++r) d = s_cuts[r] <= k ? r : d;
+  }
+  return d;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_route_count(RouteArgs a, u32 *__restrict__ tile_cnt, u32 *__restrict__ counts) {
   __shared__ u32 s_cuts[2 * DIST_MAX_RANKS + 2];
-  __shared__ u32 s_cnt[DIST_MAX_RANKS + 1];
-  const int ncut = MODE == 1 ? 2 * nr : nr + 1;
-  if (threadIdx.x < (u32)ncut) s_cuts[threadIdx.x] = cuts[threadIdx.x];
-  if (threadIdx.x <= (u32)nr) s_cnt[threadIdx.x] = 0;
+  __shared__ u32 s_cnt[NRP];
+  const int ncut = MODE == 1 ? 2 * a.nr : a.nr + 1;
+  if (threadIdx.x < (u32)ncut) s_cuts[threadIdx.x] = a.cuts[threadIdx.x];
+  if (threadIdx.x < (u32)NRP) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  // warp-uniform loop bounds: the per-destination counts are taken from ballots (lane r accumulates destination r)
   const u32 lane = threadIdx.x & 31;
-  u32 acc = 0;
-  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
-    const u64 i = base + threadIdx.x;
-    int d = -1;
-    if (i < n) {
-      u32 k = keys[i];
-      if (MODE == 1) {
-        k >>= 1;
-        const u32 *c = s_cuts + (k >= nbx ? nr : 0);
-        d = 0;
-        for (int r = 1; r < nr; ++r) d = c[r] <= k ? r : d;
-        if (d == me) d = nr;
-      } else if (k == drop_key) {
-        d = nr;
-      } else {
-        d = 0;
-        for (int r = 1; r < nr; ++r) d = s_cuts[r] <= k ? r : d;
-      }
-      dest[i] = (u32)d;
-    }
-    for (int r = 0; r <= nr; ++r) {
+  u32 acc = 0;  // lane r accumulates destination r
+  const u64 base = (u64)blockIdx.x * SPLIT_TILE;
+#pragma unroll
+  for (int j = 0; j < SPLIT_ROUNDS; ++j) {
+    const u64 i = base + (u64)j * 256 + threadIdx.x;
+    const int d = i < a.n ? route_of<MODE>(a.keys[i], s_cuts, a) : -1;
+    for (int r = 0; r <= a.nr; ++r) {
       const u32 b = __ballot_sync(0xFFFFFFFFu, d == r);
       if (lane == (u32)r) acc += __popc(b);
     }
   }
-  if (lane <= (u32)nr && acc) atomicAdd(&s_cnt[lane], acc);
+  if (lane <= (u32)a.nr && acc) atomicAdd(&s_cnt[lane], acc);
   __syncthreads();
-  if (threadIdx.x <= (u32)nr && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x <= (u32)a.nr) {
+    const u32 c = s_cnt[threadIdx.x];
+    tile_cnt[(u64)blockIdx.x * NRP + threadIdx.x] = c;
+    if (c) atomicAdd(&counts[threadIdx.x], c);
+  }
+}
+
+// block d: tile_cnt[.][d] -> exclusive prefix over the tiles + start of destination d in the send buffer
+__global__ void __launch_bounds__(1024) k_tile_offsets(u32 *__restrict__ tile_cnt, u32 tiles, const u32 *__restrict__ counts) {
+  const int d = blockIdx.x;
+  __shared__ u32 s_carry;
+  if (threadIdx.x == 0) {
+    u32 base = 0;
+    for (int r = 0; r < d; ++r) base += counts[r];
+    s_carry = base;
+  }
+  __syncthreads();
+  for (u32 t0 = 0; t0 < tiles; t0 += 1024) {
+    const u32 t = t0 + threadIdx.x;
+    const u32 v = t < tiles ? tile_cnt[(u64)t * NRP + d] : 0;
+    u32 total;
+    const u32 ex = block_excl_scan<1024>(v, &total);
+    const u32 c = s_carry;
+    if (t < tiles) tile_cnt[(u64)t * NRP + d] = c + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = c + total;
+    __syncthreads();
+  }
+}
+
+struct PayRec32 {  // exchange 1: the whole 32-byte record
+  const uint4 *rec;
+  uint4 *out;
+  __device__ __forceinline__ void operator()(u32 i, u32 pos) const {
+    const uint4 a = rec[2 * (u64)i], b = rec[2 * (u64)i + 1];
+    out[2 * (u64)pos] = a;
+    out[2 * (u64)pos + 1] = b;
+  }
+};
+struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
+  const u32 *keys;
+  const uint2 *cl;
+  u32 rank_off, key_and;
+  uint4 *out;
+  __device__ __forceinline__ void operator()(u32 i, u32 pos) const {
+    const uint2 c = cl[i];
+    out[pos] = make_uint4(keys[i] & key_and, c.x, c.y, rank_off + i);
+  }
+};
+struct PayGidRow {  // output exchange: {h, file index, identity bits, gid}
+  const uint4 *hfi_r;
+  const u32 *gid_rank;
+  uint4 *out;
+  __device__ __forceinline__ void operator()(u32 i, u32 pos) const {
+    uint4 v = hfi_r[i];
+    v.w = gid_rank[i];
+    out[pos] = v;
+  }
+};
+
+template <int MODE, class Pay>
+__global__ void __launch_bounds__(256) k_split_pack(RouteArgs a, const u32 *__restrict__ tile_off, Pay pay, u32 *__restrict__ perm) {
+  __shared__ u32 s_cuts[2 * DIST_MAX_RANKS + 2];
+  __shared__ u32 s_run[NRP];
+  __shared__ u32 s_w[8][NRP];
+  const int ncut = MODE == 1 ? 2 * a.nr : a.nr + 1;
+  const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < (u32)ncut) s_cuts[tid] = a.cuts[tid];
+  if (tid < (u32)NRP) s_run[tid] = tid < (u32)a.nr ? tile_off[(u64)blockIdx.x * NRP + tid] : 0;
+  __syncthreads();
+  const u32 lt = lanemask_lt();
+  const u64 base = (u64)blockIdx.x * SPLIT_TILE;
+  for (int j = 0; j < SPLIT_ROUNDS; ++j) {
+    const u64 i = base + (u64)j * 256 + tid;
+    const int d = i < a.n ? route_of<MODE>(a.keys[i], s_cuts, a) : -1;
+    u32 before = 0, cnt = 0;
+    for (int r = 0; r < a.nr; ++r) {
+      const u32 b = __ballot_sync(0xFFFFFFFFu, d == r);
+      if (d == r) before = __popc(b & lt);
+      if (lane == (u32)r) cnt = __popc(b);
+    }
+    if (lane < (u32)a.nr) s_w[w][lane] = cnt;
+    __syncthreads();
+    if (d >= 0 && d < a.nr) {
+      u32 pos = s_run[d] + before;
+      for (u32 q = 0; q < w; ++q) pos += s_w[q][d];
+      if (pos < a.out_cap) {
+        pay((u32)i, pos);
+        if (perm) perm[pos] = (u32)i;
+      }
+    }
+    __syncthreads();
+    if (tid < (u32)a.nr) {
+      u32 t = 0;
+      for (int q = 0; q < 8; ++q) t += s_w[q][tid];
+      s_run[tid] += t;
+    }
+    __syncthreads();
+  }
 }
 
 // ---- row movers ----------------------------------------------------------------------------------------------------
 
-// out[t] = rec[perm[t]] (32-byte records, two uint4 each), t < n
-__global__ void __launch_bounds__(256) k_gather_rec32(const uint4 *__restrict__ rec, const u32 *__restrict__ perm, u32 n,
-                                                      uint4 *__restrict__ out) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const uint4 *src = rec + 2 * (u64)perm[t];
-  const uint4 a = src[0], b = src[1];
-  out[2 * (u64)t] = a;
-  out[2 * (u64)t + 1] = b;
-}
+// The three kernels below produce the keys of a sort; like K1/K2 on one GPU they count the digits of those keys on the way
+// (HistOut), so that the sort needs no histogram pass of its own.  Warp-uniform loops: every lane votes in hist_add.
 
 // key0 = xStart / 10 of the arrived records (the sort key of the processing order)
-__global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ rec, u32 n, u32 *__restrict__ key0) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) key0[i] = rec[2 * (u64)i].x / XBUCKET;
+__global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ rec, u32 n, u32 *__restrict__ key0, HistOut ho) {
+  __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
+  hist_zero(s_h);
+  __syncthreads();
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 i = base + threadIdx.x;
+    u32 k = 0;
+    if (i < n) key0[i] = k = rec[2 * i].x / XBUCKET;
+    hist_add(s_h, k, i < n, ho);
+  }
+  __syncthreads();
+  hist_flush(s_h, ho);
 }
 
-// rows of one axis pass: {key, center, length, global rank} of element perm[t]
-__global__ void __launch_bounds__(256) k_pack_axis_rows(const u32 *__restrict__ keys, const uint2 *__restrict__ cl, const u32 *__restrict__ perm,
-                                                        u32 n, u32 rank_off, u32 key_and, uint4 *__restrict__ rows) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const u32 i = perm[t];
-  const uint2 c = cl[i];
-  rows[t] = make_uint4(keys[i] & key_and, c.x, c.y, rank_off + i);
-}
-// ... and their arrival: keys[j], cl[j], grank[j] of row j
+// arrival of the rows of one axis pass: keys[j], cl[j], grank[j] of row j
 __global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restrict__ rows, u32 n, u32 *__restrict__ keys,
-                                                          uint2 *__restrict__ cl, u32 *__restrict__ grank) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const uint4 r = rows[j];
-  keys[j] = r.x;
-  cl[j] = make_uint2(r.y, r.z);
-  grank[j] = r.w;
+                                                          uint2 *__restrict__ cl, u32 *__restrict__ grank, HistOut ho) {
+  __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
+  hist_zero(s_h);
+  __syncthreads();
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 j = base + threadIdx.x;
+    u32 k = 0;
+    if (j < n) {
+      const uint4 r = rows[j];
+      keys[j] = k = r.x;
+      cl[j] = make_uint2(r.y, r.z);
+      grank[j] = r.w;
+    }
+    hist_add(s_h, k, j < n, ho);
+  }
+  __syncthreads();
+  hist_flush(s_h, ho);
 }
 
-// rows of the output exchange: {h, file index, identity bits, gid} of rank perm[t]
-__global__ void __launch_bounds__(256) k_pack_gid_rows(const uint4 *__restrict__ hfi_r, const u32 *__restrict__ gid_rank,
-                                                       const u32 *__restrict__ perm, u32 n, uint4 *__restrict__ rows) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const u32 i = perm[t];
-  uint4 v = hfi_r[i];
-  v.w = gid_rank[i];
-  rows[t] = v;
-}
-__global__ void __launch_bounds__(256) k_gid_keys(const uint4 *__restrict__ rows, u32 n, u32 gid_base, u32 *__restrict__ keys) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) keys[j] = rows[j].w - gid_base;
+__global__ void __launch_bounds__(256) k_gid_keys(const uint4 *__restrict__ rows, u32 n, u32 gid_base, u32 *__restrict__ keys, HistOut ho) {
+  __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
+  hist_zero(s_h);
+  __syncthreads();
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 j = base + threadIdx.x;
+    u32 k = 0;
+    if (j < n) keys[j] = k = rows[j].w - gid_base;
+    hist_add(s_h, k, j < n, ho);
+  }
+  __syncthreads();
+  hist_flush(s_h, ho);
 }
 
 // ---- owners: from indices of a rank's working list to global ranks ---------------------------------------------------
@@ -317,54 +431,59 @@ int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cu
   k_cuts_x<<<1, 64, 0, st>>>(cuts0, nr, g, link_x, cuts_x);
   return 1;
 }
-int dist_route(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *dest, u32 *counts, cudaStream_t st) {
-  cudaMemsetAsync(counts, 0, (nr + 1) * sizeof(u32), st);
+u64 dist_split_work_bytes(u64 n) { return ((n + SPLIT_TILE - 1) / SPLIT_TILE + 1) * NRP * 4; }
+
+template <int MODE, class Pay>
+static int split_pack(const RouteArgs &a, u32 *tile_cnt, u32 *counts, const Pay &pay, u32 *perm, cudaStream_t st) {
+  cudaMemsetAsync(counts, 0, (a.nr + 1) * sizeof(u32), st);
+  if (a.n == 0) return 0;
+  const u32 tiles = (a.n + SPLIT_TILE - 1) / SPLIT_TILE;
+  KScope ks(KID_DIST_ROWS, st, a.n);
+  k_route_count<MODE><<<tiles, 256, 0, st>>>(a, tile_cnt, counts);
+  k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, counts);
+  k_split_pack<MODE, Pay><<<tiles, 256, 0, st>>>(a, tile_cnt, pay, perm);
+  return 3;
+}
+// exchange 1: local records (file order) -> send buffer ordered by destination; counts[nr] = dropped records
+int dist_split_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *out, u32 *tile_cnt,
+                       u32 *counts, cudaStream_t st) {
+  return split_pack<0>(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu}, tile_cnt, counts, PayRec32{rec, out}, nullptr, st);
+}
+// X halo: the fragments whose X super-bucket belongs to another rank; perm[t] = local rank of the t-th row sent
+int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 rank_off, uint4 *out,
+                    u32 out_cap, u32 *perm, u32 *tile_cnt, u32 *counts, cudaStream_t st) {
+  return split_pack<1>(RouteArgs{keys2, n, cuts_x, nr, me, 0xFFFFFFFFu, nbx, out_cap}, tile_cnt, counts,
+                       PayAxisRow{keys2, cl, rank_off, 0xFFFFFFFEu, out}, perm, st);
+}
+// Y pass: every fragment to the owner of its Y super-bucket range
+int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, int nr, u32 rank_off, uint4 *out, u32 *perm,
+                    u32 *tile_cnt, u32 *counts, cudaStream_t st) {
+  return split_pack<0>(RouteArgs{keys, n, cuts, nr, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu}, tile_cnt, counts,
+                       PayAxisRow{keys, cl, rank_off, 0xFFFFFFFFu, out}, perm, st);
+}
+// output exchange: every fragment to the owner of its group-id range
+int dist_split_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *out, u32 *tile_cnt, u32 *counts,
+                   cudaStream_t st) {
+  return split_pack<0>(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu}, tile_cnt, counts, PayGidRow{hfi_r, gid_rank, out}, nullptr, st);
+}
+static unsigned hist_grid(u64 n) {  // few CTAs: few histogram flushes
+  const unsigned b = blocks_for(n), cap = (unsigned)sm_count() * 8;
+  return b > cap ? cap : b;
+}
+int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
-  unsigned b = blocks_for(n, 256 * 4);
-  const unsigned cap = (unsigned)sm_count() * 8;
-  k_route<0><<<b > cap ? cap : b, 256, 0, st>>>(keys, n, cuts, nr, drop_key, 0, 0, dest, counts);
+  k_key0_of_rec<<<hist_grid(n), 256, 0, st>>>(rec, n, key0, ho);
   return 1;
 }
-int dist_route_x(const u32 *keys2, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 *dest, u32 *counts, cudaStream_t st) {
-  cudaMemsetAsync(counts, 0, (nr + 1) * sizeof(u32), st);
-  if (n == 0) return 0;
-  unsigned b = blocks_for(n, 256 * 4);
-  const unsigned cap = (unsigned)sm_count() * 8;
-  k_route<1><<<b > cap ? cap : b, 256, 0, st>>>(keys2, n, cuts_x, nr, 0xFFFFFFFFu, nbx, me, dest, counts);
-  return 1;
-}
-int dist_gather_rec32(const uint4 *rec, const u32 *perm, u32 n, uint4 *out, cudaStream_t st) {
+int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
   KScope ks(KID_DIST_ROWS, st, n);
-  k_gather_rec32<<<blocks_for(n), 256, 0, st>>>(rec, perm, n, out);
+  k_unpack_axis_rows<<<hist_grid(n), 256, 0, st>>>(rows, n, keys, cl, grank, ho);
   return 1;
 }
-int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, cudaStream_t st) {
+int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
-  k_key0_of_rec<<<blocks_for(n), 256, 0, st>>>(rec, n, key0);
-  return 1;
-}
-int dist_pack_axis_rows(const u32 *keys, const uint2 *cl, const u32 *perm, u32 n, u32 rank_off, u32 key_and, uint4 *rows, cudaStream_t st) {
-  if (n == 0) return 0;
-  KScope ks(KID_DIST_ROWS, st, n);
-  k_pack_axis_rows<<<blocks_for(n), 256, 0, st>>>(keys, cl, perm, n, rank_off, key_and, rows);
-  return 1;
-}
-int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, cudaStream_t st) {
-  if (n == 0) return 0;
-  KScope ks(KID_DIST_ROWS, st, n);
-  k_unpack_axis_rows<<<blocks_for(n), 256, 0, st>>>(rows, n, keys, cl, grank);
-  return 1;
-}
-int dist_pack_gid_rows(const uint4 *hfi_r, const u32 *gid_rank, const u32 *perm, u32 n, uint4 *rows, cudaStream_t st) {
-  if (n == 0) return 0;
-  KScope ks(KID_DIST_ROWS, st, n);
-  k_pack_gid_rows<<<blocks_for(n), 256, 0, st>>>(hfi_r, gid_rank, perm, n, rows);
-  return 1;
-}
-int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, cudaStream_t st) {
-  if (n == 0) return 0;
-  k_gid_keys<<<blocks_for(n), 256, 0, st>>>(rows, n, gid_base, keys);
+  k_gid_keys<<<hist_grid(n), 256, 0, st>>>(rows, n, gid_base, keys, ho);
   return 1;
 }
 int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, u32 *halo_res, cudaStream_t st) {

@@ -102,9 +102,16 @@ struct Transport {
   virtual int gather_small(const u32 *d_row, u32 *d_all, u32 *h_all, cudaStream_t st) = 0;
   // recv[world][bytes] <- every rank's send[bytes]; stream-ordered; doubles as a barrier between the ranks' streams
   virtual int all_gather(const void *send, void *recv, size_t bytes, cudaStream_t st) = 0;
-  // variable all-to-all; offsets and counts in elements of `elem` bytes
+  // variable all-to-all; offsets and counts in elements of `elem` bytes.  poff[p] = where this rank's block starts in
+  // rank p's receive buffer (used by the transports that write into the peer's memory).
   virtual int all_to_all(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt,
-                         size_t elem, cudaStream_t st) = 0;
+                         const u64 *poff, size_t elem, cudaStream_t st) = 0;
+  // peer memory: every rank's partition arena has the same layout, so a local pointer translates to any peer's copy
+  const u8 *my_base = nullptr;
+  u8 *peer_base[DIST_MAX_RANKS] = {nullptr};
+  bool peers_mapped = false;
+  template <class T>
+  T *on_peer(int p, T *local) const { return (T *)(peer_base[p] + ((const u8 *)local - my_base)); }
 };
 
 struct NcclTransport : Transport {
@@ -133,9 +140,26 @@ struct NcclTransport : Transport {
     bytes_sent += bytes * (u64)(world - 1);
     return check(nccl_api().AllGather(send, recv, bytes, ncclUint8, comm, st), "ncclAllGather");
   }
-  int all_to_all(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt, size_t elem,
-                 cudaStream_t st) override {
+  // Bulk rows do not go through NCCL's send/recv kernels: every rank PUSHES its blocks into the peers' receive buffers
+  // with copy-engine peer copies over NVLink (the arenas are mapped into each other: cudaIpc between processes), peers
+  // in staggered order so that no receiver is hit by everybody at once; a 4-byte ncclAllGather behind the copies is the
+  // barrier that tells a rank that all blocks addressed to it have landed.
+  int all_to_all(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt,
+                 const u64 *poff, size_t elem, cudaStream_t st) override {
     const NcclApi &N = nccl_api();
+    if (peers_mapped && !getenv_nccl_rows()) {
+      for (int k = 0; k < world; ++k) {
+        const int p = (rank + k) % world;
+        if (!scnt[p]) continue;
+        u8 *dst = (p == rank ? (u8 *)recv : on_peer(p, (u8 *)recv)) + poff[p] * elem;
+        if (cudaMemcpyAsync(dst, (const u8 *)send + soff[p] * elem, scnt[p] * elem, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+          err = std::string("all_to_all: peer copy failed: ") + cudaGetErrorString(cudaGetLastError());
+          return RK_ERR_CUDA;
+        }
+        if (p != rank) bytes_sent += scnt[p] * elem;
+      }
+      return check(N.AllGather(d_flag, d_flag_all, 4, ncclUint8, comm, st), "ncclAllGather (barrier)");
+    }
     if (scnt[rank]) {
       if (cudaMemcpyAsync((u8 *)recv + roff[rank] * elem, (const u8 *)send + soff[rank] * elem, scnt[rank] * elem,
                           cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
@@ -154,6 +178,11 @@ struct NcclTransport : Transport {
     }
     const int rc2 = check(N.GroupEnd(), "ncclGroupEnd");
     return rc ? rc : rc2;
+  }
+  u32 *d_flag = nullptr, *d_flag_all = nullptr;  // barrier payload (set by the owner of the transport)
+  static bool getenv_nccl_rows() {  // RK_DIST_NCCL_ROWS=1: rows through ncclSend/ncclRecv (tuning reference)
+    static const bool v = getenv("RK_DIST_NCCL_ROWS") != nullptr;
+    return v;
   }
 };
 
@@ -208,8 +237,8 @@ struct LocalTransport : Transport {
     bytes_sent += bytes * (u64)(world - 1);
     return cuda(e, "all_gather");
   }
-  int all_to_all(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt, size_t elem,
-                 cudaStream_t st) override {
+  int all_to_all(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt, const u64 *,
+                 size_t elem, cudaStream_t st) override {
     cudaError_t e = cudaStreamSynchronize(st);
     g->ptr[rank] = send;
     for (int p = 0; p < world; ++p) g->soff[rank][p] = soff[p], g->scnt[rank][p] = scnt[p];
@@ -235,8 +264,55 @@ struct LocalTransport : Transport {
 // ---------------------------------------------------------------------------------------------------------------------
 // per-rank state
 // ---------------------------------------------------------------------------------------------------------------------
+// RK_DIST_TRACE=1: CUDA-event pairs around every transport call and the sections between them, printed per rank after
+// the final synchronisation of rk_dist_group (a tuning aid: where a step spends its time)
+struct Trace {
+  bool on = false;
+  struct Rec { const char *what; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void begin(const char *what, cudaStream_t st) {
+    if (!on) return;
+    Rec r{what, get(), get()};
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (on && !recs.empty()) cudaEventRecord(recs.back().b, st);
+  }
+  void dump(int rank) {
+    if (!on) return;
+    std::string line = "[rk_dist rank " + std::to_string(rank) + "]";
+    float total = 0.f;
+    for (auto &r : recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) cudaGetLastError();
+      // label: the transport function and its first argument, e.g. all_to_all(D.send_rows
+      std::string w(r.what);
+      const size_t p0 = w.find("->"), p1 = w.find(',');
+      w = w.substr(p0 == std::string::npos ? 0 : p0 + 2, p1 == std::string::npos ? std::string::npos : p1 - (p0 == std::string::npos ? 0 : p0 + 2));
+      char buf[160];
+      snprintf(buf, sizeof buf, " %s)=%.3f", w.c_str(), ms);
+      line += buf;
+      total += ms;
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+    fprintf(stderr, "%s | comm total %.3f ms\n", line.c_str(), total);
+  }
+};
+
 struct Exchange {  // counts of one variable all-to-all, as this rank sees it (elements)
   u64 soff[DIST_MAX_RANKS], scnt[DIST_MAX_RANKS], roff[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
+  u64 poff[DIST_MAX_RANKS];   // forward: start of my block in rank p's receive buffer (= p's roff[me])
+  u64 rpoff[DIST_MAX_RANKS];  // the way back: start of my block in rank p's send-order buffer (= p's soff[me])
   u64 n_send = 0, n_recv = 0;
   // from the gathered count matrix: row s = what rank s sends to every destination
   void from_matrix(const u32 *h_all, int word0, int nr, int me) {
@@ -250,6 +326,12 @@ struct Exchange {  // counts of one variable all-to-all, as this rank sees it (e
       roff[s] = n_recv;
       rcnt[s] = h_all[(size_t)s * SMALL_WORDS + word0 + me];
       n_recv += rcnt[s];
+    }
+    for (int p = 0; p < nr; ++p) {
+      u64 f = 0, r = 0;
+      for (int s = 0; s < me; ++s) f += h_all[(size_t)s * SMALL_WORDS + word0 + p];
+      for (int d = 0; d < me; ++d) r += h_all[(size_t)p * SMALL_WORDS + word0 + d];
+      poff[p] = f, rpoff[p] = r;
     }
   }
 };
@@ -266,11 +348,11 @@ struct Dist {
   Transport *tr = nullptr;
   u64 cap = 0, hcap = 0;
   void *arena = nullptr;
-  void *shared = nullptr;  // [parent cap][gidscan cap], mapped by the peers
   void *peer_open[DIST_MAX_RANKS] = {nullptr};
   bool peers_ready = false;
   u32 *h_small = nullptr;  // pinned [world][SMALL_WORDS]
   PeerTable pt{};
+  Trace trace;
   // grow-only side buffers whose size depends on the input, not on cap
   u8 *aos_buf = nullptr;
   u64 aos_bytes = 0;
@@ -292,9 +374,10 @@ struct Dist {
   // carved device pointers
   Counters *cnt = nullptr;
   u32 *d_small = nullptr, *d_small_all = nullptr, *nroots_all = nullptr, *nroots_all2 = nullptr;
+  u32 *prehist = nullptr;  // 4 x [4][256]: digit counts of the rank / X / Y / gid sort keys, gathered by their producers
   u32 *hist = nullptr, *hist_all = nullptr, *cuts0 = nullptr, *cuts_y = nullptr, *cuts_x = nullptr, *cuts_g = nullptr;
   uint4 *rec4_loc = nullptr, *send_rows = nullptr, *rec4_arr = nullptr, *recv_rows = nullptr;
-  u32 *key0_loc = nullptr, *dest = nullptr, *sdest = nullptr, *perm0 = nullptr, *perm_x = nullptr, *perm_y = nullptr, *perm_g = nullptr;
+  u32 *key0_loc = nullptr, *tile_cnt = nullptr, *perm_x = nullptr, *perm_y = nullptr;
   u32 *key0a = nullptr, *k0_r = nullptr, *aidx_r = nullptr, *tmp_k = nullptr, *tmp_v = nullptr;
   void *sort_work = nullptr;
   uint2 *xl = nullptr, *yl_r = nullptr, *yl_a = nullptr;
@@ -308,7 +391,7 @@ struct Dist {
   u8 *xm_send = nullptr, *xm_a = nullptr;
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr, *worklist = nullptr;
   u32 work_cap = 0;
-  u32 *gid_rank = nullptr;
+  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr;
   void *scan_work = nullptr;
   u32 *gid_a = nullptr, *sgid = nullptr, *srank_g = nullptr;
   void *order_scratch = nullptr;
@@ -331,6 +414,7 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.d_small_all = (u32 *)take((u64)nr * SMALL_WORDS * 4);
   D.nroots_all = (u32 *)take(DIST_MAX_RANKS * 4);
   D.nroots_all2 = (u32 *)take(DIST_MAX_RANKS * 4);
+  D.prehist = (u32 *)take(4 * 4 * 256 * 4);
   D.hist = (u32 *)take(DIST_BINS * 4);
   D.hist_all = (u32 *)take((u64)nr * DIST_BINS * 4);
   D.cuts0 = (u32 *)take((DIST_MAX_RANKS + 1) * 4);
@@ -342,12 +426,9 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.rec4_arr = (uint4 *)take(M * 32);
   D.recv_rows = (uint4 *)take(M * 16);
   D.key0_loc = (u32 *)take(M * 4);
-  D.dest = (u32 *)take(M * 4);
-  D.sdest = (u32 *)take(M * 4);
-  D.perm0 = (u32 *)take(M * 4);
-  D.perm_x = (u32 *)take(M * 4);
+  D.tile_cnt = (u32 *)take(dist_split_work_bytes(M));
+  D.perm_x = (u32 *)take(H * 4);
   D.perm_y = (u32 *)take(M * 4);
-  D.perm_g = (u32 *)take(M * 4);
   D.key0a = (u32 *)take(M * 4);
   D.k0_r = (u32 *)take(M * 4);
   D.aidx_r = (u32 *)take(M * 4);
@@ -376,6 +457,10 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.ry_a = (u32 *)take(M * 4);
   D.parent_x = (u32 *)take(MC * 4);
   D.xm_bits = (u32 *)take((MC + 31) / 32 * 4);
+  D.parent = (u32 *)take(M * 4);
+  D.gidscan = (u32 *)take(M * 4);
+  D.flag = (u32 *)take(16);
+  D.flag_all = (u32 *)take(DIST_MAX_RANKS * 4);
   D.parent_y = (u32 *)take(M * 4);
   D.yo_a = (u32 *)take(M * 4);
   D.yo_s = (u32 *)take(M * 4);
@@ -406,8 +491,8 @@ static void dist_release_buffers(Dist &D) {
   }
   D.peers_ready = false;
   if (D.arena) cudaFree(D.arena);
-  if (D.shared) cudaFree(D.shared);
-  D.arena = D.shared = nullptr;
+  D.arena = nullptr;
+  if (D.tr) D.tr->peers_mapped = false;
   D.cap = D.hcap = 0;
   D.loaded = false;
 }
@@ -424,24 +509,23 @@ static int dist_allocate(rk_ctx *ctx, u64 cap) {
   D.hcap = cap / 8 + 65536;
   const u64 need = dist_carve(D, nullptr);
   cudaError_t e = cudaMalloc(&D.arena, need);
-  if (e == cudaSuccess) e = cudaMalloc(&D.shared, cap * 8);
   if (e != cudaSuccess) {
     cudaGetLastError();
     dist_release_buffers(D);
-    return fail(ctx, RK_ERR_NOMEM, "cudaMalloc(%llu bytes for %llu rows per rank): %s", (unsigned long long)(need + cap * 8),
+    return fail(ctx, RK_ERR_NOMEM, "cudaMalloc(%llu bytes for %llu rows per rank): %s", (unsigned long long)need,
                 (unsigned long long)cap, cudaGetErrorString(e));
   }
   dist_carve(D, (u8 *)D.arena);
-  D.parent = (u32 *)D.shared;
-  D.gidscan = D.parent + cap;
   return RK_OK;
 }
 
 static int tr_fail(rk_ctx *ctx, int rc) { return fail(ctx, rc, "%s", ctx->dist->tr->err.c_str()); }
-#define TR(call)                           \
-  do {                                     \
-    const int rc_ = (call);                \
-    if (rc_ != RK_OK) return tr_fail(ctx, rc_); \
+#define TR(call)                                  \
+  do {                                            \
+    D.trace.begin(#call, ctx->stream);            \
+    const int rc_ = (call);                       \
+    D.trace.end(ctx->stream);                     \
+    if (rc_ != RK_OK) return tr_fail(ctx, rc_);   \
   } while (0)
 
 static int dist_init_common(rk_ctx *ctx, int rank, int world, Transport *tr, u64 cap) {
@@ -454,6 +538,7 @@ static int dist_init_common(rk_ctx *ctx, int rank, int world, Transport *tr, u64
   D->rank = rank, D->world = world, D->tr = tr;
   tr->rank = rank, tr->world = world;
   ctx->dist = D;
+  D->trace.on = getenv("RK_DIST_TRACE") != nullptr;
   CK(cudaSetDevice(ctx->device));
   CK(cudaHostAlloc((void **)&D->h_small, (size_t)world * SMALL_WORDS * sizeof(u32), cudaHostAllocDefault));
   return dist_allocate(ctx, cap);
@@ -462,9 +547,9 @@ static int dist_init_common(rk_ctx *ctx, int rank, int world, Transport *tr, u64
 static int dist_export(rk_ctx *ctx, DistBlob *b) {
   Dist &D = *ctx->dist;
   memset(b, 0, sizeof *b);
-  b->pid = (u64)getpid(), b->ptr = (u64)(uintptr_t)D.shared, b->cap = D.cap, b->device = ctx->device;
+  b->pid = (u64)getpid(), b->ptr = (u64)(uintptr_t)D.arena, b->cap = D.cap, b->device = ctx->device;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaIpcGetMemHandle(&b->handle, D.shared));
+  CK(cudaIpcGetMemHandle(&b->handle, D.arena));
   return RK_OK;
 }
 
@@ -476,11 +561,11 @@ static int dist_import(rk_ctx *ctx, const u8 *blobs, size_t stride) {
     memcpy(&b, blobs + (size_t)r * stride, sizeof b);
     if (b.cap != D.cap) return fail(ctx, RK_ERR_ARG, "rank %d was initialised with capacity %llu, this rank with %llu", r,
                                     (unsigned long long)b.cap, (unsigned long long)D.cap);
-    u32 *base = nullptr;
+    u8 *base = nullptr;
     if (r == D.rank) {
-      base = (u32 *)D.shared;
+      base = (u8 *)D.arena;
     } else if (b.pid == (u64)getpid()) {
-      base = (u32 *)(uintptr_t)b.ptr;
+      base = (u8 *)(uintptr_t)b.ptr;
       if (b.device != ctx->device) {
         const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
@@ -493,15 +578,18 @@ static int dist_import(rk_ctx *ctx, const u8 *blobs, size_t stride) {
       CK(cudaIpcOpenMemHandle((void **)&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
       D.peer_open[r] = base;
     }
-    D.pt.parent[r] = base;
-    D.pt.gidscan[r] = base + D.cap;
+    D.tr->peer_base[r] = base;
+    // the arenas are carved identically (same capacity, same number of ranks): local offsets hold on every peer
+    D.pt.parent[r] = (const u32 *)(base + ((const u8 *)D.parent - (const u8 *)D.arena));
+    D.pt.gidscan[r] = (const u32 *)(base + ((const u8 *)D.gidscan - (const u8 *)D.arena));
   }
+  D.tr->my_base = (const u8 *)D.arena;
+  D.tr->peers_mapped = true;
+  if (NcclTransport *nt = dynamic_cast<NcclTransport *>(D.tr)) nt->d_flag = D.flag, nt->d_flag_all = D.flag_all;
   D.pt.nr = D.world, D.pt.me = D.rank;
   D.peers_ready = true;
   return RK_OK;
 }
-
-static int sort_bits_for_ranks(int nr) { return ceil_log2((u64)nr + 1) < 1 ? 1 : ceil_log2((u64)nr + 1); }
 
 // error words of all ranks after a count exchange: every rank sees the same matrix, so every rank returns together
 static int dist_check_small(rk_ctx *ctx, bool range_errors) {
@@ -586,7 +674,9 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   // K1 on the local slice of the file
   CK(cudaMemsetAsync(D.cnt, 0, sizeof(Counters), st));
   CK(cudaMemsetAsync(D.d_small, 0, SMALL_WORDS * 4, st));
+  CK(cudaMemsetAsync(D.prehist, 0, 3 * 4 * 256 * 4, st));
   CK(cudaMemsetAsync(linkx_loc, 0, (lxw + lyw) * 4, st));
+  auto hist_of = [&](int which, int bits) { return HistOut{D.prehist + which * 1024, (bits + 7) / 8, bits}; };
   if (too_many) {
     const u32 e = ERR_WORKLIST;  // reported below as a capacity error
     CK(cudaMemcpyAsync(&D.cnt->err, &e, 4, cudaMemcpyHostToDevice, st));
@@ -595,12 +685,10 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
                             &D.cnt->n_dropped, &D.cnt->err, st, D.rec4_loc, HistOut{nullptr, 0, 0}, (u32)file_off);
   // exchange 1: to the owner of the xStart/10 range
   const int shift0 = D.bits_rank > 12 ? D.bits_rank - 12 : 0;
-  const int rbits = sort_bits_for_ranks(nr);
   launches += dist_coarse_hist(D.key0_loc, (u32)n_use, shift0, 0, g.vsize - 1, D.hist, st);
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
   launches += dist_cuts_from_hist(D.hist_all, nr, shift0, D.cuts0, st);
-  launches += dist_route(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.dest, D.d_small + W_CNT_A, st);
-  launches += launch_sort_pairs(D.dest, nullptr, D.sdest, D.perm0, D.tmp_k, D.tmp_v, n_use, rbits, D.sort_work, st, &D.cnt->err);
+  launches += dist_split_records(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.rec4_loc, D.send_rows, D.tile_cnt, D.d_small + W_CNT_A, st);
   {
     const int rc = dist_gather_counts(ctx);  // host sync 1
     if (rc) return rc;
@@ -633,12 +721,12 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   const u32 m = (u32)m_of[me];
   D.m_loc = m;
 
-  launches += dist_gather_rec32(D.rec4_loc, D.perm0, (u32)D.ex1.n_send, D.send_rows, st);
-  TR(D.tr->all_to_all(D.send_rows, D.ex1.soff, D.ex1.scnt, D.rec4_arr, D.ex1.roff, D.ex1.rcnt, 32, st));
+  TR(D.tr->all_to_all(D.send_rows, D.ex1.soff, D.ex1.scnt, D.rec4_arr, D.ex1.roff, D.ex1.rcnt, D.ex1.poff, 32, st));
   CK(cudaEventRecord(ev[2], st));
   // processing order: sources arrive in file order, so a stable sort by xStart/10 is the global order
-  launches += dist_key0_of_rec(D.rec4_arr, m, D.key0a, st);
-  launches += launch_sort_pairs(D.key0a, nullptr, D.k0_r, D.aidx_r, D.tmp_k, D.tmp_v, m, D.bits_rank, D.sort_work, st, &D.cnt->err);
+  launches += dist_key0_of_rec(D.rec4_arr, m, D.key0a, hist_of(0, D.bits_rank), st);
+  launches += launch_sort_pairs(D.key0a, nullptr, D.k0_r, D.aidx_r, D.tmp_k, D.tmp_v, m, D.bits_rank, D.sort_work, st, &D.cnt->err,
+                                m ? D.prehist : nullptr);
   CK(cudaEventRecord(ev[3], st));
   // link maps: OR over the ranks, so that a run of linked buckets has one key everywhere
   TR(D.tr->all_gather(linkx_loc, link_all, lxw * 4, st));
@@ -646,20 +734,19 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   TR(D.tr->all_gather(linky_loc, link_all, lyw * 4, st));
   launches += dist_or_rows(link_all, nr, lyw, linky, st);
   launches += launch_keys(D.aidx_r, m, g, D.rec4_arr, linkx, linky, D.xl, D.yl_r, D.ys_r, D.kx2, D.ky, D.identity_r, st,
-                          HistOut{nullptr, 0, 0}, HistOut{nullptr, 0, 0}, D.gfidx_r, 1u);
+                          hist_of(1, D.bits_x + 1), HistOut{nullptr, 0, 0}, D.gfidx_r, 1u);
   launches += launch_hkey(D.k0_r, D.ys_r, m, nullptr, st, D.gfidx_r, D.identity_r, D.hfi_r);
   CK(cudaEventRecord(ev[4], st));
   // X halo: fragments whose X super-bucket belongs to a higher rank
   launches += dist_cuts_x(D.cuts0, nr, g, linkx, D.cuts_x, st);
-  launches += dist_route_x(D.kx2, m, D.cuts_x, nr, g.nbx, me, D.dest, D.d_small + W_CNT_A, st);
-  launches += launch_sort_pairs(D.dest, nullptr, D.sdest, D.perm_x, D.tmp_k, D.tmp_v, m, rbits, D.sort_work, st, &D.cnt->err);
+  launches += dist_split_halo(D.kx2, D.xl, m, D.cuts_x, nr, g.nbx, me, D.rank_off, D.halo_send, (u32)D.hcap, D.perm_x, D.tile_cnt,
+                              D.d_small + W_CNT_A, st);
   // Y: to the owner of the Y super-bucket range
   const int shift_y = D.bits_y > 12 ? D.bits_y - 12 : 0;
   launches += dist_coarse_hist(D.ky, m, shift_y, 0, 0xFFFFFFFFu, D.hist, st);
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
   launches += dist_cuts_from_hist(D.hist_all, nr, shift_y, D.cuts_y, st);
-  launches += dist_route(D.ky, m, D.cuts_y, nr, 0xFFFFFFFFu, D.dest, D.d_small + W_CNT_B, st);
-  launches += launch_sort_pairs(D.dest, nullptr, D.sdest, D.perm_y, D.tmp_k, D.tmp_v, m, rbits, D.sort_work, st, &D.cnt->err);
+  launches += dist_split_axis(D.ky, D.yl_r, m, D.cuts_y, nr, D.rank_off, D.send_rows, D.perm_y, D.tile_cnt, D.d_small + W_CNT_B, st);
   {
     const int rc = dist_gather_counts(ctx);  // host sync 2
     if (rc) return rc;
@@ -683,16 +770,16 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   }
   D.n_away = (u32)D.exh.n_send, D.n_halo = (u32)D.exh.n_recv, D.m_y = (u32)D.exy.n_recv;
 
-  launches += dist_pack_axis_rows(D.kx2, D.xl, D.perm_x, D.n_away, D.rank_off, 0xFFFFFFFEu, D.halo_send, st);
-  TR(D.tr->all_to_all(D.halo_send, D.exh.soff, D.exh.scnt, D.halo_recv, D.exh.roff, D.exh.rcnt, 16, st));
-  launches += dist_unpack_axis_rows(D.halo_recv, D.n_halo, D.kx2 + m, D.xl + m, D.halo_grank, st);
+  TR(D.tr->all_to_all(D.halo_send, D.exh.soff, D.exh.scnt, D.halo_recv, D.exh.roff, D.exh.rcnt, D.exh.poff, 16, st));
+  launches += dist_unpack_axis_rows(D.halo_recv, D.n_halo, D.kx2 + m, D.xl + m, D.halo_grank, hist_of(1, D.bits_x + 1), st);
   CK(cudaEventRecord(ev[5], st));
-  launches += launch_sort_pairs(D.kx2, nullptr, D.skx, D.rx, D.tmp_k, D.tmp_v, (u64)m + D.n_halo, D.bits_x + 1, D.sort_work, st, &D.cnt->err);
+  launches += launch_sort_pairs(D.kx2, nullptr, D.skx, D.rx, D.tmp_k, D.tmp_v, (u64)m + D.n_halo, D.bits_x + 1, D.sort_work, st, &D.cnt->err,
+                                (m + D.n_halo) ? D.prehist + 1024 : nullptr);
   CK(cudaEventRecord(ev[6], st));
-  launches += dist_pack_axis_rows(D.ky, D.yl_r, D.perm_y, m, D.rank_off, 0xFFFFFFFFu, D.send_rows, st);
-  TR(D.tr->all_to_all(D.send_rows, D.exy.soff, D.exy.scnt, D.recv_rows, D.exy.roff, D.exy.rcnt, 16, st));
-  launches += dist_unpack_axis_rows(D.recv_rows, D.m_y, D.ky_a, D.yl_a, D.grank_a, st);
-  launches += launch_sort_pairs(D.ky_a, nullptr, D.sky_a, D.ry_a, D.tmp_k, D.tmp_v, D.m_y, D.bits_y, D.sort_work, st, &D.cnt->err);
+  TR(D.tr->all_to_all(D.send_rows, D.exy.soff, D.exy.scnt, D.recv_rows, D.exy.roff, D.exy.rcnt, D.exy.poff, 16, st));
+  launches += dist_unpack_axis_rows(D.recv_rows, D.m_y, D.ky_a, D.yl_a, D.grank_a, hist_of(2, D.bits_y), st);
+  launches += launch_sort_pairs(D.ky_a, nullptr, D.sky_a, D.ry_a, D.tmp_k, D.tmp_v, D.m_y, D.bits_y, D.sort_work, st, &D.cnt->err,
+                                D.m_y ? D.prehist + 2048 : nullptr);
   CK(cudaEventRecord(ev[7], st));
   D.loaded = true;
 
@@ -745,31 +832,31 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   mx.key_shift = 1;
   launches += launch_match(mx, st);
   launches += dist_x_owners(D.parent_x, m, nh, D.rank_off, D.halo_grank, D.parent, D.halo_res, st);
-  TR(D.tr->all_to_all(D.halo_res, D.exh.roff, D.exh.rcnt, D.away_res, D.exh.soff, D.exh.scnt, 4, st));
+  TR(D.tr->all_to_all(D.halo_res, D.exh.roff, D.exh.rcnt, D.away_res, D.exh.soff, D.exh.scnt, D.exh.rpoff, 4, st));
   launches += dist_apply_away(D.away_res, D.perm_x, D.n_away, D.parent, st);
   CK(cudaEventRecord(ev[1], st));
   // Y pass on the owners of the Y ranges: X-matched fragments insert without a query (commonFunctions.cpp:59)
   launches += dist_pack_xm(D.parent, D.perm_y, m, D.xm_send, st);
-  TR(D.tr->all_to_all(D.xm_send, D.exy.soff, D.exy.scnt, D.xm_a, D.exy.roff, D.exy.rcnt, 1, st));
+  TR(D.tr->all_to_all(D.xm_send, D.exy.soff, D.exy.scnt, D.xm_a, D.exy.roff, D.exy.rcnt, D.exy.poff, 1, st));
   if (D.m_y) CK(cudaMemsetAsync(D.parent_y, 0xFF, (size_t)D.m_y * 4, st));
   MatchArgs my = mx;
   my.skey = D.sky_a, my.srank = D.ry_a, my.cl_r = D.yl_a, my.parent = D.parent_y, my.m = D.m_y, my.max_index = D.g.my, my.is_y = 1;
   my.work_count = D.cnt->work_y, my.key_shift = 0, my.xm_bytes = D.xm_a;
   launches += launch_match(my, st);
   launches += dist_y_owners(D.parent_y, D.grank_a, D.m_y, D.yo_a, st);
-  TR(D.tr->all_to_all(D.yo_a, D.exy.roff, D.exy.rcnt, D.yo_s, D.exy.soff, D.exy.scnt, 4, st));
+  TR(D.tr->all_to_all(D.yo_a, D.exy.roff, D.exy.rcnt, D.yo_s, D.exy.soff, D.exy.scnt, D.exy.rpoff, 4, st));
   launches += dist_merge_y(D.yo_s, D.perm_y, m, D.parent, st);
   CK(cudaEventRecord(ev[2], st));
   // forest: roots per rank, then every chain is followed to its root through the peers' parent arrays
   launches += dist_root_scan(D.parent, m, D.gidscan, D.d_small + W_X0, D.scan_work, st);
   TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's parent and root scan are final)
   launches += dist_chase_peers(D.pt, D.nroots_all, m, D.gid_rank, st);
-  TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all2, 4, st));  // nobody rewrites parent[] while a peer still reads it
+  // (no second barrier: the count exchange of the output stage below completes on a rank only after every rank has
+  // entered it, i.e. finished chasing, and parent[] is not written again before the next rk_dist_group)
   CK(cudaEventRecord(ev[3], st));
   // output exchange: to the owner of the group-id range
   launches += dist_cuts_gid(D.nroots_all, nr, D.cuts_g, D.d_small + W_X1, st);
-  launches += dist_route(D.gid_rank, m, D.cuts_g, nr, 0xFFFFFFFFu, D.dest, D.d_small + W_CNT_A, st);
-  launches += launch_sort_pairs(D.dest, nullptr, D.sdest, D.perm_g, D.tmp_k, D.tmp_v, m, sort_bits_for_ranks(nr), D.sort_work, st, &D.cnt->err);
+  launches += dist_split_gid(D.gid_rank, D.hfi_r, m, D.cuts_g, nr, D.send_rows, D.tile_cnt, D.d_small + W_CNT_A, st);
   {
     const int rc = dist_gather_counts(ctx);  // host sync 3
     if (rc) return rc;
@@ -791,12 +878,13 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   const u32 gid_base = (u32)(total_groups * (u64)me / (u64)nr);
   const u64 local_groups = total_groups * (u64)(me + 1) / (u64)nr - gid_base;
   const int bits_g = ceil_log2(local_groups) < 1 ? 1 : ceil_log2(local_groups);
-  launches += dist_pack_gid_rows(D.hfi_r, D.gid_rank, D.perm_g, m, D.send_rows, st);
-  TR(D.tr->all_to_all(D.send_rows, exg.soff, exg.scnt, D.recv_rows, exg.roff, exg.rcnt, 16, st));
-  launches += dist_gid_keys(D.recv_rows, mg, gid_base, D.gid_a, st);
+  TR(D.tr->all_to_all(D.send_rows, exg.soff, exg.scnt, D.recv_rows, exg.roff, exg.rcnt, exg.poff, 16, st));
+  CK(cudaMemsetAsync(D.prehist + 3072, 0, 4 * 256 * 4, st));
+  launches += dist_gid_keys(D.recv_rows, mg, gid_base, D.gid_a, HistOut{D.prehist + 3072, (bits_g + 7) / 8, bits_g}, st);
   CK(cudaEventRecord(ev[4], st));
   // members arrive in processing order (sources in rank order): a stable sort by group id is push_back order
-  launches += launch_sort_pairs(D.gid_a, nullptr, D.sgid, D.srank_g, D.tmp_k, D.tmp_v, mg, bits_g, D.sort_work, st, &D.cnt->err);
+  launches += launch_sort_pairs(D.gid_a, nullptr, D.sgid, D.srank_g, D.tmp_k, D.tmp_v, mg, bits_g, D.sort_work, st, &D.cnt->err,
+                                mg ? D.prehist + 3072 : nullptr);
   OrderArgs oa{};
   oa.sgid = D.sgid, oa.srank = D.srank_g, oa.hfi_r = D.recv_rows;
   oa.m = mg, oa.do_sort = (flags & RK_F_NO_SORT) ? 0 : 1, oa.gid_base = gid_base;
@@ -835,6 +923,7 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
+  D.trace.dump(me);
 
   out->n_kept = mg;
   out->n_groups = total_groups;
