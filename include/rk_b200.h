@@ -112,6 +112,25 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
  * rk_group with RK_F_NO_SORT, orders the members of every group on the device and returns the result again. */
 int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out);
 
+/* Replaces sort_groups (src/commonFunctions.cpp:148-159) as the PURE function the reference has: perm[j] = index (into
+ * the member arrays handed in) of the member that std::sort leaves at position j, for m members given group by group
+ * (gid nondecreasing), y[j] = yStart and d[j] = diag_func[xStart/10] of member j (host arrays).  Nothing of an earlier
+ * rk_group is used: any list, any diag_func.  Synchronous. */
+int rk_sort_members(rk_ctx *ctx, uint64_t m, const uint32_t *gid, const uint64_t *y, const uint64_t *d, uint32_t *perm);
+
+/* Replaces SequenceOcupationList (src/SequenceOcupationList.h:13-33) for code that drives the occupation lists call by call
+ * (the reference's generate_fragment_groups body, src/commonFunctions.cpp:41-80, runs unchanged on top of it): the lists
+ * live in device memory, insert() is queued and applied in order before the next query, get_associated_group() is one
+ * kernel that scans the probed buckets newest-first with the reference's strict `>` on the binary64 deviation.  A tag is
+ * the caller's group handle (the facade passes the FragsGroup pointer); 0 = no group.  Whole databases should use
+ * rk_group, which evaluates all queries of an axis in parallel. */
+typedef struct rk_sol rk_sol;
+rk_sol *rk_sol_create(int device, double len_ratio, double pos_ratio, uint64_t seq_size);
+void rk_sol_destroy(rk_sol *s);
+int rk_sol_insert(rk_sol *s, uint64_t center, uint64_t length, uint64_t tag);
+int rk_sol_get_associated(rk_sol *s, uint64_t center, uint64_t length, uint64_t *tag);
+const char *rk_sol_last_error(const rk_sol *s);
+
 /* Replaces the formatting half of save_frags_from_group / store_frag (src/commonFunctions.cpp:101-115) for the
  * result of the last rk_group / rk_sort_groups: the text of output lines first_line .. first_line+n_lines-1
  *   Frag,xStart,yStart,xEnd,yEnd,strand,gid,length,score,ident,similarity,identity,0,repval\n

@@ -617,6 +617,50 @@ static int st_check_errors(rk_ctx *ctx, bool range_errors) {
   return RK_OK;
 }
 
+// sort_groups (src/commonFunctions.cpp:148-159) as the pure function the reference has: the order of the members of
+// every group under std::sort by h = |yStart - diag_func[xStart/10]|, from the arguments alone — no state of an earlier
+// rk_group is used.  The caller gathers y = f.yStart and d = diag_func[f.xStart/10] per member (loads, no arithmetic).
+int rk_sort_members(rk_ctx *ctx, uint64_t m, const uint32_t *gid, const uint64_t *y, const uint64_t *d, uint32_t *perm) {
+  if (!ctx || !ctx->st_cnt || (m && (!gid || !y || !d || !perm))) return RK_ERR_ARG;
+  if (m >= 0xFFFFFFF0ull) return fail(ctx, RK_ERR_ARG, "more than 2^32-16 members");
+  if (m == 0) return RK_OK;
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  cudaStream_t st = ctx->stream;
+  const u64 a4 = align_up(m * 4, 256), a8 = align_up(m * 8, 256);
+  void *scr = nullptr;
+  const int rc = st_scratch(ctx, 2 * a8 + 7 * a4 + align_up(m, 256) + align_up(order_scratch_bytes(m), 256) + 256, &scr);
+  if (rc != RK_OK) return rc;
+  u8 *p = (u8 *)scr;
+  u64 *d_y = (u64 *)p; p += a8;
+  u64 *d_d = (u64 *)p; p += a8;
+  u32 *d_gid = (u32 *)p; p += a4;
+  u32 *d_h = (u32 *)p; p += a4;
+  u32 *d_idx = (u32 *)p; p += a4;
+  float *d_zero = (float *)p; p += a4;
+  u32 *d_order = (u32 *)p; p += a4;
+  u32 *d_ogid = (u32 *)p; p += a4;
+  float *d_oident = (float *)p; p += a4;  // (identity is not part of this call: zeros in, zeros out)
+  u8 *d_rep = p; p += align_up(m, 256);
+  void *oscr = p;
+  CK(cudaMemcpyAsync(d_y, y, m * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_d, d, m * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_gid, gid, m * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->st_cnt, 0, sizeof(Counters), st));
+  launch_member_keys(d_y, d_d, (u32)m, d_h, d_idx, d_zero, &ctx->st_cnt->err, st);
+  OrderArgs oa{};
+  oa.sgid = d_gid, oa.srank = nullptr, oa.hfi_r = nullptr, oa.h = d_h, oa.fidx_r = d_idx, oa.identity_r = d_zero;
+  oa.m = (u32)m, oa.do_sort = 1;
+  order_carve(oa, oscr, m);
+  oa.work_count = ctx->st_cnt->work_g;
+  oa.out_order = d_order, oa.out_gid = d_ogid, oa.out_repval = d_rep, oa.out_identity = d_oident;
+  oa.err = &ctx->st_cnt->err;
+  launch_order(oa, st);
+  CK(cudaMemcpyAsync(perm, d_order, m * 4, cudaMemcpyDeviceToHost, st));
+  const int rc2 = st_check_errors(ctx, true);
+  return rc2;
+}
+
 int rk_gen_workload(rk_ctx *ctx, uint64_t seed, uint64_t lx, uint64_t ly, double p_rep, uint64_t families, uint64_t ax, uint64_t ay,
                     uint64_t tandem_every, uint64_t start, uint64_t count, void *out_device) {
   if (!ctx || (count && !out_device)) return RK_ERR_ARG;

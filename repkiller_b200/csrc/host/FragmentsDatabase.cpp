@@ -290,6 +290,32 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   ms_device_load_ = std::chrono::duration<double, std::milli>(t3 - t2).count();
 }
 
+// FragmentsDatabase.cpp:84-97 of the reference fills loaded_frags[xStart/10] by push_back in file order.  Here the
+// visiting order comes from the device (rank_fidx = the stable radix sort of K2a: bucket by bucket, file order inside),
+// so iterating begin()..end() visits exactly the fragments, in exactly the order, that rk_group processes.
+void FragmentsDatabase::build_buckets() const {
+  std::unique_ptr<std::vector<FragFile>[]> b(new std::vector<FragFile>[vsize]);
+  const uint64_t kept = load_stats_.n_kept;
+  std::vector<uint32_t> rank_fidx(kept ? kept : 1);
+  if (kept) {
+    const int64_t got = rk_debug_fetch(ctx_, "rank_fidx", rank_fidx.data(), kept * sizeof(uint32_t));
+    if (got < 0) throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(ctx_));
+  }
+  for (uint64_t i = 0; i < kept; ++i) {
+    const FragFile &f = records_[rank_fidx[i]];
+    b[f.xStart / 10].push_back(f);
+  }
+  if (kept < count_)  // fragments of bucket getA()-1: loaded by the reference, never visited (FragmentsDatabase.h:29-31)
+    for (uint64_t i = 0; i < count_; ++i)
+      if (records_[i].xStart / 10 == vsize - 1) b[vsize - 1].push_back(records_[i]);
+  buckets_ = std::move(b);
+}
+
+const std::vector<FragFile> *FragmentsDatabase::begin() const {
+  std::call_once(buckets_once_, [this] { build_buckets(); });
+  return buckets_.get();
+}
+
 FragmentsDatabase::~FragmentsDatabase() {
   if (ctx_) rk_destroy(ctx_);
   if (records_) rk_host_free(records_);

@@ -5,6 +5,8 @@
 
 #include <cstdint>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,6 +27,10 @@ class FragmentsDatabase {
   std::string header;
   rk_load_stats load_stats_{};
   double ms_read_ = 0, ms_parse_ = 0, ms_device_load_ = 0;  // host wall clock of the three ingest phases
+  // the reference's bucket array, built on first use from the processing order the device computed (K2a)
+  mutable std::unique_ptr<std::vector<FragFile>[]> buckets_;
+  mutable std::once_flag buckets_once_;
+  void build_buckets() const;
 
  public:
   // Parses the GECKO CSV exactly like the reference (16 header lines, Frag rows, readFragment's accept/pad
@@ -37,7 +43,12 @@ class FragmentsDatabase {
 
   size_t getA() const { return vsize; }                 // reference: FragmentsDatabase.h:23-25
   uint64_t getTotalFrags() const { return count_; }      // reference: FragmentsDatabase.h:32-34
-  const FragFile *records() const { return records_; }   // replaces begin()/end(): file order, not buckets
+  // reference: FragmentsDatabase.h:26-31 — the xStart/10 bucket array; end() is begin() + getA() - 1, i.e. the last
+  // bucket is never visited.  Built lazily (a host copy of every record, like the reference holds) from the device's
+  // processing order; the grouping functions of this repo do not need it.
+  const std::vector<FragFile> *begin() const;
+  const std::vector<FragFile> *end() const { return begin() + vsize - 1; }
+  const FragFile *records() const { return records_; }   // the records in file order (pinned host memory)
   rk_ctx *ctx() const { return ctx_; }
   const rk_load_stats &load_stats() const { return load_stats_; }
   double ms_read() const { return ms_read_; }

@@ -1,6 +1,7 @@
 #include "commonFunctions.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <map>
@@ -35,10 +36,6 @@ void init_args(const std::vector<std::string> &args, std::ifstream &multifrags, 
 
 namespace {
 
-// which database filled which list (sort_groups receives only the list)
-std::mutex g_reg_mtx;
-std::map<const FGList *, const FragmentsDatabase *> g_registry;
-
 void build_groups(const FragmentsDatabase &db, const rk_result &r, FGList &out) {
   const FragFile *recs = db.records();
   out.clear();
@@ -56,15 +53,6 @@ void build_groups(const FragmentsDatabase &db, const rk_result &r, FGList &out) 
   }
 }
 
-void reorder_groups(const FragmentsDatabase &db, const rk_result &r, FGList &fgl) {
-  const FragFile *recs = db.records();
-  uint64_t j = 0;
-  for (FragsGroup *fg : fgl) {
-    for (size_t k = 0; k < fg->size(); ++k) (*fg)[k] = recs + r.order[j + k];
-    j += fg->size();
-  }
-}
-
 [[noreturn]] void device_error(const FragmentsDatabase &db) {
   throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(db.ctx()));
 }
@@ -76,10 +64,6 @@ size_t generate_fragment_groups(const FragmentsDatabase &frags_db, FGList &efrag
   rk_result r;
   if (rk_group(frags_db.ctx(), lensim, possim, RK_F_HOST_RESULT | RK_F_NO_SORT, &r) != RK_OK) device_error(frags_db);
   build_groups(frags_db, r, efrags_groups);
-  {
-    std::lock_guard<std::mutex> lk(g_reg_mtx);
-    g_registry[&efrags_groups] = &frags_db;
-  }
   std::cout << std::flush;  // reference: commonFunctions.cpp:78
   return efrags_groups.size();
 }
@@ -89,17 +73,51 @@ void generate_diagonal_func(const FragmentsDatabase &fdb, size_t *diag_func) {
   if (rk_diagonal_func(fdb.ctx(), reinterpret_cast<uint64_t *>(diag_func)) != RK_OK) device_error(fdb);
 }
 
-void sort_groups(FGList &fgl, const size_t *) {
-  const FragmentsDatabase *db = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_reg_mtx);
-    auto it = g_registry.find(&fgl);
-    if (it != g_registry.end()) db = it->second;
+namespace {
+// sort_groups has no database argument: it owns a small context (created on first use, calls serialised)
+struct SortContext {
+  std::mutex mtx;
+  rk_ctx *ctx = nullptr;
+  ~SortContext() { if (ctx) rk_destroy(ctx); }
+};
+SortContext g_sort;
+}  // namespace
+
+void sort_groups(FGList &fgl, const size_t *diag_func) {
+  uint64_t m = 0;
+  for (const FragsGroup *fg : fgl) m += fg->size();
+  if (m == 0) return;
+  std::vector<uint32_t> gid(m), perm(m);
+  std::vector<uint64_t> y(m), d(m);
+  uint64_t j = 0;
+  uint32_t g = 0;
+  for (const FragsGroup *fg : fgl) {
+    for (const FragFile *f : *fg) {
+      gid[j] = g;
+      y[j] = f->yStart;
+      d[j] = diag_func[f->xStart / 10];  // reference: commonFunctions.cpp:152,154
+      ++j;
+    }
+    ++g;
   }
-  if (!db) throw std::runtime_error("sort_groups: this list was not produced by generate_fragment_groups");
-  rk_result r;
-  if (rk_sort_groups(db->ctx(), RK_F_HOST_RESULT, &r) != RK_OK) device_error(*db);
-  reorder_groups(*db, r, fgl);
+  std::lock_guard<std::mutex> lk(g_sort.mtx);
+  if (!g_sort.ctx) {
+    const char *e = getenv("RK_DEVICE");
+    g_sort.ctx = rk_create(e ? atoi(e) : 0);
+    if (!g_sort.ctx) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
+  }
+  if (rk_sort_members(g_sort.ctx, m, gid.data(), y.data(), d.data(), perm.data()) != RK_OK)
+    throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(g_sort.ctx));
+  j = 0;
+  std::vector<const FragFile *> tmp;
+  for (FragsGroup *fg : fgl) {
+    const size_t n = fg->size();
+    if (n > 1) {
+      tmp.assign(fg->begin(), fg->end());
+      for (size_t k = 0; k < n; ++k) (*fg)[k] = tmp[perm[j + k] - j];  // perm holds member indices of the whole list
+    }
+    j += n;
+  }
 }
 
 FGList *group_and_sort(const FragmentsDatabase &frags_db, double len_ratio, double pos_ratio, rk_result *stats) {
@@ -113,10 +131,6 @@ FGList *group_and_sort(const FragmentsDatabase &frags_db, double len_ratio, doub
 
 void free_groups(FGList *fgl) {
   if (!fgl) return;
-  {
-    std::lock_guard<std::mutex> lk(g_reg_mtx);
-    g_registry.erase(fgl);
-  }
   for (FragsGroup *g : *fgl) delete g;
   delete fgl;
 }

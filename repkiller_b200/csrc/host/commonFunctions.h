@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "FragmentsDatabase.h"
+#include "SequenceOcupationList.h"
 #include "structs.h"
 
 void print_help();  // reference: commonFunctions.cpp:3-7
@@ -20,8 +21,9 @@ size_t generate_fragment_groups(const FragmentsDatabase &frags_db, FGList &efrag
                                 double len_pos_ratio, double pos_ratio);
 // reference: commonFunctions.cpp:161-177; diag_func has frags_db.getA() entries, [0, getA()-2] are written.
 void generate_diagonal_func(const FragmentsDatabase &fdb, size_t *diag_func);
-// reference: commonFunctions.cpp:148-159.  fgl must be the list the last generate_fragment_groups filled for
-// that database: the member order is computed on the device (K5b) from the state that call left there.
+// reference: commonFunctions.cpp:148-159.  A pure function of its arguments, like the reference's: any list of groups,
+// any diag_func.  Per member the host gathers yStart and diag_func[xStart/10]; h and libstdc++'s std::sort order of
+// every group are computed on the device (rk_sort_members, K5b) on a context of its own (GPU RK_DEVICE, default 0).
 void sort_groups(FGList &fgl, const size_t *diag_func);
 // One call for the three above (what the CLI uses: no intermediate host lists).
 FGList *group_and_sort(const FragmentsDatabase &frags_db, double len_ratio, double pos_ratio, rk_result *stats = nullptr);

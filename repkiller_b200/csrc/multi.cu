@@ -286,9 +286,9 @@ struct Trace {
   void end(cudaStream_t st) {
     if (on && !recs.empty()) cudaEventRecord(recs.back().b, st);
   }
-  void dump(int rank) {
+  void dump(int rank, const std::string &counts) {
     if (!on) return;
-    std::string line = "[rk_dist rank " + std::to_string(rank) + "]";
+    std::string line = "[rk_dist rank " + std::to_string(rank) + "] " + counts;
     float total = 0.f;
     for (auto &r : recs) {
       float ms = 0.f;
@@ -923,7 +923,13 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
-  D.trace.dump(me);
+  if (D.trace.on) {
+    char cb[200];
+    snprintf(cb, sizeof cb, "ranked=%u halo_in=%u halo_out=%u y=%u lines=%u groups=%llu stages x=%.3f y=%.3f forest=%.3f exch=%.3f order=%.3f |", m, nh,
+             D.n_away, D.m_y, mg, (unsigned long long)total_groups, ev_ms(ev[0], ev[1]), ev_ms(ev[1], ev[2]), ev_ms(ev[2], ev[3]),
+             ev_ms(ev[3], ev[4]), ev_ms(ev[4], ev[5]));
+    D.trace.dump(me, cb);
+  }
 
   out->n_kept = mg;
   out->n_groups = total_groups;

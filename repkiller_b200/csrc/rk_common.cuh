@@ -303,6 +303,9 @@ int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *wo
 int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, u32 *gid_rank, cudaStream_t st);
 int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st);
 
+// sort_groups as a function of (groups, diag_func): h = |y - d| per member, member index, zero identity (sol.cu)
+int launch_member_keys(const u64 *y, const u64 *d, u32 m, u32 *h, u32 *idx, float *zero, u32 *err, cudaStream_t st);
+
 u64 order_scratch_bytes(u64 m);
 void order_carve(OrderArgs &a, void *scratch, u64 m);  // sets packed .. worklist, work_cap
 int launch_order(const OrderArgs &a, cudaStream_t st);
