@@ -22,7 +22,7 @@ NONE = 0xFFFFFFFF
 
 def build(ref: bool = True) -> None:
     """Compile the C restatement and, when /root/reference is present, the reference behind ref_driver.cpp."""
-    subprocess.check_call(["make", "-s", "-C", HERE, "lib"] + (["ref"] if ref else []))
+    subprocess.check_call(["make", "-s", "-C", HERE, "lib"] + (["ref", "refbody"] if ref else []))
 
 
 class _Result(C.Structure):

@@ -9,8 +9,16 @@
 //                                             the reference's call sequence (repkiller.cpp:83-96):
 //                                             generate_fragment_groups -> generate_diagonal_func -> sort_groups ->
 //                                             save_all_frag_pairs, each through its own facade (GPU)
+//   rk_hostcheck steps_pure <in.csv> <out.csv> <len_ratio> <pos_ratio> <len_ratio2> <pos_ratio2>
+//                                             sort_groups is a pure function: a second grouping with other ratios is
+//                                             made BEFORE the first list is sorted; the output is the first one's (GPU)
+//   rk_hostcheck sort_any <in.csv> <len_ratio> <pos_ratio>
+//                                             sort_groups with an arbitrary diag_func table against std::sort with the
+//                                             reference's comparator (commonFunctions.cpp:148-159) on the same lists (GPU)
+//   rk_hostcheck buckets <in.csv> <out.bin>   the records visited by begin()..end(), in visiting order (GPU)
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -120,6 +128,60 @@ int main(int argc, char **argv) {
     generate_diagonal_func(db, diag.data());
     sort_groups(groups, diag.data());
     save_all_frag_pairs(argv[3], sm, groups);
+    return 0;
+  }
+  if (mode == "steps_pure" && argc >= 8) {
+    std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+    sequence_manager sm;
+    FragmentsDatabase db(in, sm);
+    FGList groups, other;
+    generate_fragment_groups(db, groups, sm, std::stod(argv[4]), std::stod(argv[5]));
+    generate_fragment_groups(db, other, sm, std::stod(argv[6]), std::stod(argv[7]));  // leaves ITS state on the device
+    std::vector<size_t> diag(db.getA());
+    generate_diagonal_func(db, diag.data());
+    sort_groups(other, diag.data());
+    sort_groups(groups, diag.data());
+    save_all_frag_pairs(argv[3], sm, groups);
+    return 0;
+  }
+  if (mode == "sort_any" && argc >= 5) {
+    std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+    sequence_manager sm;
+    FragmentsDatabase db(in, sm);
+    FGList groups;
+    generate_fragment_groups(db, groups, sm, std::stod(argv[3]), std::stod(argv[4]));
+    std::vector<size_t> diag(db.getA());
+    for (size_t b = 0; b < diag.size(); ++b) diag[b] = (b * 2654435761ull) % 977;  // any table: many ties, no relation to the data
+    FGList want;
+    for (FragsGroup *g : groups) want.push_back(new FragsGroup(*g));
+    for (FragsGroup *g : want) {
+      if (g->size() <= 1) continue;
+      const size_t *df = diag.data();
+      std::sort(g->begin(), g->end(), [df](const FragFile *f1, const FragFile *f2) {
+        const uint64_t d1 = df[f1->xStart / 10], d2 = df[f2->xStart / 10];
+        const uint64_t h1 = f1->yStart > d1 ? f1->yStart - d1 : d1 - f1->yStart;
+        const uint64_t h2 = f2->yStart > d2 ? f2->yStart - d2 : d2 - f2->yStart;
+        return h1 < h2;
+      });
+    }
+    sort_groups(groups, diag.data());
+    size_t bad = 0, big = 0;
+    for (size_t i = 0; i < groups.size(); ++i) {
+      if (groups[i]->size() > 16) ++big;
+      if (*groups[i] != *want[i]) ++bad;
+    }
+    printf("%zu groups, %zu with more than 16 members, %zu differ from std::sort\n", groups.size(), big, bad);
+    return bad != 0;
+  }
+  if (mode == "buckets" && argc >= 4) {
+    std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+    sequence_manager sm;
+    FragmentsDatabase db(in, sm);
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 3;
+    for (const auto &fl : db)
+      for (const auto &fr : fl) fwrite(&fr, sizeof(FragFile), 1, f);
+    fclose(f);
     return 0;
   }
   return 2;

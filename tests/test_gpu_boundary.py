@@ -1,0 +1,109 @@
+"""The drop-in boundary: the reference's class and function names over the C ABI.
+  * the reference's OWN generate_fragment_groups body (commonFunctions.cpp:41-80, compiled unchanged by oracle/Makefile
+    `refbody` where /root/reference is present) against FragmentsDatabase::begin()/end() and SequenceOcupationList of
+    this repo must reproduce the reference's golden bytes;
+  * sort_groups is a pure function of (list, diag_func), like the reference's;
+  * the bucket view visits the records the way the reference's bucket array does;
+  * short CSV rows (readFragment's padding rule) through the CLI."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from repkiller_b200 import gen
+from repkiller_b200.frags import FRAG_DTYPE, make_header
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "repkiller_b200", "bin", "repkiller")
+HOSTCHECK = os.path.join(ROOT, "repkiller_b200", "bin", "rk_hostcheck")
+REFBODY = os.path.join(ROOT, "oracle", "_ref", "ref_body_check")
+
+
+def _need(path):
+    if not os.path.exists(path):
+        pytest.skip(f"{os.path.relpath(path, ROOT)} is built where the reference sources are present (python __graft_entry__.py)")
+
+
+def test_reference_loop_body_on_the_facades_fuzz(tmp_path, fuzz_cases):
+    _need(REFBODY)
+    for c in fuzz_cases[::4]:
+        inp = tmp_path / "in.csv"
+        inp.write_text(c["csv"], newline="")
+        outp = tmp_path / "out.csv"
+        p = subprocess.run([REFBODY, str(inp), str(outp), repr(c["len_ratio"]), repr(c["pos_ratio"])], capture_output=True)
+        assert p.returncode == 0, p.stderr
+        assert outp.read_bytes() == c["ref_out"].encode("latin1"), f"fuzz seed {c['seed']}"
+
+
+@pytest.mark.parametrize("name", ["dense", "c1"])
+def test_reference_loop_body_on_the_facades_golden_md5(tmp_path, medium_cases, name):
+    """100k fragments: ~200k single device queries, groups of thousands of members, std::sort tie order"""
+    _need(REFBODY)
+    c = medium_cases[name]
+    w = gen.Workload(**c["workload"])
+    inp = tmp_path / "in.csv"
+    O.write_input_csv(str(inp), gen.generate(w), w.lx, w.ly)
+    outp = tmp_path / "out.csv"
+    p = subprocess.run([REFBODY, str(inp), str(outp), repr(w.len_ratio), repr(w.pos_ratio)], capture_output=True, timeout=900)
+    assert p.returncode == 0, p.stderr
+    assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"]
+
+
+def test_sort_groups_is_a_pure_function(tmp_path, medium_cases):
+    """a grouping with other ratios between generate_fragment_groups and sort_groups must not change the result"""
+    c = medium_cases["c1"]
+    w = gen.Workload(**c["workload"])
+    inp = tmp_path / "c1.csv"
+    O.write_input_csv(str(inp), gen.generate(w), w.lx, w.ly)
+    outp = tmp_path / "out.csv"
+    p = subprocess.run([HOSTCHECK, "steps_pure", str(inp), str(outp), "0.05", "0.05", "0.5", "0.5"], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"]
+
+
+def test_sort_groups_with_any_table_equals_std_sort(tmp_path, medium_cases):
+    w = gen.Workload(**medium_cases["dense"]["workload"])
+    inp = tmp_path / "in.csv"
+    O.write_input_csv(str(inp), gen.generate(w), w.lx, w.ly)
+    p = subprocess.run([HOSTCHECK, "sort_any", str(inp), repr(w.len_ratio), repr(w.pos_ratio)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    n_big = int(p.stdout.split(" with more than 16 members")[0].split(",")[-1])
+    assert n_big > 10 and " 0 differ" in p.stdout, p.stdout
+
+
+def test_bucket_view_is_the_processing_order(tmp_path):
+    w = gen.scaled(gen.WORKLOADS["c1"], 50_000)
+    rec = gen.generate(w)
+    rec["xStart"][:7] = (w.lx + 1) // 10 * 10   # some fragments of the never-visited last bucket (xStart/10 == vsize-1)
+    inp = tmp_path / "in.csv"
+    O.write_input_csv(str(inp), rec, w.lx, w.ly)
+    outp = tmp_path / "visited.bin"
+    p = subprocess.run([HOSTCHECK, "buckets", str(inp), str(outp)], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    loaded, lx1, ly1, _ = O.load_csv(str(inp))
+    g = O.group(loaded, lx1, ly1, 0.05, 0.05)
+    assert g.n_kept < loaded.shape[0]
+    got = np.fromfile(outp, dtype=FRAG_DTYPE)
+    assert got.tobytes() == loaded[g.rank_fidx].tobytes()
+
+
+def test_cli_short_rows_do_not_overflow_the_record_buffer(tmp_path):
+    """readFragment accepts `Frag,5` (7 bytes, missing fields repeat the last one): far more records than bytes/28"""
+    rows = "".join(f"Frag,{5 + (i % 90)}\n" for i in range(20000))
+    text = make_header(2000, 2000, 20000) + rows
+    inp = tmp_path / "in.csv"
+    inp.write_text(text, newline="")
+    outp = tmp_path / "out.csv"
+    p = subprocess.run([CLI, str(inp), str(outp), "0.5", "0.5"], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    rec, lx1, ly1, hdr = O.load_csv(str(inp))
+    assert rec.shape[0] == 20000
+    g = O.group(rec, lx1, ly1, 0.5, 0.5)
+    want = tmp_path / "want.csv"
+    O.write_output(str(want), hdr, rec, g)
+    assert outp.read_bytes() == want.read_bytes()
