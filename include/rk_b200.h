@@ -112,6 +112,17 @@ int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk
  * rk_group with RK_F_NO_SORT, orders the members of every group on the device and returns the result again. */
 int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out);
 
+/* Per-group statistics of the last rk_group / rk_sort_groups (not part of the reference's output file; its groups are the
+ * FragsGroups of src/commonFunctions.cpp:56-76 in creation order): one entry per group id.  x/y span = [min start,
+ * max(start + length)); mean_identity = mean of the identity column; multiplicity = sum of lengths / X span (how many
+ * copies cover the span).  Integers are exact; the two doubles agree with a sequential evaluation to ~1e-15 relative.
+ * stats: pinned host array owned by the context (valid until the next call), d_stats: the same on the device. */
+typedef struct {
+  uint32_t count, x_lo, x_hi, y_lo, y_hi, first_line;
+  double mean_identity, multiplicity;
+} rk_group_stats;
+int rk_group_statistics(rk_ctx *ctx, unsigned flags, const rk_group_stats **stats, const rk_group_stats **d_stats, uint64_t *n_groups);
+
 /* Replaces sort_groups (src/commonFunctions.cpp:148-159) as the PURE function the reference has: perm[j] = index (into
  * the member arrays handed in) of the member that std::sort leaves at position j, for m members given group by group
  * (gid nondecreasing), y[j] = yStart and d[j] = diag_func[xStart/10] of member j (host arrays).  Nothing of an earlier
@@ -174,47 +185,11 @@ int rk_profile_enable(rk_ctx *ctx, int on);
 int rk_profile_read(rk_ctx *ctx, rk_kernel_time *out, int cap, int reset);
 
 /* Stand-alone stable LSD radix sort of (u32 key, u32 value) pairs on the device (kernel K2), exported for
- * tests and the multi-GPU driver.  All pointers are device pointers; values_in may be NULL (values = 0..n-1).
+ * tests.  All pointers are device pointers; values_in may be NULL (values = 0..n-1).
  * `work` needs rk_sort_pairs_work_bytes(n) bytes.  The result is in keys_out/values_out. */
 uint64_t rk_sort_pairs_work_bytes(uint64_t n);
 int rk_sort_pairs(rk_ctx *ctx, const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out,
                   uint32_t *values_out, uint32_t *keys_tmp, uint32_t *values_tmp, uint64_t n, int key_bits, void *work);
-
-/* ---- multi-GPU stage entry points -----------------------------------------------------------------------------
- * The kernels of rk_load_aos / rk_group on caller-owned DEVICE arrays, for the range-partitioned single
- * comparison (repkiller_b200/dist.py): fragments are exchanged between ranks (NCCL) between these calls, so every
- * array is already in the order the kernel consumes ("direct" layout).  Work is queued on the context's stream. */
-uint64_t rk_st_link_words(uint64_t seq_len); /* u32 words of one link bitmap (axis length = loaded length) */
-/* K1 on this rank's slice of the file; link_x/link_y (rk_st_link_words words each) are this rank's contribution
- * and must be OR-ed over the ranks (rk_st_or_words) before rk_st_keys.  Synchronises; *n_dropped = fragments of the
- * never-visited last X bucket. */
-int rk_st_decode(rk_ctx *ctx, const void *aos, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, uint32_t *xs, uint32_t *ys,
-                 uint32_t *len, uint8_t *flags, float *identity, uint32_t *key0, uint32_t *link_x, uint32_t *link_y,
-                 uint64_t *n_dropped);
-int rk_st_or_words(rk_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n_words);
-/* Row plumbing of the redistributions: a fragment travels as a row of k <= 8 32-bit words.  `cols` is a HOST array
- * of k device pointers.  interleave: rows[i][j] = cols[j][i]; gather_rows: out[i][:] = rows[idx[i]][:];
- * unpack_rows: cols[j][i] = rows[idx ? idx[i] : i][j] (NULL column pointers are skipped); scatter: out[idx[i]] = values[i]. */
-int rk_st_interleave(rk_ctx *ctx, const uint32_t *const *cols, uint64_t n, int k, uint32_t *rows);
-int rk_st_gather_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *out);
-int rk_st_unpack_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *const *cols);
-int rk_st_scatter(rk_ctx *ctx, const uint32_t *values, const uint32_t *idx, uint64_t n, uint32_t *out);
-/* centers and super-bucket sort keys of m fragments given in processing order */
-int rk_st_keys(rk_ctx *ctx, uint64_t m, uint64_t seqx_len, uint64_t seqy_len, const uint32_t *xs_r, const uint32_t *ys_r,
-               const uint32_t *len_r, const uint8_t *flags_r, const uint32_t *link_x, const uint32_t *link_y, uint32_t *cx,
-               uint32_t *cy, uint32_t *kx, uint32_t *ky);
-/* one axis pass (K3) over m fragments stably sorted by skey: sid = global processing rank, sc = center, slen = length,
- * sxm = NULL for the X pass, else 1 where the fragment already has an X owner (Y pass).  owner[i] = global rank of
- * the matched entry's fragment or RK_NONE.  seq_len = loaded length of this axis. */
-int rk_st_match(rk_ctx *ctx, uint64_t m, const uint32_t *skey, const uint32_t *sid, const uint32_t *sc, const uint32_t *slen,
-                const uint8_t *sxm, uint64_t seq_len, double len_ratio, double pos_ratio, uint32_t *owner);
-/* K4 on the all-gathered parent array (m_total global ranks): group ids of ranks [lo, lo+cnt).  Synchronises. */
-int rk_st_forest(rk_ctx *ctx, const uint32_t *parent, uint64_t m_total, uint64_t lo, uint64_t cnt, uint32_t *gid_out,
-                 uint64_t *n_groups);
-int rk_st_hkey(rk_ctx *ctx, const uint32_t *k0_r, const uint32_t *ys_r, uint64_t m, uint32_t *h);
-/* K5b/c over m fragments stably sorted by group id (processing order inside a group).  Synchronises. */
-int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *sh, const uint32_t *sfidx, const float *sident,
-                int do_sort, uint32_t *out_order, uint32_t *out_gid, uint8_t *out_repval, float *out_identity);
 
 /* ---- one comparison partitioned over several GPUs ---------------------------------------------
  * The reference is one process on one host (src/repkiller.cpp); these entry points run the same

@@ -152,6 +152,25 @@ def write_input_csv(path: str, records: np.ndarray, lx_header: int, ly_header: i
         raise OSError(f"cannot write {path}")
 
 
+def group_statistics(records: np.ndarray, g: OracleGroups) -> np.ndarray:
+    """sequential per-group reduction over the oracle's groups (checker of rk_group_statistics)"""
+    from repkiller_b200.capi import GROUP_STATS_DTYPE
+    L = lib()
+    L.rko_group_statistics.argtypes = [C.c_void_p, C.POINTER(_Result), C.c_void_p]
+    L.rko_group_statistics.restype = C.c_int
+    r = _Result()
+    r.n_kept, r.n_groups = g.n_kept, g.n_groups
+    keep = [np.ascontiguousarray(g.order), np.ascontiguousarray(g.out_gid), np.ascontiguousarray(g.identity)]
+    r.order = keep[0].ctypes.data_as(C.POINTER(C.c_uint32))
+    r.out_gid = keep[1].ctypes.data_as(C.POINTER(C.c_uint32))
+    r.identity = keep[2].ctypes.data_as(C.POINTER(C.c_float))
+    rec = np.ascontiguousarray(records)
+    out = np.zeros(g.n_groups, dtype=GROUP_STATS_DTYPE)
+    if L.rko_group_statistics(rec.ctypes.data, C.byref(r), out.ctypes.data):
+        raise ValueError("rko_group_statistics failed")
+    return out
+
+
 def std_sort_by_key(idx: np.ndarray, h: np.ndarray) -> np.ndarray:
     """libstdc++ std::sort order of idx under comp(a, b) = h[a] < h[b]."""
     out = np.ascontiguousarray(idx, dtype=np.uint32).copy()

@@ -23,14 +23,14 @@ NSTAGES = len(STAGES)
 # every symbol include/rk_b200.h declares
 SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_group", "rk_sort_groups", "rk_host_alloc", "rk_host_free",
            "rk_diagonal_func", "rk_format_lines", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
-           # multi-GPU stage entry points (bound in repkiller_b200/dist.py)
-           "rk_st_link_words", "rk_st_decode", "rk_st_or_words", "rk_st_keys", "rk_st_match", "rk_st_forest", "rk_st_hkey",
-           "rk_st_order", "rk_st_interleave", "rk_st_gather_rows", "rk_st_unpack_rows", "rk_st_scatter", "rk_gen_workload",
+           "rk_gen_workload", "rk_sort_members", "rk_group_statistics", "rk_sol_create", "rk_sol_destroy", "rk_sol_insert", "rk_sol_get_associated", "rk_sol_last_error",
            # one comparison over several GPUs
            "rk_dist_unique_id", "rk_dist_init", "rk_dist_export", "rk_dist_import", "rk_dist_load_aos", "rk_dist_group",
            "rk_create_multi", "rk_destroy_multi", "rk_multi_last_error", "rk_multi_ranks", "rk_multi_ctx", "rk_multi_transport",
            "rk_multi_load_aos", "rk_multi_group", "rk_multi_info"]
 DIST_ID_BYTES, DIST_BLOB_BYTES = 128, 128
+GROUP_STATS_DTYPE = np.dtype([("count", "<u4"), ("x_lo", "<u4"), ("x_hi", "<u4"), ("y_lo", "<u4"), ("y_hi", "<u4"), ("first_line", "<u4"),
+                              ("mean_identity", "<f8"), ("multiplicity", "<f8")])
 
 
 class RkError(RuntimeError):
@@ -96,6 +96,8 @@ def load_library():
     L.rk_format_lines.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(_Text)]
     L.rk_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.rk_profile_read.argtypes = [C.c_void_p, C.POINTER(_KernelTime), C.c_int, C.c_int]
+    L.rk_group_statistics.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.rk_sort_members.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rk_dist_unique_id.argtypes = [C.c_void_p]
     L.rk_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
     L.rk_dist_export.argtypes = [C.c_void_p, C.c_void_p]
@@ -284,6 +286,24 @@ class Context:
 
     def sort_pairs_work_bytes(self, n: int) -> int:
         return int(self._L.rk_sort_pairs_work_bytes(n))
+
+    def group_statistics(self) -> np.ndarray:
+        """per-group statistics of the last group() as a structured array (GROUP_STATS_DTYPE), one row per group id"""
+        hp, dp, ng = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self._L.rk_group_statistics(self._h, F_HOST_RESULT, C.byref(hp), C.byref(dp), C.byref(ng)))
+        if ng.value == 0:
+            return np.zeros(0, dtype=GROUP_STATS_DTYPE)
+        return np.frombuffer(C.string_at(hp.value, ng.value * GROUP_STATS_DTYPE.itemsize), dtype=GROUP_STATS_DTYPE).copy()
+
+    def sort_members(self, gid: np.ndarray, y: np.ndarray, d: np.ndarray) -> np.ndarray:
+        """sort_groups as a pure function: perm[j] = index of the member std::sort leaves at position j (members given
+        group by group, h = |y - d|)"""
+        g = np.ascontiguousarray(gid, dtype=np.uint32)
+        yy, dd = np.ascontiguousarray(y, dtype=np.uint64), np.ascontiguousarray(d, dtype=np.uint64)
+        perm = np.zeros(g.shape[0], dtype=np.uint32)
+        self._check(self._L.rk_sort_members(self._h, g.shape[0], C.c_void_p(g.ctypes.data), C.c_void_p(yy.ctypes.data),
+                                            C.c_void_p(dd.ctypes.data), C.c_void_p(perm.ctypes.data)))
+        return perm
 
     # ---- one comparison over several GPUs, one process per GPU (rk_dist_*; collective calls) ----
     def dist_init(self, rank: int, world: int, unique_id: bytes, cap_per_rank: int):

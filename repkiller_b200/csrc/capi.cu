@@ -181,6 +181,7 @@ int finish_group(rk_ctx *ctx, unsigned flags, rk_result *out, u64 launches) {
   CK(cudaGetLastError());
   if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
   ctx->have_group = true;
+  ctx->n_groups_last = ctx->h_cnt->n_groups;
 
   out->n_kept = m;
   out->n_groups = ctx->h_cnt->n_groups;
@@ -258,6 +259,8 @@ void rk_destroy(rk_ctx *c) {
   if (c->st_cnt) cudaFree(c->st_cnt);
   if (c->st_scratch) cudaFree(c->st_scratch);
   if (c->d_text) cudaFree(c->d_text);
+  if (c->d_stats) cudaFree(c->d_stats);
+  if (c->h_stats) cudaFreeHost(c->h_stats);
   for (char *t : c->h_text) if (t) cudaFreeHost(t);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
@@ -443,6 +446,46 @@ int rk_sort_groups(rk_ctx *ctx, unsigned flags, rk_result *out) {
   return finish_group(ctx, flags, out, launches);
 }
 
+int rk_group_statistics(rk_ctx *ctx, unsigned flags, const rk_group_stats **stats, const rk_group_stats **d_stats, uint64_t *n_groups) {
+  static_assert(sizeof(rk_group_stats) == sizeof(rk_group_stats_dev) && sizeof(rk_group_stats) == 40, "stats layout");
+  if (!ctx) return RK_ERR_ARG;
+  if (!ctx->loaded || !ctx->have_group) return fail(ctx, RK_ERR_STATE, "rk_group_statistics before rk_group");
+  CK(cudaSetDevice(ctx->device));
+  ProfGuard pg(ctx);
+  cudaStream_t st = ctx->stream;
+  const u64 ng = ctx->n_groups_last;
+  if (ng > ctx->stats_cap) {
+    CK(cudaStreamSynchronize(st));
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    ctx->d_stats = nullptr, ctx->stats_cap = 0;
+    const u64 cap = ng + ng / 8 + 1024;
+    cudaError_t e = cudaMalloc(&ctx->d_stats, cap * sizeof(rk_group_stats));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, RK_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)(cap * sizeof(rk_group_stats)), cudaGetErrorString(e));
+    }
+    ctx->stats_cap = cap;
+  }
+  launch_group_stats(ctx->out_order, ctx->out_gid, ctx->out_identity, ctx->rec4, ctx->m, (u32)ng, (rk_group_stats_dev *)ctx->d_stats, st);
+  if ((flags & RK_F_HOST_RESULT) && ng) {
+    if (ng > ctx->h_stats_cap) {
+      CK(cudaStreamSynchronize(st));
+      if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+      ctx->h_stats = nullptr, ctx->h_stats_cap = 0;
+      const u64 cap = ng + ng / 8 + 1024;
+      CK(cudaHostAlloc(&ctx->h_stats, cap * sizeof(rk_group_stats), cudaHostAllocDefault));
+      ctx->h_stats_cap = cap;
+    }
+    CK(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, ng * sizeof(rk_group_stats), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (stats) *stats = ((flags & RK_F_HOST_RESULT) && ng) ? (const rk_group_stats *)ctx->h_stats : nullptr;
+  if (d_stats) *d_stats = (const rk_group_stats *)ctx->d_stats;
+  if (n_groups) *n_groups = ng;
+  return RK_OK;
+}
+
 int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func) {
   if (!ctx || !diag_func) return RK_ERR_ARG;
   if (!ctx->loaded) return fail(ctx, RK_ERR_STATE, "rk_diagonal_func before rk_load_aos");
@@ -584,9 +627,7 @@ int rk_sort_pairs(rk_ctx *ctx, const uint32_t *keys_in, const uint32_t *values_i
   return RK_OK;
 }
 
-// ---- multi-GPU stage entry points: the same kernels on caller-owned device arrays ("direct" layout) ----------
-// All pointers are device pointers.  Work is queued on the context's stream (set it to the caller's stream with
-// rk_set_stream); only the calls that return a host value synchronise.
+// ---- scratch and error word of the calls that work on caller data (rk_sort_members) --------------------------
 
 static int st_scratch(rk_ctx *ctx, u64 bytes, void **out) {
   if (bytes > ctx->st_scratch_bytes) {
@@ -669,134 +710,6 @@ int rk_gen_workload(rk_ctx *ctx, uint64_t seed, uint64_t lx, uint64_t ly, double
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   return RK_OK;
-}
-
-uint64_t rk_st_link_words(uint64_t seq_len) { return (2ull * (seq_len / DIVISOR + 2) + 31) / 32 + 1; }
-
-int rk_st_decode(rk_ctx *ctx, const void *aos, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, uint32_t *xs, uint32_t *ys,
-                 uint32_t *len, uint8_t *flags, float *identity, uint32_t *key0, uint32_t *link_x, uint32_t *link_y,
-                 uint64_t *n_dropped) {
-  if (!ctx || !ctx->st_cnt || (n && !aos)) return RK_ERR_ARG;
-  if ((uintptr_t)aos & 15) return fail(ctx, RK_ERR_ARG, "device record pointer must be 16-byte aligned");
-  CK(cudaSetDevice(ctx->device));
-  ProfGuard pg(ctx);
-  const Geometry g = make_geometry(seqx_len, seqy_len);
-  CK(cudaMemsetAsync(ctx->st_cnt, 0, sizeof(Counters), ctx->stream));
-  CK(cudaMemsetAsync(link_x, 0, rk_st_link_words(seqx_len) * 4, ctx->stream));
-  CK(cudaMemsetAsync(link_y, 0, rk_st_link_words(seqy_len) * 4, ctx->stream));
-  launch_decode((const u8 *)aos, n, g, xs, ys, len, flags, identity, key0, link_x, link_y, &ctx->st_cnt->n_dropped,
-                &ctx->st_cnt->err, ctx->stream);
-  const int rc = st_check_errors(ctx, true);
-  if (rc != RK_OK) return rc;
-  if (n_dropped) *n_dropped = ctx->h_cnt->n_dropped;
-  return RK_OK;
-}
-
-int rk_st_or_words(rk_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n_words) {
-  if (!ctx) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  launch_or_words(dst, src, n_words, ctx->stream);
-  return RK_OK;
-}
-
-int rk_st_interleave(rk_ctx *ctx, const uint32_t *const *cols, uint64_t n, int k, uint32_t *rows) {
-  if (!ctx || k < 1 || k > 8) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  launch_interleave(cols, n, k, rows, ctx->stream);
-  return RK_OK;
-}
-int rk_st_gather_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *out) {
-  if (!ctx || k < 1 || k > 8) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  launch_gather_rows(rows, idx, n, k, out, ctx->stream);
-  return RK_OK;
-}
-int rk_st_unpack_rows(rk_ctx *ctx, const uint32_t *rows, const uint32_t *idx, uint64_t n, int k, uint32_t *const *cols) {
-  if (!ctx || k < 1 || k > 8) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  launch_unpack_rows(rows, idx, n, k, cols, ctx->stream);
-  return RK_OK;
-}
-int rk_st_scatter(rk_ctx *ctx, const uint32_t *values, const uint32_t *idx, uint64_t n, uint32_t *out) {
-  if (!ctx) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  launch_scatter_u32(values, idx, n, out, ctx->stream);
-  return RK_OK;
-}
-
-int rk_st_keys(rk_ctx *ctx, uint64_t m, uint64_t seqx_len, uint64_t seqy_len, const uint32_t *xs_r, const uint32_t *ys_r,
-               const uint32_t *len_r, const uint8_t *flags_r, const uint32_t *link_x, const uint32_t *link_y, uint32_t *cx,
-               uint32_t *cy, uint32_t *kx, uint32_t *ky) {
-  if (!ctx) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  ProfGuard pg(ctx);
-  launch_keys_direct((u32)m, make_geometry(seqx_len, seqy_len), xs_r, ys_r, len_r, flags_r, link_x, link_y, cx, cy, kx, ky,
-                     ctx->stream);
-  return RK_OK;
-}
-
-int rk_st_match(rk_ctx *ctx, uint64_t m, const uint32_t *skey, const uint32_t *sid, const uint32_t *sc, const uint32_t *slen,
-                const uint8_t *sxm, uint64_t seq_len, double len_ratio, double pos_ratio, uint32_t *owner) {
-  if (!ctx || !ctx->st_cnt) return RK_ERR_ARG;
-  if (!(len_ratio > 0) || !(pos_ratio > 0)) return fail(ctx, RK_ERR_ARG, "ratios must be greater than zero");
-  CK(cudaSetDevice(ctx->device));
-  ProfGuard pg(ctx);
-  const u64 m1 = m ? m : 1;
-  const u32 cap = (u32)(m1 / 32 + 2);
-  void *scr = nullptr;
-  const int rc = st_scratch(ctx, (3 * m1 + cap) * 4 + 1024, &scr);
-  if (rc != RK_OK) return rc;
-  MatchArgs a{};
-  a.skey = skey, a.srank = sid, a.m = (u32)m, a.max_index = (u32)(seq_len / DIVISOR);
-  a.len_ratio = len_ratio, a.pos_ratio = pos_ratio, a.is_y = sxm ? 1 : 0;
-  a.ent_rank = (u32 *)scr, a.ent_c = a.ent_rank + m1, a.ent_len = a.ent_c + m1, a.worklist = a.ent_len + m1;
-  a.work_cap = cap, a.work_count = ctx->st_cnt->work_x, a.err = &ctx->st_cnt->err;
-  a.direct = 1, a.sc = sc, a.slen = slen, a.sxm = sxm, a.owner = owner;
-  launch_match(a, ctx->stream);
-  return RK_OK;
-}
-
-int rk_st_forest(rk_ctx *ctx, const uint32_t *parent, uint64_t m_total, uint64_t lo, uint64_t cnt, uint32_t *gid_out,
-                 uint64_t *n_groups) {
-  if (!ctx || !ctx->st_cnt) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  ProfGuard pg(ctx);
-  void *scr = nullptr;
-  const int rc = st_scratch(ctx, forest_work_bytes((u32)(m_total ? m_total : 1)), &scr);
-  if (rc != RK_OK) return rc;
-  launch_forest(parent, (u32)m_total, gid_out, &ctx->st_cnt->n_groups, scr, ctx->stream, (u32)lo, (u32)cnt);
-  const int rc2 = st_check_errors(ctx, false);
-  if (rc2 != RK_OK) return rc2;
-  if (n_groups) *n_groups = ctx->h_cnt->n_groups;
-  return RK_OK;
-}
-
-int rk_st_hkey(rk_ctx *ctx, const uint32_t *k0_r, const uint32_t *ys_r, uint64_t m, uint32_t *h) {
-  if (!ctx) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  ProfGuard pg(ctx);
-  launch_hkey(k0_r, ys_r, (u32)m, h, ctx->stream);
-  return RK_OK;
-}
-
-int rk_st_order(rk_ctx *ctx, uint64_t m, const uint32_t *sgid, const uint32_t *sh, const uint32_t *sfidx, const float *sident,
-                int do_sort, uint32_t *out_order, uint32_t *out_gid, uint8_t *out_repval, float *out_identity) {
-  if (!ctx || !ctx->st_cnt) return RK_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  ProfGuard pg(ctx);
-  const u64 m1 = m ? m : 1;
-  void *scr = nullptr;
-  const int rc = st_scratch(ctx, order_scratch_bytes(m1), &scr);
-  if (rc != RK_OK) return rc;
-  OrderArgs oa{};
-  oa.sgid = sgid, oa.srank = nullptr, oa.hfi_r = nullptr, oa.h = sh, oa.fidx_r = sfidx, oa.identity_r = sident;
-  oa.m = (u32)m, oa.do_sort = do_sort;
-  order_carve(oa, scr, m1);
-  oa.work_count = ctx->st_cnt->work_g;
-  oa.out_order = out_order, oa.out_gid = out_gid, oa.out_repval = out_repval, oa.out_identity = out_identity;
-  oa.err = &ctx->st_cnt->err;
-  launch_order(oa, ctx->stream);
-  return st_check_errors(ctx, false);
 }
 
 }  // extern "C"

@@ -90,121 +90,6 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u
   return 1;
 }
 
-// multi-GPU stage: the fragments are already in processing order on this rank; the link maps are the OR over ranks
-__global__ void __launch_bounds__(256)
-    k_keys_direct(u32 m, Geometry g, const u32 *__restrict__ xs_r, const u32 *__restrict__ ys_r, const u32 *__restrict__ len_r,
-                  const u8 *__restrict__ flags_r, const u32 *__restrict__ link_x, const u32 *__restrict__ link_y,
-                  u32 *__restrict__ cx, u32 *__restrict__ cy, u32 *__restrict__ kx, u32 *__restrict__ ky) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const u32 l = len_r[i];
-  const u32 sc = flags_r[i] & FL_REVERSE;
-  const u32 x = xs_r[i] + l / 2, y = ys_r[i] + l / 2;
-  cx[i] = x;
-  cy[i] = y;
-  kx[i] = run_start(link_x, sc * g.nbx + x / DIVISOR);
-  ky[i] = run_start(link_y, sc * g.nby + y / DIVISOR);
-}
-
-int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
-                       const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st) {
-  if (m == 0) return 0;
-  KScope ks(KID_KEYS, st, m);
-  k_keys_direct<<<(m + 255) / 256, 256, 0, st>>>(m, g, xs_r, ys_r, len_r, flags_r, link_x, link_y, cx, cy, kx, ky);
-  return 1;
-}
-
-__global__ void __launch_bounds__(256) k_or_words(u32 *__restrict__ dst, const u32 *__restrict__ src, u64 n) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] |= src[i];
-}
-int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st) {
-  if (n == 0) return 0;
-  k_or_words<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, src, n);
-  return 1;
-}
-
-// ---- row plumbing of the multi-GPU redistributions: fragments travel as rows of k 32-bit words -------------------
-struct ColPtrs {
-  const u32 *in[8];
-  u32 *out[8];
-};
-
-// The three row kernels work on tiles of 256 rows, one WORD of the tile per thread and step (word w of the tile is
-// column w % k of row w / k), so that the row side is always touched as contiguous runs of k words and the column
-// side along i.
-constexpr int ROW_TILE = 256;
-__device__ __forceinline__ u32 div_small(u32 w, u32 magic) { return (w * magic) >> 16; }  // w / k for w < 4096, k <= 8
-static inline u32 div_magic(int k) { return (65536u + (u32)k - 1) / (u32)k; }
-
-// rows[i][j] = cols[j][i]
-__global__ void __launch_bounds__(ROW_TILE) k_interleave(ColPtrs c, u64 n, int k, u32 magic, u32 *__restrict__ rows) {
-  const u64 i0 = (u64)blockIdx.x * ROW_TILE;
-  const u32 cnt = (u32)min((u64)ROW_TILE, n - i0);
-  u32 *dst = rows + i0 * k;
-  for (u32 w = threadIdx.x; w < cnt * (u32)k; w += ROW_TILE) {
-    const u32 r = div_small(w, magic), j = w - r * k;
-    dst[w] = c.in[j][i0 + r];
-  }
-}
-// out[i][:] = rows[idx[i]][:]
-__global__ void __launch_bounds__(ROW_TILE) k_gather_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
-                                                          u32 magic, u32 *__restrict__ out) {
-  const u64 i0 = (u64)blockIdx.x * ROW_TILE;
-  const u32 cnt = (u32)min((u64)ROW_TILE, n - i0);
-  u32 *dst = out + i0 * k;
-  for (u32 w = threadIdx.x; w < cnt * (u32)k; w += ROW_TILE) {
-    const u32 r = div_small(w, magic), j = w - r * k;
-    dst[w] = rows[(u64)idx[i0 + r] * k + j];
-  }
-}
-// cols[j][i] = rows[idx ? idx[i] : i][j]
-__global__ void __launch_bounds__(ROW_TILE) k_unpack_rows(const u32 *__restrict__ rows, const u32 *__restrict__ idx, u64 n, int k,
-                                                          u32 magic, ColPtrs c) {
-  __shared__ u32 s[ROW_TILE * 8 + 8];
-  const u64 i0 = (u64)blockIdx.x * ROW_TILE;
-  const u32 cnt = (u32)min((u64)ROW_TILE, n - i0);
-  for (u32 w = threadIdx.x; w < cnt * (u32)k; w += ROW_TILE) {
-    const u32 r = div_small(w, magic), j = w - r * k;
-    s[w + (r >> 5)] = idx ? rows[(u64)idx[i0 + r] * k + j] : rows[i0 * k + w];  // one pad word per 32 rows (even k)
-  }
-  __syncthreads();
-  if (threadIdx.x < cnt)
-    for (int j = 0; j < k; ++j)
-      if (c.out[j]) c.out[j][i0 + threadIdx.x] = s[threadIdx.x * k + j + (threadIdx.x >> 5)];
-}
-// out[idx[i]] = v[i]
-__global__ void __launch_bounds__(256) k_scatter_u32(const u32 *__restrict__ v, const u32 *__restrict__ idx, u64 n,
-                                                     u32 *__restrict__ out) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[idx[i]] = v[i];
-}
-
-int launch_interleave(const u32 *const *cols, u64 n, int k, u32 *rows, cudaStream_t st) {
-  if (n == 0) return 0;
-  ColPtrs c{};
-  for (int j = 0; j < k; ++j) c.in[j] = cols[j];
-  k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, n, k, div_magic(k), rows);
-  return 1;
-}
-int launch_gather_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *out, cudaStream_t st) {
-  if (n == 0) return 0;
-  k_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, div_magic(k), out);
-  return 1;
-}
-int launch_unpack_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *const *cols, cudaStream_t st) {
-  if (n == 0) return 0;
-  ColPtrs c{};
-  for (int j = 0; j < k; ++j) c.out[j] = cols[j];
-  k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, idx, n, k, div_magic(k), c);
-  return 1;
-}
-int launch_scatter_u32(const u32 *v, const u32 *idx, u64 n, u32 *out, cudaStream_t st) {
-  if (n == 0) return 0;
-  k_scatter_u32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, idx, n, out);
-  return 1;
-}
-
 // SequenceOcupationList::deviation (SequenceOcupationList.cpp:20-31).  t_len = length*len_ratio and
 // t_pos = length*pos_ratio are the query's (the relation is asymmetric).
 __device__ __forceinline__ double deviation(u32 ec, u32 el, u32 c, u32 len, double t_len, double t_pos) {
@@ -261,35 +146,24 @@ __device__ __forceinline__ int quotient_vs_one(u32 d, const Thresh &th) {
   return q > 1.0 ? 0 : (q == 1.0 ? 2 : 1);
 }
 
-// Two data layouts.  Indirect (single GPU): srank[i] is the processing rank, centers/lengths are gathered from the
-// rank-ordered arrays and the owner is stored at parent[rank].  Direct (multi-GPU stages): sc/slen/sxm are already
-// in sorted order, srank[i] is the id to report (global rank) and the owner is stored at owner[i].
+// srank[i] is the fragment's index in the pass's working list (single GPU: the processing rank; multi-GPU: the position
+// in [own fragments ++ halo] / in arrival order); centers/lengths are gathered from the list-ordered cl_r and the owner is
+// stored at parent[index].
 __device__ __forceinline__ void load_elem(const MatchArgs &a, u32 pos, u32 &r, u32 &c, u32 &len, bool &xm) {
   r = a.srank[pos];
-  if (a.direct) {
-    c = a.sc[pos];
-    len = a.slen[pos];
-    xm = a.sxm != nullptr && a.sxm[pos] != 0;
-  } else {
-    const uint2 cl = a.cl_r[r];
-    c = cl.x;
-    len = cl.y;
-    // X-matched: Y-insert without a query (commonFunctions.cpp:59); one bit per rank, set by the X pass (the 1.25 MB
-    // map of 10M fragments stays in L2, a gather of parent[r] would cost a DRAM sector)
-    xm = a.is_y && (a.xm_bytes ? a.xm_bytes[r] != 0 : (((a.xm_bits[r >> 5] >> (r & 31)) & 1u) != 0));
-  }
+  const uint2 cl = a.cl_r[r];
+  c = cl.x;
+  len = cl.y;
+  // X-matched: Y-insert without a query (commonFunctions.cpp:59); one bit per rank, set by the X pass (the 1.25 MB
+  // map of 10M fragments stays in L2, a gather of parent[r] would cost a DRAM sector)
+  xm = a.is_y && (a.xm_bytes ? a.xm_bytes[r] != 0 : (((a.xm_bits[r >> 5] >> (r & 31)) & 1u) != 0));
 }
-__device__ __forceinline__ void store_owner(const MatchArgs &a, u32 pos, u32 r, u32 v) {
-  if (a.direct) {
-    a.owner[pos] = v;
-  } else {
-    a.parent[r] = v;
-    if (!a.is_y && v != RK_NONE32) atomicOr(&a.xm_bits[r >> 5], 1u << (r & 31));
-  }
+__device__ __forceinline__ void store_owner(const MatchArgs &a, u32 r, u32 v) {
+  a.parent[r] = v;
+  if (!a.is_y && v != RK_NONE32) atomicOr(&a.xm_bits[r >> 5], 1u << (r & 31));
 }
-// "no match" is stored by the X pass only: in the Y pass parent[] already holds the X result (indirect), and the
-// direct owner[] array is pre-filled with NONE by the launcher.
-__device__ __forceinline__ bool stores_none(const MatchArgs &a) { return !a.is_y && !a.direct; }
+// "no match" is stored by the X pass only: in the Y pass parent[] already holds the X result (multi-GPU: NONE).
+__device__ __forceinline__ bool stores_none(const MatchArgs &a) { return !a.is_y; }
 
 constexpr int MT_HEADS = 256;           // a CTA stages 256 positions + 32 of halo; warp w owns the segments whose head
 constexpr int MT_TILE = MT_HEADS + 32;  // lies in positions [32w, 32w+32) — they end before 32w+64 (the warp's window)
@@ -476,18 +350,18 @@ __global__ void __launch_bounds__(MT_HEADS, RK_MT_MINB) k_match_small(MatchArgs 
   }
 
   // phase 3 (a fragment that does not query keeps what it has: X-matched in the Y pass; length 0 gets "none")
-  const bool y_or_direct = !stores_none(a);
-  if (actA && !(y_or_direct && bnA.x == NO_BUCKET)) {
+  const bool y_pass = !stores_none(a);
+  if (actA && !(y_pass && bnA.x == NO_BUCKET)) {
     const u32 hit = candA & insA;
     u32 owner = RK_NONE32;
     if (hit) owner = s_rank[wb + ((hit & (hit - 1)) == 0 ? (u32)__ffs(hit) - 1 : best_of(hit, win, clA.x, clA.y, a.len_ratio, a.pos_ratio))];
-    if (hit || !y_or_direct) store_owner(a, bs + eA, s_rank[eA], owner);
+    if (hit || !y_pass) store_owner(a, s_rank[eA], owner);
   }
-  if (actB && !(y_or_direct && bnB.x == NO_BUCKET)) {
+  if (actB && !(y_pass && bnB.x == NO_BUCKET)) {
     const unsigned long long hit = candB & (((unsigned long long)insB << 32) | insA);
     u32 owner = RK_NONE32;
     if (hit) owner = s_rank[wb + ((hit & (hit - 1)) == 0 ? (u32)__ffsll((long long)hit) - 1 : best_of(hit, win, clB.x, clB.y, a.len_ratio, a.pos_ratio))];
-    if (hit || !y_or_direct) store_owner(a, bs + eB, s_rank[eB], owner);
+    if (hit || !y_pass) store_owner(a, s_rank[eB], owner);
   }
 }
 
@@ -627,8 +501,8 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
         pending &= ~((2u << L) - 1u);  // lanes <= L are final
       }
       if (valid && !xm) {
-        if (best != RK_NONE32) store_owner(a, q, r, best);
-        else if (!a.is_y || a.direct) store_owner(a, q, r, RK_NONE32);  // also clears a tier-1 partial result
+        if (best != RK_NONE32) store_owner(a, r, best);
+        else if (!a.is_y) store_owner(a, r, RK_NONE32);  // the X pass stores "none" for every fragment it owns
       }
       __syncwarp();  // entry stores of this chunk are read by every lane in the next one
       // stable compaction once half of the list is dead
@@ -663,8 +537,7 @@ __global__ void __launch_bounds__(128) k_match_long(MatchArgs a) {
 int launch_match(const MatchArgs &a, cudaStream_t st) {
   if (a.m == 0) return 0;
   cudaMemsetAsync(a.work_count, 0, 2 * sizeof(u32), st);
-  if (!a.direct && !a.is_y) cudaMemsetAsync(a.xm_bits, 0, ((size_t)a.m + 31) / 32 * sizeof(u32), st);
-  if (a.direct) cudaMemsetAsync(a.owner, 0xFF, (size_t)a.m * sizeof(u32), st);
+  if (!a.is_y) cudaMemsetAsync(a.xm_bits, 0, ((size_t)a.m + 31) / 32 * sizeof(u32), st);
   {
     KScope ks(KID_MATCH_SMALL, st, a.m);
     k_match_small<<<(a.m + MT_HEADS - 1) / MT_HEADS, MT_HEADS, 0, st>>>(a);

@@ -175,21 +175,12 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u
                 uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x = HistOut{nullptr, 0, 0},
                 HistOut hist_y = HistOut{nullptr, 0, 0}, u32 *gfidx_r = nullptr, u32 own_bit = 0);
 
-int launch_keys_direct(u32 m, Geometry g, const u32 *xs_r, const u32 *ys_r, const u32 *len_r, const u8 *flags_r,
-                       const u32 *link_x, const u32 *link_y, u32 *cx, u32 *cy, u32 *kx, u32 *ky, cudaStream_t st);
-int launch_or_words(u32 *dst, const u32 *src, u64 n, cudaStream_t st);
-// rows of k <= 8 u32 words: interleave columns, gather rows by index, unpack (optionally permuted) rows to columns
-int launch_interleave(const u32 *const *cols, u64 n, int k, u32 *rows, cudaStream_t st);
-int launch_gather_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *out, cudaStream_t st);
-int launch_unpack_rows(const u32 *rows, const u32 *idx, u64 n, int k, u32 *const *cols, cudaStream_t st);
-int launch_scatter_u32(const u32 *v, const u32 *idx, u64 n, u32 *out, cudaStream_t st);
-
 // K3: one axis pass of generate_fragment_groups.  is_y: fragments with parent != NONE insert unconditionally.
 struct MatchArgs {
   const u32 *skey;   // sorted super-bucket keys
-  const u32 *srank;  // rank of the fragment at each sorted position
-  const uint2 *cl_r; // {center on this axis, length}, rank order
-  u32 *parent;       // rank-indexed; X pass writes every entry, Y pass fills unmatched ones
+  const u32 *srank;  // index (in the pass's working list) of the fragment at each sorted position
+  const uint2 *cl_r; // {center on this axis, length}, list order
+  u32 *parent;       // list-indexed; X pass writes every entry, Y pass fills unmatched ones
   u32 *xm_bits;      // one bit per rank: matched in the X pass (written by the X pass, read by the Y pass)
   u32 m;
   u32 max_index;     // axis max_index
@@ -202,17 +193,12 @@ struct MatchArgs {
   u32 *err;
   int key_shift;       // segments are runs of equal (skey >> key_shift); multi-GPU X pass: bit 0 = "own fragment, not halo"
   const u8 *xm_bytes;  // Y pass, when set: one byte per rank instead of the xm_bits map (multi-GPU: the flags travel as bytes)
-  // direct layout (multi-GPU stages): inputs already in sorted order, result per sorted position
-  int direct;
-  const u32 *sc, *slen;
-  const u8 *sxm;
-  u32 *owner;
 };
 int launch_match(const MatchArgs &a, cudaStream_t st);
 
 // K4: roots, group ids.
 u64 forest_work_bytes(u32 m);
-// lo/cnt: resolve only ranks [lo, lo+cnt) of a parent array of m entries (multi-GPU: the rank's own slice)
+// lo/cnt: resolve only ranks [lo, lo+cnt) of a parent array of m entries
 int launch_forest(const u32 *parent, u32 m, u32 *gid_rank, u32 *n_groups, void *work, cudaStream_t st, u32 lo = 0,
                   u32 cnt = 0xFFFFFFFFu, HistOut hist = HistOut{nullptr, 0, 0});
 
@@ -229,7 +215,7 @@ struct OrderArgs {
   const u32 *sgid;    // sorted gids
   const u32 *srank;   // rank at each sorted position
   const uint4 *hfi_r; // single GPU: {h, file index, identity bits, 0} by rank (gathered through srank)
-  // direct layout (srank == nullptr, multi-GPU stages): the three arrays are already in gid-sorted order
+  // direct layout (srank == nullptr, rk_sort_members): the three arrays are already in gid-sorted order
   const u32 *h;
   const u32 *fidx_r;
   const float *identity_r;
@@ -305,6 +291,14 @@ int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st);
 
 // sort_groups as a function of (groups, diag_func): h = |y - d| per member, member index, zero identity (sol.cu)
 int launch_member_keys(const u64 *y, const u64 *d, u32 m, u32 *h, u32 *idx, float *zero, u32 *err, cudaStream_t st);
+
+// K8: per-group statistics over the output arrays (same layout as rk_group_stats of include/rk_b200.h)
+struct rk_group_stats_dev {
+  u32 count, x_lo, x_hi, y_lo, y_hi, first_line;
+  double mean_identity, multiplicity;
+};
+int launch_group_stats(const u32 *out_order, const u32 *out_gid, const float *out_identity, const uint4 *rec4, u32 m, u32 n_groups,
+                       rk_group_stats_dev *st, cudaStream_t stream);
 
 u64 order_scratch_bytes(u64 m);
 void order_carve(OrderArgs &a, void *scratch, u64 m);  // sets packed .. worklist, work_cap

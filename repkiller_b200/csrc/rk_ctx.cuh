@@ -80,7 +80,7 @@ struct rk_ctx {
   cudaEvent_t ev[RK_NSTAGES + 2];
   rk::Profiler prof;
 
-  // multi-GPU stage calls (rk_st_*): own counters and a grow-only scratch area
+  // calls on caller data (rk_sort_members): own counters and a grow-only scratch area
   rk::Counters *st_cnt = nullptr;
   void *st_scratch = nullptr;
   rk::u64 st_scratch_bytes = 0;
@@ -92,6 +92,11 @@ struct rk_ctx {
   char *h_text[2] = {nullptr, nullptr};  // alternating: a chunk stays valid while the next one is produced
   rk::u64 h_text_bytes[2] = {0, 0};
   int h_text_next = 0;
+
+  // K8 per-group statistics: device array + pinned host mirror (grow-only)
+  void *d_stats = nullptr, *h_stats = nullptr;
+  rk::u64 stats_cap = 0, h_stats_cap = 0;
+  rk::u64 n_groups_last = 0;
 
   bool loaded = false;
   rk::u64 n = 0;

@@ -323,13 +323,10 @@ def _killer(n):
 
 
 def test_group_order_is_libstdcxx_sort_for_every_size_and_pattern(ctx):
-    """K5b alone through rk_st_order: groups of every size class (<= 16 stable, 17..128 and 129..1024 by one warp,
-    > 1024 split in global memory) with keys that are random, heavily tied, constant, sorted, reversed, organ-pipe
-    and median-of-three killers (depth limit -> heap sort) must come out in the order std::sort leaves them
-    (oracle: rko_std_sort_by_key runs the real std::sort)."""
-    import torch
-    from repkiller_b200.dist import CudaStages
-    st = CudaStages(ctx, torch.device("cuda:0"))
+    """K5b alone through rk_sort_members (sort_groups as a function of its arguments): groups of every size class (<= 16
+    stable, 17..128 and 129..1024 by one warp, > 1024 split in global memory) with keys that are random, heavily tied,
+    constant, sorted, reversed, organ-pipe and median-of-three killers (depth limit -> heap sort) must come out in the
+    order std::sort leaves them (oracle: rko_std_sort_by_key runs the real std::sort)."""
     rng = np.random.default_rng(5)
     sizes = list(range(1, 40)) + [63, 64, 65, 100, 127, 128, 129, 130, 200, 255, 256, 257, 500, 1000, 1023, 1024, 1025, 1026,
                                    1500, 2047, 2048, 2049, 3000, 5000, 9000, 20000]
@@ -351,30 +348,41 @@ def test_group_order_is_libstdcxx_sort_for_every_size_and_pattern(ctx):
             hs.append(np.asarray(fn(n), dtype=np.int64))
             gids.append(np.full(n, g, np.int64))
             g += 1
-    h = np.concatenate(hs).astype(np.uint32)
+    h64 = np.concatenate(hs).astype(np.uint64)
     gid = np.concatenate(gids).astype(np.uint32)
-    m = h.shape[0]
-    fidx = rng.permutation(m).astype(np.uint32)                 # any payload: it must follow its member
-    ident = rng.random(m, dtype=np.float32)
-    dev = torch.device("cuda:0")
-    t = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
-    o, og, rep, idn = st.order(t(gid), t(h), t(fidx), t(ident), True)
-    torch.cuda.synchronize()
-    o = o.cpu().numpy().view(np.uint32)
-    og = og.cpu().numpy().view(np.uint32)
-    rep, idn = rep.cpu().numpy(), idn.cpu().numpy()
-    assert_same("gid", og, gid)
+    # h = |y - d|: half of the members get their key from above the table value, half from below
+    d = rng.integers(1 << 30, 1 << 31, h64.shape[0]).astype(np.uint64)
+    y = np.where(rng.integers(0, 2, h64.shape[0]) == 0, d + h64, d - h64)
+    perm = ctx.sort_members(gid, y, d)
     pos = 0
-    h64 = h.astype(np.uint64)
     for hh in hs:
         n = hh.shape[0]
         idx = np.arange(pos, pos + n, dtype=np.uint32)
         want = O.std_sort_by_key(idx, h64) if n > 1 else idx
-        msg = first_diff(o[pos:pos + n], fidx[want])
+        msg = first_diff(perm[pos:pos + n], want)
         assert msg is None, f"group of {n} at {pos}: {msg}"
-        assert np.array_equal(idn[pos:pos + n].view(np.uint32), ident[want].view(np.uint32))
-        assert np.array_equal(rep[pos:pos + n], np.r_[0 if n == 1 else 1, np.full(n - 1, 2)].astype(np.uint8))
         pos += n
+
+
+@pytest.mark.parametrize("wl", ["c1", "dense", "c3"])
+def test_group_statistics_match_oracle_reduction(ctx, wl):
+    """K8 (north_star kernel 5): count, spans and first line exact; mean identity and multiplicity within 1e-6 relative
+    of the oracle's sequential reduction over the reference's groups."""
+    from dataclasses import replace
+    w = {"c1": gen.WORKLOADS["c1"],
+         "dense": replace(gen.WORKLOADS["c1"], n=60_000, lx=400_000, ly=300_000, families=40, p_rep=0.6, seed=31),
+         "c3": gen.scaled(gen.WORKLOADS["c3"], 300_000)}[wl]
+    rec = gen.generate(w)
+    res, g = check_against_oracle(ctx, rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio, stages=False)
+    got = ctx.group_statistics()
+    want = O.group_statistics(rec, g)
+    assert got.shape[0] == g.n_groups
+    for f in ("count", "x_lo", "x_hi", "y_lo", "y_hi", "first_line"):
+        assert_same(f, got[f], want[f])
+    for f in ("mean_identity", "multiplicity"):
+        rel = np.abs(got[f] - want[f]) / np.maximum(np.abs(want[f]), 1e-300)
+        assert rel.max() <= 1e-6, (f, float(rel.max()))   # tolerance of BASELINE.json's north_star
+    assert got["count"].sum() == g.n_kept and got["count"].max() > 16
 
 
 def test_two_giant_families_small_input(ctx):
