@@ -322,12 +322,26 @@ def ours(args):
         st = ctx.load(dev.data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=False)
 
-    def step_e2e():   # pinned host records in, pinned host result out, through the same two C-ABI calls
+    # e2e: pinned HOST buffers in, pinned host result out, through the C-ABI calls a C++ caller makes.  Single GPU: the
+    # compact ingest the drop-in CLI uses (rk_load_packed: the parser fills {xStart, yStart, length, ident} + strand +
+    # {xEnd, yEnd, score, similarity}, 33 B per fragment) — and, reported beside it, the 109-byte record ingest
+    # (rk_load_aos).  N > 1: rk_dist_load_aos takes the records.
+    packed = None
+    if do_e2e and not partitioned:
+        from repkiller_b200.frags import FRAG_DTYPE
+        k4, sd, r4 = capi.pack_records(host.numpy().view(FRAG_DTYPE))
+        packed = [torch.from_numpy(a).pin_memory() for a in (k4, sd, r4)]
+
+    def step_e2e():
         if partitioned:
             st = ctx.dist_load(host.data_ptr(), n, lo, lx1, ly1)
             return st, ctx.dist_group(w.len_ratio, w.pos_ratio, host_result=True, copy=False, timing=True)
-        st = ctx.load(host.data_ptr(), lx1, ly1, n=n)
+        st = ctx.load_packed(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(), lx1, ly1, n=n)
         return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=True, copy=False)   # pinned result buffers, as a C caller sees them
+
+    def step_e2e_aos():
+        st = ctx.load(host.data_ptr(), lx1, ly1, n=n)
+        return st, ctx.group(w.len_ratio, w.pos_ratio, host_result=True, copy=False)
 
     def timed(fn, k):
         barrier()
@@ -371,8 +385,13 @@ def ours(args):
             for _ in range(max(1, args.warmup // 2)):
                 step_e2e()
         ms_e2e, last_e = timed(step_e2e, args.steps)
+        ms_e2e_aos = None
+        if not partitioned:
+            with torch.cuda.stream(stream):
+                step_e2e_aos()
+            ms_e2e_aos, _ = timed(step_e2e_aos, args.steps)
     else:
-        ms_e2e = float("nan")
+        ms_e2e, ms_e2e_aos = float("nan"), None
 
     # Checksum of the whole output (position-dependent, 64 bit), outside the timed regions.  N > 1: the sum over the ranks'
     # ranges of lines, and beside it the checksum of the SAME comparison grouped by rank 0 alone on its one GPU
@@ -446,8 +465,14 @@ def ours(args):
                                      "independent sequence pairs per rank, no data-path collective") if world > 1 else "single GPU"},
             "checksum": checksum, "checksum_same_comparison_on_1_gpu": checksum_1gpu,
             "checksum_match": (checksum == checksum_1gpu) if checksum_1gpu is not None else None,
-            "e2e": {"value": e2e_value if do_e2e else None, "unit": UNIT, "h2d_bytes_per_step": int(n * 109), "d2h_bytes_per_step": int(lines * 13 + 40),
-                    "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value if do_e2e else None, "unit": UNIT,
+                    "h2d_bytes_per_step": int(n * 109) if partitioned else int(n * 33), "d2h_bytes_per_step": int(lines * 13 + 40),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "ingest": "rk_dist_load_aos: 109-byte records" if partitioned else
+                              "rk_load_packed: 33 B per fragment (what the drop-in CLI's parser hands over)",
+                    "record_ingest": None if ms_e2e_aos is None else {
+                        "ms_per_step": ms_e2e_aos / args.steps, "value": n_total * args.steps / (ms_e2e_aos / 1e3),
+                        "h2d_bytes_per_step": int(n * 109), "ingest": "rk_load_aos: 109-byte FragFile records"}},
             # kernels of this library launched inside timed region 1 (the C ABI counts them per call); the partitioned
             # path reports its timed launch groups (torch's own kernels and NCCL are not counted)
             # (partitioned: rank 0's kernels; NCCL's own kernels are not counted)

@@ -103,6 +103,14 @@ int rk_set_stream(rk_ctx *ctx, void *cuda_stream);
 int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags,
                 rk_load_stats *stats);
 
+/* The same as rk_load_aos from the compact form a CSV parser can fill directly (33 B per fragment instead of 109 B over
+ * PCIe): key4 = {xStart, yStart, length, ident} as four uint32 per fragment, strand = one byte per fragment, rest4 =
+ * {xEnd, yEnd, score, similarity bits} as four uint32 per fragment (only rk_format_lines reads it; NULL when the caller
+ * writes the output itself).  All host or all device memory; every value must fit in 32 bits (the reference's uint64
+ * fields: use rk_load_aos otherwise).  Synchronous. */
+int rk_load_packed(rk_ctx *ctx, const uint32_t *key4, const uint8_t *strand, const uint32_t *rest4, uint64_t n, uint64_t seqx_len,
+                   uint64_t seqy_len, unsigned flags, rk_load_stats *stats);
+
 /* Replaces generate_fragment_groups + generate_diagonal_func + sort_groups
  * (src/commonFunctions.cpp:41-80,161-177,148-159; call sites src/repkiller.cpp:84-91) for one
  * (len_ratio, pos_ratio) pair.  Both ratios must be > 0 (src/commonFunctions.cpp:26-27).  Synchronous. */

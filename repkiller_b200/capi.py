@@ -21,7 +21,7 @@ STAGES = ["h2d", "decode", "ranksort", "keys", "xsort", "ysort", "xmatch", "ymat
 NSTAGES = len(STAGES)
 
 # every symbol include/rk_b200.h declares
-SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_group", "rk_sort_groups", "rk_host_alloc", "rk_host_free",
+SYMBOLS = ["rk_create", "rk_create_error", "rk_destroy", "rk_last_error", "rk_set_stream", "rk_load_aos", "rk_load_packed", "rk_group", "rk_sort_groups", "rk_host_alloc", "rk_host_free",
            "rk_diagonal_func", "rk_format_lines", "rk_debug_fetch", "rk_profile_enable", "rk_profile_read", "rk_sort_pairs_work_bytes", "rk_sort_pairs", "rk_version",
            "rk_gen_workload", "rk_sort_members", "rk_group_statistics", "rk_sol_create", "rk_sol_destroy", "rk_sol_insert", "rk_sol_get_associated", "rk_sol_last_error",
            # one comparison over several GPUs
@@ -85,6 +85,7 @@ def load_library():
     L.rk_last_error.restype = C.c_char_p
     L.rk_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.rk_load_aos.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(_LoadStats)]
+    L.rk_load_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(_LoadStats)]
     L.rk_group.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint, C.POINTER(_Result)]
     L.rk_diagonal_func.argtypes = [C.c_void_p, C.c_void_p]
     L.rk_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64]
@@ -201,6 +202,24 @@ class Context:
             assert n is not None
         st = _LoadStats()
         self._check(self._L.rk_load_aos(self._h, C.c_void_p(ptr), n, seqx_len, seqy_len, F_TIMING if timing else 0, C.byref(st)))
+        return LoadStats(st.n_loaded, st.n_kept, st.vsize, {STAGES[i]: st.ms_stage[i] for i in range(NSTAGES)}, st.ms_device,
+                         st.n_launches)
+
+    def load_packed(self, key4, strand, rest4, seqx_len: int, seqy_len: int, n: int | None = None, timing: bool = True) -> LoadStats:
+        """The compact ingest (rk_load_packed): numpy arrays key4 [n,4] u32, strand [n] u8, rest4 [n,4] u32 or None — or int
+        pointers (host or device) with n given."""
+        if isinstance(key4, np.ndarray):
+            k, s_ = np.ascontiguousarray(key4, dtype=np.uint32), np.ascontiguousarray(strand, dtype=np.uint8)
+            r = np.ascontiguousarray(rest4, dtype=np.uint32) if rest4 is not None else None
+            n = s_.shape[0]
+            self._keep = (k, s_, r)
+            pk, ps, pr = k.ctypes.data, s_.ctypes.data, (r.ctypes.data if r is not None else None)
+        else:
+            pk, ps, pr = int(key4), int(strand), (int(rest4) if rest4 else None)
+            assert n is not None
+        st = _LoadStats()
+        self._check(self._L.rk_load_packed(self._h, C.c_void_p(pk), C.c_void_p(ps), C.c_void_p(pr) if pr else None, n, seqx_len, seqy_len,
+                                           F_TIMING if timing else 0, C.byref(st)))
         return LoadStats(st.n_loaded, st.n_kept, st.vsize, {STAGES[i]: st.ms_stage[i] for i in range(NSTAGES)}, st.ms_device,
                          st.n_launches)
 
@@ -348,6 +367,18 @@ def _groups_of(r: "_Result", host_result: bool, copy: bool) -> Groups:
     return Groups(m, r.n_groups, arr(r.order, np.uint32), arr(r.gid, np.uint32), arr(r.repval, np.uint8), arr(r.identity, np.float32),
                   {"order": r.d_order, "gid": r.d_gid, "repval": r.d_repval, "identity": r.d_identity},
                   {STAGES[i]: r.ms_stage[i] for i in range(NSTAGES)}, r.ms_device, r.n_launches)
+
+
+def pack_records(rec: np.ndarray):
+    """(key4, strand, rest4) of 109-byte FragFile records for Context.load_packed; every value must fit in 32 bits"""
+    for f in ("xStart", "yStart", "length", "ident", "xEnd", "yEnd", "score"):
+        if rec.shape[0] and int(rec[f].max()) >> 32:
+            raise ValueError(f"{f} does not fit in 32 bits: use Context.load (rk_load_aos)")
+    key4 = np.stack([rec["xStart"], rec["yStart"], rec["length"], rec["ident"]], axis=1).astype(np.uint32)
+    rest4 = np.stack([rec["xEnd"].astype(np.uint32), rec["yEnd"].astype(np.uint32), rec["score"].astype(np.uint32),
+                      rec["similarity"].view(np.uint32)], axis=1)
+    strand = rec["strand"].view(np.uint8).copy()
+    return np.ascontiguousarray(key4), strand, np.ascontiguousarray(rest4)
 
 
 def dist_unique_id() -> bytes:

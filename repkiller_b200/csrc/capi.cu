@@ -33,7 +33,7 @@ thread_local Profiler *tl_prof = nullptr;
 namespace {
 
 // carve the workspace for n records; returns bytes needed.  With base == nullptr only sizes are computed.
-u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
+u64 carve(rk_ctx *c, u8 *base, u64 n, u64 stage_bytes, u64 lxw, u64 lyw) {
   u64 off = 0;
   auto take = [&](u64 bytes) -> u8 * {
     u8 *p = base ? base + off : nullptr;
@@ -42,7 +42,7 @@ u64 carve(rk_ctx *c, u8 *base, u64 n, bool need_aos, u64 lxw, u64 lyw) {
   };
   const u64 n1 = n ? n : 1;
   c->d_cnt = (Counters *)take(sizeof(Counters));
-  c->d_aos = need_aos ? take(align_up(n1 * RK_FRAG_BYTES, 16) + 16) : nullptr;
+  c->d_aos = stage_bytes ? take(stage_bytes) : nullptr;  // host records staged on the device (109 B or 33 B each)
   c->rec4 = (uint4 *)take(n1 * 32);
   c->key0 = (u32 *)take(n1 * 4);
   c->identity_r = (float *)take(n1 * 4);
@@ -280,10 +280,27 @@ int rk_set_stream(rk_ctx *ctx, void *cuda_stream) {
   return RK_OK;
 }
 
-int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags,
-                rk_load_stats *stats) {
-  if (!ctx) return RK_ERR_ARG;
-  if (!frags && n) return fail(ctx, RK_ERR_ARG, "null record pointer");
+}  // extern "C"
+
+namespace {
+
+bool is_device_pointer(const void *p) {
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, p) == cudaSuccess) return pa.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  return false;
+}
+
+// The two ingest forms: 109-byte records (rk_load_aos) or the compact arrays of rk_load_packed.
+struct LoadSource {
+  const void *aos = nullptr;
+  const void *key4 = nullptr, *strand = nullptr, *rest4 = nullptr;
+  bool packed() const { return aos == nullptr; }
+};
+
+// FragmentsDatabase's constructor after parsing (src/FragmentsDatabase.cpp:84-100) on the device: K1, the processing
+// order (K2a), the occupation-list buckets of both axes (K2 keys, K2b/c) and generate_diagonal_func per fragment (K5a).
+int load_common(rk_ctx *ctx, const LoadSource &src, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags, rk_load_stats *stats) {
   if (n >= 0xFFFFFFF0ull) return fail(ctx, RK_ERR_ARG, "more than 2^32-16 records per context; partition the input");
   if (seqx_len >= (1ull << 32) || seqy_len >= (1ull << 32))
     return fail(ctx, RK_ERR_RANGE, "sequence length does not fit in 32 bits");
@@ -292,20 +309,20 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   ctx->loaded = false;
   ctx->have_group = false;
 
-  bool on_device = false;
-  if (n) {
-    cudaPointerAttributes pa;
-    if (cudaPointerGetAttributes(&pa, frags) == cudaSuccess) on_device = pa.type == cudaMemoryTypeDevice;
-    else cudaGetLastError();
-  }
-  if (on_device && ((uintptr_t)frags & 15)) return fail(ctx, RK_ERR_ARG, "device record pointer must be 16-byte aligned");
+  const void *first = src.packed() ? src.key4 : src.aos;
+  const bool on_device = n ? is_device_pointer(first) : false;
+  if (on_device && (((uintptr_t)first & 15) || (src.rest4 && ((uintptr_t)src.rest4 & 15))))
+    return fail(ctx, RK_ERR_ARG, "device record pointers must be 16-byte aligned");
+  if (src.packed() && n && (on_device != is_device_pointer(src.strand) || (src.rest4 && on_device != is_device_pointer(src.rest4))))
+    return fail(ctx, RK_ERR_ARG, "the arrays of rk_load_packed must all be host or all be device memory");
 
   const Geometry g = make_geometry(seqx_len, seqy_len);
   const u64 lxw = (2ull * g.nbx + 31) / 32 + 1, lyw = (2ull * g.nby + 31) / 32 + 1;
 
-  // (re)carve the workspace
-  const bool need_aos = !on_device;
-  const u64 need = carve(ctx, nullptr, n, need_aos, lxw, lyw);
+  // (re)carve the workspace; the staging area holds the host records on the device: 109 B or 33 B per record
+  const u64 stage_bytes = on_device ? 0 : (src.packed() ? align_up(n * 16, 256) + align_up(n, 256) + (src.rest4 ? align_up(n * 16, 256) : 0)
+                                                        : align_up(n * RK_FRAG_BYTES, 16) + 16);
+  const u64 need = carve(ctx, nullptr, n, stage_bytes, lxw, lyw);
   if (need > ctx->arena_bytes) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->arena) cudaFree(ctx->arena);
@@ -318,7 +335,7 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
     }
     ctx->arena_bytes = need;
   }
-  carve(ctx, (u8 *)ctx->arena, n, need_aos, lxw, lyw);
+  carve(ctx, (u8 *)ctx->arena, n, stage_bytes, lxw, lyw);
   ctx->link_x_words = lxw;
   ctx->link_y_words = lyw;
   ctx->n = n;
@@ -330,12 +347,27 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   cudaStream_t st = ctx->stream;
   cudaEvent_t *ev = ctx->ev;
   CK(cudaEventRecord(ev[0], st));
-  const u8 *aos = (const u8 *)frags;
+  const u8 *aos = (const u8 *)src.aos;
+  const uint4 *key4 = (const uint4 *)src.key4, *rest4 = (const uint4 *)src.rest4;
+  const u8 *strand = (const u8 *)src.strand;
   if (!on_device && n) {
-    CK(cudaMemcpyAsync(ctx->d_aos, frags, n * RK_FRAG_BYTES, cudaMemcpyHostToDevice, st));
-    aos = ctx->d_aos;
+    if (src.packed()) {
+      u8 *p = ctx->d_aos;
+      CK(cudaMemcpyAsync(p, src.key4, n * 16, cudaMemcpyHostToDevice, st));
+      key4 = (const uint4 *)p, p += align_up(n * 16, 256);
+      CK(cudaMemcpyAsync(p, src.strand, n, cudaMemcpyHostToDevice, st));
+      strand = p, p += align_up(n, 256);
+      if (src.rest4) {  // only rk_format_lines reads these: the copy runs while the kernels below work
+        CK(cudaMemcpyAsync(p, src.rest4, n * 16, cudaMemcpyHostToDevice, st));
+        rest4 = (const uint4 *)p;
+      }
+    } else {
+      CK(cudaMemcpyAsync(ctx->d_aos, src.aos, n * RK_FRAG_BYTES, cudaMemcpyHostToDevice, st));
+      aos = ctx->d_aos;
+    }
   }
   ctx->aos_dev = aos;
+  ctx->pk_key = key4, ctx->pk_rest = rest4, ctx->pk_strand = strand;
   CK(cudaEventRecord(ev[1], st));
   CK(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), st));
   CK(cudaMemsetAsync(ctx->link_x, 0, lxw * 4, st));
@@ -343,8 +375,12 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
   u64 launches = 0;
   CK(cudaMemsetAsync(ctx->prehist, 0, 3 * 4 * 256 * 4, st));
   auto hist_of = [&](int which, int bits) { return HistOut{ctx->prehist + which * 1024, (bits + 7) / 8, bits}; };
-  launches += launch_decode(aos, n, g, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->key0, ctx->link_x, ctx->link_y,
-                            &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st, ctx->rec4, hist_of(0, ctx->bits_rank));
+  if (src.packed())
+    launches += launch_decode_packed(key4, strand, n, g, ctx->key0, ctx->link_x, ctx->link_y, &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st,
+                                     ctx->rec4, hist_of(0, ctx->bits_rank));
+  else
+    launches += launch_decode(aos, n, g, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->key0, ctx->link_x, ctx->link_y,
+                              &ctx->d_cnt->n_dropped, &ctx->d_cnt->err, st, ctx->rec4, hist_of(0, ctx->bits_rank));
   CK(cudaEventRecord(ev[2], st));
   // the rank sort does not depend on the number of dropped records: they carry the largest key and sort last
   launches += launch_sort_pairs(ctx->key0, nullptr, ctx->k0_r, ctx->fidx_r, ctx->tmp_k, ctx->tmp_v, n, ctx->bits_rank, ctx->sort_work, st, &ctx->d_cnt->err,
@@ -391,6 +427,28 @@ int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, u
     }
   }
   return RK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rk_load_aos(rk_ctx *ctx, const void *frags, uint64_t n, uint64_t seqx_len, uint64_t seqy_len, unsigned flags,
+                rk_load_stats *stats) {
+  if (!ctx) return RK_ERR_ARG;
+  if (!frags && n) return fail(ctx, RK_ERR_ARG, "null record pointer");
+  LoadSource src;
+  src.aos = frags ? frags : (const void *)"";  // n == 0: any non-null marker of the AoS form
+  return load_common(ctx, src, n, seqx_len, seqy_len, flags, stats);
+}
+
+int rk_load_packed(rk_ctx *ctx, const uint32_t *key4, const uint8_t *strand, const uint32_t *rest4, uint64_t n, uint64_t seqx_len,
+                   uint64_t seqy_len, unsigned flags, rk_load_stats *stats) {
+  if (!ctx) return RK_ERR_ARG;
+  if (n && (!key4 || !strand)) return fail(ctx, RK_ERR_ARG, "null array");
+  LoadSource src;
+  src.key4 = key4, src.strand = strand, src.rest4 = rest4;
+  return load_common(ctx, src, n, seqx_len, seqy_len, flags, stats);
 }
 
 int rk_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned flags, rk_result *out) {
@@ -505,6 +563,8 @@ int rk_diagonal_func(rk_ctx *ctx, uint64_t *diag_func) {
 int rk_format_lines(rk_ctx *ctx, uint64_t first_line, uint64_t n_lines, rk_text *out) {
   if (!ctx || !out) return RK_ERR_ARG;
   if (!ctx->loaded || !ctx->have_group) return fail(ctx, RK_ERR_STATE, "rk_format_lines before rk_group");
+  if (!ctx->aos_dev && !ctx->pk_rest)
+    return fail(ctx, RK_ERR_STATE, "the database was loaded with rk_load_packed without the xEnd/yEnd/score/similarity array");
   if (first_line > ctx->m || n_lines > ctx->m - first_line) return fail(ctx, RK_ERR_ARG, "line range beyond the %u output lines", ctx->m);
   if (n_lines > RK_FORMAT_MAX_LINES) return fail(ctx, RK_ERR_ARG, "at most %llu lines per call", (unsigned long long)RK_FORMAT_MAX_LINES);
   CK(cudaSetDevice(ctx->device));
@@ -525,7 +585,8 @@ int rk_format_lines(rk_ctx *ctx, uint64_t first_line, uint64_t n_lines, rk_text 
     ctx->d_text_bytes = need;
   }
   FormatArgs fa{};
-  fa.aos = ctx->aos_dev, fa.order = ctx->out_order, fa.gid = ctx->out_gid, fa.repval = ctx->out_repval, fa.identity = ctx->out_identity;
+  fa.aos = ctx->aos_dev, fa.pk_key = ctx->pk_key, fa.pk_rest = ctx->pk_rest, fa.pk_strand = ctx->pk_strand;
+  fa.order = ctx->out_order, fa.gid = ctx->out_gid, fa.repval = ctx->out_repval, fa.identity = ctx->out_identity;
   fa.first_line = (u32)first_line, fa.n_lines = (u32)n_lines;
   fa.text = (char *)ctx->d_text;
   u32 *work = (u32 *)((u8 *)ctx->d_text + text_cap);

@@ -1,5 +1,7 @@
 #include "FragmentsDatabase.h"
 
+#include <atomic>
+
 #include <cerrno>
 #include <chrono>
 #include <cstdlib>
@@ -245,35 +247,54 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   const size_t body = size - pos;
   if (nthreads < 1 || body < (1u << 20)) nthreads = 1;
   if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
-  // pinned memory for the records (full-speed H2D) is allocated beside the parse, for min(T, bytes / 28) records: a
-  // full GECKO row has 14 non-empty fields and 13 commas, i.e. at least 30 bytes with its line end.  This is only a
-  // guess: readFragment's short-row padding also accepts rows like "Frag,5" (7 bytes), so the count is checked after
-  // the parse and the buffer is re-allocated for exactly `accepted` records when the guess was too small.
+  // The device gets the compact form (rk_load_packed: 33 B per fragment over PCIe instead of the 109-byte record): pinned
+  // memory for it is allocated beside the parse, for min(T, bytes / 28) records — a full GECKO row has 14 non-empty
+  // fields and 13 commas, i.e. at least 30 bytes with its line end.  This is only a guess: readFragment's short-row
+  // padding also accepts rows like "Frag,5" (7 bytes), so the count is checked after the parse and the buffers are
+  // re-allocated for exactly `accepted` records when the guess was too small.
   const uint64_t rows_upper = body / 28 + 1;
   cap_ = (rows_upper < total_frags ? rows_upper : total_frags) + 2;
   create_thread.join();
   if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
-  std::thread alloc_thread([this] { records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16); });
+  auto packed_bytes = [](uint64_t cap) { return cap * 33 + 64; };
+  std::thread alloc_thread([this, &packed_bytes] { packed_ = (unsigned char *)rk_host_alloc(packed_bytes(cap_)); });
   Joiner alloc_joiner{alloc_thread};
   std::vector<std::vector<FragFile>> chunks = parse_rows_parallel(data, size, pos, nthreads);
   uint64_t accepted = 0;
   for (const auto &c : chunks) accepted += c.size();
   alloc_thread.join();
   if (accepted > total_frags) throw std::runtime_error("Unexpected number of fragments");  // :99
-  if (records_ && accepted > cap_) {  // short rows: more records than bytes / 28
-    rk_host_free(records_);
-    records_ = nullptr;
-  }
-  if (!records_ && accepted > cap_) {
+  if (accepted > cap_) {  // short rows: more records than bytes / 28
+    if (packed_) rk_host_free(packed_);
     cap_ = accepted;
-    records_ = (FragFile *)rk_host_alloc(cap_ * sizeof(FragFile) + 16);
+    packed_ = (unsigned char *)rk_host_alloc(packed_bytes(cap_));
   }
-  if (!records_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
+  records_ = (FragFile *)malloc((accepted ? accepted : 1) * sizeof(FragFile));
+  if (!records_ || !packed_) throw std::runtime_error("Could not allocate memory for fragments!");  // :86
+  // records in file order (the facades hand out pointers into them) and, beside them, the compact arrays for the device:
+  // key4 = {xStart, yStart, length, ident}, rest4 = {xEnd, yEnd, score, similarity bits}, one strand byte
+  uint32_t *key4 = (uint32_t *)packed_, *rest4 = key4 + 4 * cap_;
+  unsigned char *strand = (unsigned char *)(rest4 + 4 * cap_);
+  std::atomic<bool> wide{false};  // a value beyond 32 bits: the device then takes the 109-byte records (rk_load_aos)
   {
     std::vector<std::thread> pool;
     uint64_t off = 0;
     for (auto &c : chunks) {
-      if (!c.empty()) pool.emplace_back([this, off, &c] { memcpy(records_ + off, c.data(), c.size() * sizeof(FragFile)); });
+      if (!c.empty())
+        pool.emplace_back([this, off, &c, key4, rest4, strand, &wide] {
+          memcpy(records_ + off, c.data(), c.size() * sizeof(FragFile));
+          bool w = false;
+          for (size_t k = 0; k < c.size(); ++k) {
+            const FragFile &f = c[k];
+            const uint64_t i = off + k;
+            w = w || ((f.xStart | f.yStart | f.length | f.ident | f.xEnd | f.yEnd | f.score) >> 32) != 0;
+            key4[4 * i] = (uint32_t)f.xStart, key4[4 * i + 1] = (uint32_t)f.yStart, key4[4 * i + 2] = (uint32_t)f.length, key4[4 * i + 3] = (uint32_t)f.ident;
+            rest4[4 * i] = (uint32_t)f.xEnd, rest4[4 * i + 1] = (uint32_t)f.yEnd, rest4[4 * i + 2] = (uint32_t)f.score;
+            memcpy(&rest4[4 * i + 3], &f.similarity, 4);
+            strand[i] = (unsigned char)f.strand;
+          }
+          if (w) wide = true;
+        });
       off += c.size();
     }
     for (auto &th : pool) th.join();
@@ -281,8 +302,9 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   count_ = accepted;
   const auto t2 = clk::now();
 
-  const int rc = rk_load_aos(ctx_, records_, count_, seq_manager.get_sequence_by_label(0).len,
-                             seq_manager.get_sequence_by_label(1).len, RK_F_TIMING, &load_stats_);
+  const uint64_t lx1 = seq_manager.get_sequence_by_label(0).len, ly1 = seq_manager.get_sequence_by_label(1).len;
+  const int rc = wide ? rk_load_aos(ctx_, records_, count_, lx1, ly1, RK_F_TIMING, &load_stats_)
+                      : rk_load_packed(ctx_, key4, strand, rest4, count_, lx1, ly1, RK_F_TIMING, &load_stats_);
   if (rc != RK_OK) throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(ctx_));
   const auto t3 = clk::now();
   ms_read_ = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -318,5 +340,6 @@ const std::vector<FragFile> *FragmentsDatabase::begin() const {
 
 FragmentsDatabase::~FragmentsDatabase() {
   if (ctx_) rk_destroy(ctx_);
-  if (records_) rk_host_free(records_);
+  free(records_);
+  if (packed_) rk_host_free(packed_);
 }

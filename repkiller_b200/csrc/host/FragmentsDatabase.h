@@ -20,7 +20,8 @@ bool parse_plain_float(const char *p, size_t n, float *out);
 std::vector<std::vector<FragFile>> parse_rows_parallel(const char *text, size_t size, size_t pos, unsigned nthreads);
 
 class FragmentsDatabase {
-  FragFile *records_ = nullptr;  // file order, pinned
+  FragFile *records_ = nullptr;  // file order
+  unsigned char *packed_ = nullptr;  // pinned: the compact arrays handed to rk_load_packed
   uint64_t count_ = 0, cap_ = 0;
   size_t vsize = 0;
   rk_ctx *ctx_ = nullptr;
@@ -48,7 +49,7 @@ class FragmentsDatabase {
   // processing order; the grouping functions of this repo do not need it.
   const std::vector<FragFile> *begin() const;
   const std::vector<FragFile> *end() const { return begin() + vsize - 1; }
-  const FragFile *records() const { return records_; }   // the records in file order (pinned host memory)
+  const FragFile *records() const { return records_; }   // the records in file order
   rk_ctx *ctx() const { return ctx_; }
   const rk_load_stats &load_stats() const { return load_stats_; }
   double ms_read() const { return ms_read_; }

@@ -220,6 +220,56 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const u8 *__restrict__ a
   }
 }
 
+// Compact ingest (rk_load_packed): the host parser hands over {xStart, yStart, length, ident} as four 32-bit words per
+// fragment plus one strand byte, 17 B instead of the 109-byte record (the 16 B of xEnd/yEnd/score/similarity that only
+// the output lines need travel beside them and are not touched here).  Same outputs as k_decode.
+__global__ void __launch_bounds__(256) k_decode_packed(const uint4 *__restrict__ key4, const u8 *__restrict__ strand, u64 n, Geometry g,
+                                                       DecodeOut o) {
+  __shared__ u32 s_dropped, s_err;
+  __shared__ u32 s_hist[HIST_PASSES][HIST_RADIX];
+  if (o.hist.ghist) hist_zero(s_hist);
+  if (threadIdx.x == 0) s_dropped = 0, s_err = 0;
+  __syncthreads();
+  u32 dropped = 0, err = 0;
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 i = base + threadIdx.x;
+    u32 k0 = 0;
+    if (i < n) {
+      const uint4 k = key4[i];
+      k0 = emit_fragment(i, k.x, k.y, k.z, k.w, strand[i], g, o, dropped, err);
+    }
+    if (o.hist.ghist) hist_add(s_hist, k0, i < n, o.hist);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    dropped += __shfl_xor_sync(0xFFFFFFFFu, dropped, d);
+    err |= __shfl_xor_sync(0xFFFFFFFFu, err, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (dropped) atomicAdd(&s_dropped, dropped);
+    if (err) atomicOr(&s_err, err);
+  }
+  __syncthreads();
+  if (o.hist.ghist) hist_flush(s_hist, o.hist);
+  if (threadIdx.x == 0) {
+    if (s_dropped) atomicAdd(o.n_dropped, s_dropped);
+    if (s_err) atomicOr(o.err, s_err);
+  }
+}
+
+int launch_decode_packed(const uint4 *key4, const u8 *strand, u64 n, Geometry g, u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped,
+                         u32 *err, cudaStream_t st, uint4 *rec4, HistOut hist) {
+  if (n == 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 grid = (n + 255) / 256;
+  if (grid > (u64)sms * 8) grid = (u64)sms * 8;
+  DecodeOut o{nullptr, nullptr, nullptr, rec4, nullptr, nullptr, key0, link_x, link_y, n_dropped, err, hist, 0u};
+  KScope ks(KID_DECODE, st, n);
+  k_decode_packed<<<(unsigned)grid, 256, 0, st>>>(key4, strand, n, g, o);
+  return 1;
+}
+
 // per-device opt-in to the 84 KB of dynamic shared memory (called by rk_create for the context's device)
 cudaError_t decode_init_device() {
   return cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES);

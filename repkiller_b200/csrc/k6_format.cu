@@ -25,21 +25,43 @@ __device__ __forceinline__ u64 ldg_u64_unaligned(const u8 *p) {  // records are 
   return v;
 }
 
+struct LineFields {  // what one output line prints of its record
+  u64 xs, ys, xe, ye, len, score, ident;
+  u32 sim_bits;
+  char strand;
+};
+__device__ __forceinline__ LineFields load_fields(const FormatArgs &a, u32 fidx) {
+  LineFields f;
+  if (a.aos) {
+    const u8 *rec = a.aos + (u64)fidx * FRAG_BYTES;
+    f.xs = ldg_u64_unaligned(rec + OFF_XSTART), f.ys = ldg_u64_unaligned(rec + OFF_YSTART);
+    f.xe = ldg_u64_unaligned(rec + OFF_XEND), f.ye = ldg_u64_unaligned(rec + OFF_YEND);
+    f.len = ldg_u64_unaligned(rec + OFF_LENGTH), f.score = ldg_u64_unaligned(rec + OFF_SCORE), f.ident = ldg_u64_unaligned(rec + OFF_IDENT);
+    f.sim_bits = (u32)rec[OFF_SIMILARITY] | ((u32)rec[OFF_SIMILARITY + 1] << 8) | ((u32)rec[OFF_SIMILARITY + 2] << 16) |
+                 ((u32)rec[OFF_SIMILARITY + 3] << 24);
+    f.strand = (char)rec[OFF_STRAND];
+  } else {  // compact ingest: two 16-byte words and a byte
+    const uint4 k = a.pk_key[fidx], r = a.pk_rest[fidx];
+    f.xs = k.x, f.ys = k.y, f.len = k.z, f.ident = k.w;
+    f.xe = r.x, f.ye = r.y, f.score = r.z, f.sim_bits = r.w;
+    f.strand = (char)a.pk_strand[fidx];
+  }
+  return f;
+}
+
 template <class Sink>
-__device__ __forceinline__ void format_line(Sink &s, const u8 *rec, u32 gid, u32 identity_bits, u32 repval) {
+__device__ __forceinline__ void format_line(Sink &s, const LineFields &f, u32 gid, u32 identity_bits, u32 repval) {
   s.put('F'), s.put('r'), s.put('a'), s.put('g'), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_XSTART)), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_YSTART)), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_XEND)), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_YEND)), s.put(',');
-  s.put((char)rec[OFF_STRAND]), s.put(',');
+  rkfmt::put_u64(s, f.xs), s.put(',');
+  rkfmt::put_u64(s, f.ys), s.put(',');
+  rkfmt::put_u64(s, f.xe), s.put(',');
+  rkfmt::put_u64(s, f.ye), s.put(',');
+  s.put(f.strand), s.put(',');
   rkfmt::put_u64(s, gid), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_LENGTH)), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_SCORE)), s.put(',');
-  rkfmt::put_u64(s, ldg_u64_unaligned(rec + OFF_IDENT)), s.put(',');
-  const u32 sim = (u32)rec[OFF_SIMILARITY] | ((u32)rec[OFF_SIMILARITY + 1] << 8) | ((u32)rec[OFF_SIMILARITY + 2] << 16) |
-                  ((u32)rec[OFF_SIMILARITY + 3] << 24);
-  rkfmt::put_g6(s, sim), s.put(',');
+  rkfmt::put_u64(s, f.len), s.put(',');
+  rkfmt::put_u64(s, f.score), s.put(',');
+  rkfmt::put_u64(s, f.ident), s.put(',');
+  rkfmt::put_g6(s, f.sim_bits), s.put(',');
   rkfmt::put_g6(s, identity_bits);
   s.put(','), s.put('0'), s.put(',');
   s.put((char)('0' + repval)), s.put('\n');
@@ -50,7 +72,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_format_len(FormatArgs a) {
   if (i >= a.n_lines) return;
   const u32 j = a.first_line + i;
   rkfmt::CountSink s;
-  format_line(s, a.aos + (u64)a.order[j] * FRAG_BYTES, a.gid[j], __float_as_uint(a.identity[j]), a.repval[j]);
+  format_line(s, load_fields(a, a.order[j]), a.gid[j], __float_as_uint(a.identity[j]), a.repval[j]);
   a.line_len[i] = s.n;
 }
 
@@ -63,7 +85,7 @@ __global__ void __launch_bounds__(FMT_THREADS) k_format_write(FormatArgs a) {
   if (i < a.n_lines) {
     const u32 j = a.first_line + i;
     rkfmt::BufSink s(s_text + (a.line_off[i] - base));
-    format_line(s, a.aos + (u64)a.order[j] * FRAG_BYTES, a.gid[j], __float_as_uint(a.identity[j]), a.repval[j]);
+    format_line(s, load_fields(a, a.order[j]), a.gid[j], __float_as_uint(a.identity[j]), a.repval[j]);
   }
   __syncthreads();
   char *out = a.text + base;

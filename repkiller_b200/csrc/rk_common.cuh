@@ -159,6 +159,10 @@ int launch_decode(const u8 *aos, u64 n, Geometry g, u32 *xs, u32 *ys, u32 *len, 
                   u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped, u32 *err, cudaStream_t st, uint4 *rec4 = nullptr,
                   HistOut hist = HistOut{nullptr, 0, 0}, u32 fidx_base = 0);
 
+// K1 for the compact ingest: {xStart, yStart, length, ident} words + strand bytes instead of 109-byte records
+int launch_decode_packed(const uint4 *key4, const u8 *strand, u64 n, Geometry g, u32 *key0, u32 *link_x, u32 *link_y, u32 *n_dropped,
+                         u32 *err, cudaStream_t st, uint4 *rec4, HistOut hist);
+
 // K2: stable LSD radix sort of (key,value) pairs; result in keys_out/vals_out.
 u64 sort_work_bytes(u64 n);
 // prehist: [4][256] digit counts of keys_in already accumulated by the producer of the keys (HistOut), or nullptr
@@ -241,7 +245,10 @@ struct OrderArgs {
 // K6: the text of output lines first_line .. first_line+n_lines (commonFunctions.cpp:101-115) from the loaded records and
 // the result arrays of the last grouping.
 struct FormatArgs {
-  const u8 *aos;           // the loaded records, file order, 109 bytes each
+  const u8 *aos;           // the loaded records, file order, 109 bytes each — or, after rk_load_packed (aos == nullptr):
+  const uint4 *pk_key;     //   {xStart, yStart, length, ident}
+  const uint4 *pk_rest;    //   {xEnd, yEnd, score, similarity bits}
+  const u8 *pk_strand;
   const u32 *order, *gid;  // result arrays (output order)
   const u8 *repval;
   const float *identity;

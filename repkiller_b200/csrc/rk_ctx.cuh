@@ -87,6 +87,8 @@ struct rk_ctx {
 
   // K6 text output: device text + work area (grow-only), pinned host mirror
   const rk::u8 *aos_dev = nullptr;  // the loaded records on the device (own copy, or the caller's device pointer)
+  const uint4 *pk_key = nullptr, *pk_rest = nullptr;  // ... or the compact arrays of rk_load_packed (aos_dev == nullptr)
+  const rk::u8 *pk_strand = nullptr;
   void *d_text = nullptr;
   rk::u64 d_text_bytes = 0;
   char *h_text[2] = {nullptr, nullptr};  // alternating: a chunk stays valid while the next one is produced

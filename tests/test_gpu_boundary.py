@@ -107,3 +107,22 @@ def test_cli_short_rows_do_not_overflow_the_record_buffer(tmp_path):
     want = tmp_path / "want.csv"
     O.write_output(str(want), hdr, rec, g)
     assert outp.read_bytes() == want.read_bytes()
+
+
+def test_cli_values_beyond_32_bits_take_the_record_ingest(tmp_path):
+    """the CLI packs records into the compact ingest; a 40-bit score (printed, never used for grouping) must switch it to
+    the 109-byte ingest and come out digit for digit"""
+    w = gen.scaled(gen.WORKLOADS["c1"], 5_000)
+    rec = gen.generate(w)
+    rec["score"][::7] = (1 << 40) + np.arange(rec[::7].shape[0], dtype=np.uint64)
+    inp = tmp_path / "in.csv"
+    O.write_input_csv(str(inp), rec, w.lx, w.ly)
+    outp = tmp_path / "out.csv"
+    p = subprocess.run([CLI, str(inp), str(outp), "0.05", "0.05"], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    loaded, lx1, ly1, hdr = O.load_csv(str(inp))
+    g = O.group(loaded, lx1, ly1, 0.05, 0.05)
+    want = tmp_path / "want.csv"
+    O.write_output(str(want), hdr, loaded, g)
+    assert outp.read_bytes() == want.read_bytes()
+    assert b"1099511627776" in outp.read_bytes()

@@ -364,6 +364,36 @@ def test_group_order_is_libstdcxx_sort_for_every_size_and_pattern(ctx):
         pos += n
 
 
+def test_packed_ingest_equals_record_ingest(ctx, fuzz_cases, tmp_path):
+    """rk_load_packed (33 B per fragment: what the CLI sends) must give the arrays AND the output text of rk_load_aos"""
+    from dataclasses import replace
+    cases = [(gen.generate(w), w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio) for w in (
+        gen.scaled(gen.WORKLOADS["c2"], 200_003), replace(gen.WORKLOADS["c1"], n=60_000, lx=400_000, ly=300_000, families=40, p_rep=0.6, seed=31))]
+    for c in fuzz_cases[::5]:
+        inp = tmp_path / "in.csv"
+        inp.write_text(c["csv"], newline="")
+        rec, lx1, ly1, _ = O.load_csv(str(inp))
+        cases.append((rec, lx1, ly1, c["len_ratio"], c["pos_ratio"]))
+    for rec, lx1, ly1, lr, pr in cases:
+        ctx.load(rec, lx1, ly1)
+        a = ctx.group(lr, pr)
+        text_a = ctx.format_lines()
+        st = ctx.load_packed(*capi.pack_records(rec), lx1, ly1)
+        assert st.n_loaded == rec.shape[0] and st.n_kept == a.n_kept
+        b = ctx.group(lr, pr)
+        for f in ("order", "gid", "repval"):
+            assert_same(f, getattr(b, f), getattr(a, f))
+        assert_same("identity", b.identity.view(np.uint32), a.identity.view(np.uint32))
+        assert ctx.format_lines() == text_a
+        # without the output-only array the grouping still works and the formatter says why it cannot
+        key4, strand, _ = capi.pack_records(rec)
+        ctx.load_packed(key4, strand, None, lx1, ly1)
+        assert_same("order (no rest4)", ctx.group(lr, pr).order, a.order)
+        if a.n_kept:
+            with pytest.raises(capi.RkError):
+                ctx.format_lines()
+
+
 @pytest.mark.parametrize("wl", ["c1", "dense", "c3"])
 def test_group_statistics_match_oracle_reduction(ctx, wl):
     """K8 (north_star kernel 5): count, spans and first line exact; mean identity and multiplicity within 1e-6 relative
