@@ -177,6 +177,10 @@ int finish_group(rk_ctx *ctx, unsigned flags, rk_result *out, u64 launches) {
   }
   CK(cudaEventRecord(ev[7], st));
   CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  if (ctx->copy_pending) {  // the formatter-only part of a compact load: done by the time a grouping is handed back
+    CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    ctx->copy_pending = false;
+  }
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (ctx->h_cnt->err) return fail(ctx, RK_ERR_INTERNAL, "%s", err_bits_text(ctx->h_cnt->err));
@@ -239,6 +243,8 @@ rk_ctx *rk_create(int device) {
   c->own_stream = true;
   if (const char *gr = getenv("RK_L2_GRAN")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));  // tuning switch
   for (auto &ev : c->ev) cudaEventCreate(&ev);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
   if (cudaMalloc((void **)&c->st_cnt, sizeof(Counters)) != cudaSuccess) c->st_cnt = nullptr;
   // function attributes are per device: every context sets them for its own device (a process-wide flag would leave
   // the second device of a process without the shared-memory opt-in)
@@ -265,6 +271,8 @@ void rk_destroy(rk_ctx *c) {
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream), cudaStreamDestroy(c->copy_stream);
+  if (c->copy_done) cudaEventDestroy(c->copy_done);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -357,8 +365,13 @@ int load_common(rk_ctx *ctx, const LoadSource &src, uint64_t n, uint64_t seqx_le
       key4 = (const uint4 *)p, p += align_up(n * 16, 256);
       CK(cudaMemcpyAsync(p, src.strand, n, cudaMemcpyHostToDevice, st));
       strand = p, p += align_up(n, 256);
-      if (src.rest4) {  // only rk_format_lines reads these: the copy runs while the kernels below work
-        CK(cudaMemcpyAsync(p, src.rest4, n * 16, cudaMemcpyHostToDevice, st));
+      if (src.rest4) {  // only rk_format_lines reads these: the copy runs on its own stream while the kernels work
+        CK(cudaStreamSynchronize(ctx->copy_stream));           // (an earlier load's copy into the old arena)
+        CK(cudaEventRecord(ctx->copy_done, st));               // not before the work queued on st is done with the arena
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0));
+        CK(cudaMemcpyAsync(p, src.rest4, n * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        ctx->copy_pending = true;
         rest4 = (const uint4 *)p;
       }
     } else {

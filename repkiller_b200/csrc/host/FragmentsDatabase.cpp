@@ -190,11 +190,14 @@ std::vector<std::vector<FragFile>> parse_rows_parallel(const char *data, size_t 
   return out;
 }
 
-FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device) {
+FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, const std::vector<int> &devices) {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   // CUDA start-up (a few hundred ms) runs beside the file read and the parse
-  std::thread create_thread([this, device] { ctx_ = rk_create(device); });
+  std::thread create_thread([this, &devices] {
+    if (devices.size() > 1) multi_ = rk_create_multi(devices.data(), (int)devices.size());
+    else ctx_ = rk_create(devices.empty() ? 0 : devices[0]);
+  });
   struct Joiner {
     std::thread &t;
     ~Joiner() { if (t.joinable()) t.join(); }
@@ -255,7 +258,7 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   const uint64_t rows_upper = body / 28 + 1;
   cap_ = (rows_upper < total_frags ? rows_upper : total_frags) + 2;
   create_thread.join();
-  if (!ctx_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
+  if (!ctx_ && !multi_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
   auto packed_bytes = [](uint64_t cap) { return cap * 33 + 64; };
   std::thread alloc_thread([this, &packed_bytes] { packed_ = (unsigned char *)rk_host_alloc(packed_bytes(cap_)); });
   Joiner alloc_joiner{alloc_thread};
@@ -303,9 +306,14 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
   const auto t2 = clk::now();
 
   const uint64_t lx1 = seq_manager.get_sequence_by_label(0).len, ly1 = seq_manager.get_sequence_by_label(1).len;
-  const int rc = wide ? rk_load_aos(ctx_, records_, count_, lx1, ly1, RK_F_TIMING, &load_stats_)
-                      : rk_load_packed(ctx_, key4, strand, rest4, count_, lx1, ly1, RK_F_TIMING, &load_stats_);
-  if (rc != RK_OK) throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(ctx_));
+  if (multi_) {  // the ranks take consecutive slices of the records
+    if (rk_multi_load_aos(multi_, records_, count_, lx1, ly1, RK_F_TIMING, &load_stats_) != RK_OK)
+      throw std::runtime_error(std::string("repkiller-b200: ") + rk_multi_last_error(multi_));
+  } else {
+    const int rc = wide ? rk_load_aos(ctx_, records_, count_, lx1, ly1, RK_F_TIMING, &load_stats_)
+                        : rk_load_packed(ctx_, key4, strand, rest4, count_, lx1, ly1, RK_F_TIMING, &load_stats_);
+    if (rc != RK_OK) throw std::runtime_error(std::string("repkiller-b200: ") + rk_last_error(ctx_));
+  }
   const auto t3 = clk::now();
   ms_read_ = std::chrono::duration<double, std::milli>(t1 - t0).count();
   ms_parse_ = std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -340,6 +348,7 @@ const std::vector<FragFile> *FragmentsDatabase::begin() const {
 
 FragmentsDatabase::~FragmentsDatabase() {
   if (ctx_) rk_destroy(ctx_);
+  if (multi_) rk_destroy_multi(multi_);
   free(records_);
   if (packed_) rk_host_free(packed_);
 }

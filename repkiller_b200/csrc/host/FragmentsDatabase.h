@@ -25,6 +25,7 @@ class FragmentsDatabase {
   uint64_t count_ = 0, cap_ = 0;
   size_t vsize = 0;
   rk_ctx *ctx_ = nullptr;
+  rk_multi *multi_ = nullptr;  // several GPUs: one comparison partitioned over them (rk_create_multi)
   std::string header;
   rk_load_stats load_stats_{};
   double ms_read_ = 0, ms_parse_ = 0, ms_device_load_ = 0;  // host wall clock of the three ingest phases
@@ -37,7 +38,10 @@ class FragmentsDatabase {
   // Parses the GECKO CSV exactly like the reference (16 header lines, Frag rows, readFragment's accept/pad
   // rules), fills seq_manager, then hands the records to the GPU.  Throws std::runtime_error like the
   // reference on "Unexpected number of fragments"; also on device errors (message from rk_last_error).
-  FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device = 0);
+  FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, int device = 0)
+      : FragmentsDatabase(frags_file, seq_manager, std::vector<int>{device}) {}
+  // several devices: the comparison is partitioned over them (rk_multi_*); ctx() is then null and multi() is set
+  FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, const std::vector<int> &devices);
   ~FragmentsDatabase();
   FragmentsDatabase(const FragmentsDatabase &) = delete;
   FragmentsDatabase &operator=(const FragmentsDatabase &) = delete;
@@ -51,6 +55,7 @@ class FragmentsDatabase {
   const std::vector<FragFile> *end() const { return begin() + vsize - 1; }
   const FragFile *records() const { return records_; }   // the records in file order
   rk_ctx *ctx() const { return ctx_; }
+  rk_multi *multi() const { return multi_; }
   const rk_load_stats &load_stats() const { return load_stats_; }
   double ms_read() const { return ms_read_; }
   double ms_parse() const { return ms_parse_; }

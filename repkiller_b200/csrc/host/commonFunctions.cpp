@@ -122,7 +122,12 @@ void sort_groups(FGList &fgl, const size_t *diag_func) {
 
 FGList *group_and_sort(const FragmentsDatabase &frags_db, double len_ratio, double pos_ratio, rk_result *stats) {
   rk_result r;
-  if (rk_group(frags_db.ctx(), len_ratio, pos_ratio, RK_F_HOST_RESULT | RK_F_TIMING, &r) != RK_OK) device_error(frags_db);
+  if (frags_db.multi()) {  // one comparison over several GPUs: the ranks' ranges of lines come back concatenated
+    if (rk_multi_group(frags_db.multi(), len_ratio, pos_ratio, RK_F_TIMING, &r) != RK_OK)
+      throw std::runtime_error(std::string("repkiller-b200: ") + rk_multi_last_error(frags_db.multi()));
+  } else if (rk_group(frags_db.ctx(), len_ratio, pos_ratio, RK_F_HOST_RESULT | RK_F_TIMING, &r) != RK_OK) {
+    device_error(frags_db);
+  }
   FGList *fgl = new FGList;
   build_groups(frags_db, r, *fgl);
   if (stats) *stats = r;

@@ -5,7 +5,8 @@
 // result; every pair writes the same path (as in the reference, repkiller.cpp:95-96), so the last pair's file
 // remains ([survey choice]: the reference's 3-thread pool makes the survivor timing dependent).
 // RK_TIMING=1 prints per-stage device times on stderr; RK_DEVICE selects the GPU; RK_LEGACY_WRITER=1 formats the output on
-// the host through FGList + SaverQueue instead of on the device (K6).
+// the host through FGList + SaverQueue instead of on the device (K6).  RK_DEVICES=0,1,... partitions the comparison over
+// several GPUs (rk_create_multi; NCCL between distinct devices); its lines are written by the host writer.
 #include <chrono>
 #include <cstdlib>
 #include <fstream>
@@ -70,11 +71,20 @@ int main(int argc, char *argv[]) {
                "\n"
             << std::flush;
   const bool timing = getenv("RK_TIMING") != nullptr;
-  const bool legacy_writer = getenv("RK_LEGACY_WRITER") != nullptr;
-  const int device = getenv("RK_DEVICE") ? atoi(getenv("RK_DEVICE")) : 0;
+  const bool legacy_env = getenv("RK_LEGACY_WRITER") != nullptr;
+  std::vector<int> devices;
+  if (const char *list = getenv("RK_DEVICES")) {
+    for (const char *p = list; *p;) {
+      devices.push_back(atoi(p));
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  }
+  if (devices.empty()) devices.push_back(getenv("RK_DEVICE") ? atoi(getenv("RK_DEVICE")) : 0);
+  const bool legacy_writer = legacy_env || devices.size() > 1;
 
   sequence_manager seq_manager;
-  FragmentsDatabase frag_db(frags_file, seq_manager, device);
+  FragmentsDatabase frag_db(frags_file, seq_manager, devices);
   frags_file.close();
   if (timing) {
     const rk_load_stats &ls = frag_db.load_stats();

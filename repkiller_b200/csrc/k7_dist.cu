@@ -368,10 +368,26 @@ __global__ void k_store_total(const u32 *total, u32 *out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *out = *total;
 }
 
-// gid of local rank i: follow the parents to the root — through the peers' arrays when the chain leaves this GPU (peer
-// loads over NVLink; parents always have a smaller global rank, so chains only ever run towards lower GPUs) — then
-// gid(root) = roots of lower GPUs + roots before it on its own GPU.
-__global__ void __launch_bounds__(256) k_chase_peers(PeerTable pt, const u32 *__restrict__ nroots_all, u32 m, u32 *__restrict__ gid_rank) {
+// Group ids in three steps, so that NVLink is only crossed where a chain really leaves the GPU:
+//   A  every fragment follows its parents while they are LOCAL: lroot[i] = the last local node of its chain — a root of the
+//      forest, or an "exit" whose parent lives on a lower GPU (parents always have a smaller global rank).  lroot[] is
+//      visible to the peers.
+//   B  the nodes that are their own lroot get their group id: a root from the root scan; an exit walks on through the
+//      peers' memory — per GPU it visits one read of lroot[] (jumps that GPU's whole local chain) and one of parent[].
+//   C  everybody copies the id of its lroot.
+__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, u32 m, u32 lo, u32 *__restrict__ lroot) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  u32 r = i;
+  for (;;) {
+    const u32 p = parent[r];
+    if (p == RK_NONE32 || p < lo) break;  // a root, or the parent is on a lower GPU
+    r = p - lo;                           // p < own global rank: stays inside this GPU's range
+  }
+  lroot[i] = r;
+}
+
+__global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__restrict__ nroots_all, u32 m, u32 *__restrict__ gid_l) {
   __shared__ u32 s_groot[DIST_MAX_RANKS];
   if (threadIdx.x == 0) {
     u32 run = 0;
@@ -382,16 +398,21 @@ __global__ void __launch_bounds__(256) k_chase_peers(PeerTable pt, const u32 *__
   }
   __syncthreads();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
+  if (i >= m || pt.lroot[pt.me][i] != i) return;
   int s = pt.me;
-  u32 loc = i;  // (s, loc): the node the walk stands on
+  u32 loc = i;  // (s, loc): a node that is its own lroot on GPU s
   for (;;) {
     const u32 p = pt.parent[s][loc];
     if (p == RK_NONE32) break;
     while (p < pt.roff[s]) --s;  // global rank p lives on the last rank whose offset is <= p
-    loc = p - pt.roff[s];
+    loc = pt.lroot[s][p - pt.roff[s]];
   }
-  gid_rank[i] = s_groot[s] + pt.gidscan[s][loc];
+  gid_l[i] = s_groot[s] + pt.gidscan[s][loc];
+}
+
+__global__ void __launch_bounds__(256) k_chase_map(const u32 *__restrict__ lroot, const u32 *__restrict__ gid_l, u32 m, u32 *__restrict__ gid_rank) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) gid_rank[i] = gid_l[lroot[i]];
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
@@ -524,11 +545,18 @@ int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *wo
   k_store_total<<<1, 32, 0, st>>>(bsum + nb, nroots);
   return l + 1;
 }
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, u32 *gid_rank, cudaStream_t st) {
+int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, cudaStream_t st) {
   if (m == 0) return 0;
   KScope ks(KID_CHASE, st, m);
-  k_chase_peers<<<blocks_for(m), 256, 0, st>>>(pt, nroots_all, m, gid_rank);
+  k_chase_local<<<blocks_for(m), 256, 0, st>>>(parent, m, lo, lroot);
   return 1;
+}
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *lroot, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
+  if (m == 0) return 0;
+  KScope ks(KID_CHASE, st, m);
+  k_chase_exits<<<blocks_for(m), 256, 0, st>>>(pt, nroots_all, m, gid_l);
+  k_chase_map<<<blocks_for(m), 256, 0, st>>>(lroot, gid_l, m, gid_rank);
+  return 2;
 }
 int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st) {
   if (words == 0) return 0;

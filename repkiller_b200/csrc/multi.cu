@@ -391,7 +391,7 @@ struct Dist {
   u8 *xm_send = nullptr, *xm_a = nullptr;
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr, *worklist = nullptr;
   u32 work_cap = 0;
-  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr;
+  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr;
   void *scan_work = nullptr;
   u32 *gid_a = nullptr, *sgid = nullptr, *srank_g = nullptr;
   void *order_scratch = nullptr;
@@ -459,6 +459,8 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.xm_bits = (u32 *)take((MC + 31) / 32 * 4);
   D.parent = (u32 *)take(M * 4);
   D.gidscan = (u32 *)take(M * 4);
+  D.lroot = (u32 *)take(M * 4);
+  D.gid_l = (u32 *)take(M * 4);
   D.flag = (u32 *)take(16);
   D.flag_all = (u32 *)take(DIST_MAX_RANKS * 4);
   D.parent_y = (u32 *)take(M * 4);
@@ -582,6 +584,7 @@ static int dist_import(rk_ctx *ctx, const u8 *blobs, size_t stride) {
     // the arenas are carved identically (same capacity, same number of ranks): local offsets hold on every peer
     D.pt.parent[r] = (const u32 *)(base + ((const u8 *)D.parent - (const u8 *)D.arena));
     D.pt.gidscan[r] = (const u32 *)(base + ((const u8 *)D.gidscan - (const u8 *)D.arena));
+    D.pt.lroot[r] = (const u32 *)(base + ((const u8 *)D.lroot - (const u8 *)D.arena));
   }
   D.tr->my_base = (const u8 *)D.arena;
   D.tr->peers_mapped = true;
@@ -849,8 +852,9 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   CK(cudaEventRecord(ev[2], st));
   // forest: roots per rank, then every chain is followed to its root through the peers' parent arrays
   launches += dist_root_scan(D.parent, m, D.gidscan, D.d_small + W_X0, D.scan_work, st);
-  TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's parent and root scan are final)
-  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.gid_rank, st);
+  launches += dist_chase_local(D.parent, m, D.rank_off, D.lroot, st);
+  TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's parent, root scan and lroot are final)
+  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.lroot, D.gid_l, D.gid_rank, st);
   // (no second barrier: the count exchange of the output stage below completes on a rank only after every rank has
   // entered it, i.e. finished chasing, and parent[] is not written again before the next rk_dist_group)
   CK(cudaEventRecord(ev[3], st));

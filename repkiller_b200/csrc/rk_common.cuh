@@ -267,6 +267,7 @@ constexpr int DIST_MAX_RANKS = 16;
 struct PeerTable {                    // what a rank needs to follow a parent chain across GPUs
   const u32 *parent[DIST_MAX_RANKS];  // every rank's parent array (global ranks), mapped peer memory
   const u32 *gidscan[DIST_MAX_RANKS]; // every rank's exclusive scan of root flags
+  const u32 *lroot[DIST_MAX_RANKS];   // every rank's last-local-node table (local indices)
   u32 roff[DIST_MAX_RANKS + 1];       // first global rank of every rank
   int nr, me;
 };
@@ -293,7 +294,8 @@ int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaSt
 int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st);
 u64 dist_scan_work_bytes(u32 m);
 int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *work, cudaStream_t st);
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, u32 *gid_rank, cudaStream_t st);
+int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, cudaStream_t st);
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *lroot, u32 *gid_l, u32 *gid_rank, cudaStream_t st);
 int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st);
 
 // sort_groups as a function of (groups, diag_func): h = |y - d| per member, member index, zero identity (sol.cu)

@@ -65,6 +65,9 @@ struct rk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // H2D of data only the output formatter reads (rk_load_packed's rest4), beside the kernels
+  cudaEvent_t copy_done = nullptr;
+  bool copy_pending = false;
   std::string err;
 
   // device workspace (one allocation, carved by carve())

@@ -126,3 +126,16 @@ def test_cli_values_beyond_32_bits_take_the_record_ingest(tmp_path):
     O.write_output(str(want), hdr, loaded, g)
     assert outp.read_bytes() == want.read_bytes()
     assert b"1099511627776" in outp.read_bytes()
+
+
+def test_cli_over_several_ranks(tmp_path, medium_cases):
+    """RK_DEVICES: the C++ CLI partitions the comparison over several contexts (rk_create_multi; the same device listed
+    three times makes the ranks exchange through device copies) and writes the reference's bytes"""
+    c = medium_cases["c1"]
+    w = gen.Workload(**c["workload"])
+    inp = tmp_path / "c1.csv"
+    O.write_input_csv(str(inp), gen.generate(w), w.lx, w.ly)
+    outp = tmp_path / "out.csv"
+    p = subprocess.run([CLI, str(inp), str(outp), "0.05", "0.05"], capture_output=True, env=dict(os.environ, RK_DEVICES="0,0,0"))
+    assert p.returncode == 0, p.stderr
+    assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"]
