@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(256) k_coarse_hist(const u32 *__restrict__ key
     if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
 }
 
-// one CTA of 1024 threads: hist_all[nr][DIST_BINS] summed over the ranks, cuts[r] = first bin boundary (as a key value)
+// one CTA of 1024 threads: the ranks' histograms (row r at hist_all + r * row_stride words) summed, cuts[r] = first bin boundary (as a key value)
 // at which the cumulative count reaches total*r/nr; cuts[0] = 0, cuts[nr] = 0xFFFFFFFF.  Identical on every rank.
-__global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__ hist_all, int nr, int shift, u32 *__restrict__ cuts) {
+__global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__ hist_all, u64 row_stride, int nr, int shift,
+                                                         u32 *__restrict__ cuts) {
   __shared__ unsigned long long s_cum[DIST_BINS + 1];
   __shared__ unsigned long long s_part[1024];
   constexpr int PER = DIST_BINS / 1024;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__
   for (int j = 0; j < PER; ++j) {
     const u32 b = threadIdx.x * PER + j;
     unsigned long long c = 0;
-    for (int r = 0; r < nr; ++r) c += hist_all[(u64)r * DIST_BINS + b];
+    for (int r = 0; r < nr; ++r) c += hist_all[(u64)r * row_stride + b];
     v[j] = c;
     sum += c;
   }
@@ -371,23 +372,39 @@ __global__ void k_store_total(const u32 *total, u32 *out) {
 // Group ids in three steps, so that NVLink is only crossed where a chain really leaves the GPU:
 //   A  every fragment follows its parents while they are LOCAL: lroot[i] = the last local node of its chain — a root of the
 //      forest, or an "exit" whose parent lives on a lower GPU (parents always have a smaller global rank).  lroot[] is
-//      visible to the peers.
-//   B  the nodes that are their own lroot get their group id: a root from the root scan; an exit walks on through the
-//      peers' memory — per GPU it visits one read of lroot[] (jumps that GPU's whole local chain) and one of parent[].
-//   C  everybody copies the id of its lroot.
-__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, u32 m, u32 lo, u32 *__restrict__ lroot) {
+//      visible to the peers; the exits are collected in a list.
+//   B  every exit walks on through the peers' memory — per GPU it visits one read of lroot[] (jumps that GPU's whole local
+//      chain) and one of parent[] — to a root and takes its id.  Only the exits run here (a few per cent of the fragments),
+//      all of them in flight at once: the walk is a chain of NVLink round trips, so it is the number of concurrent walks
+//      that decides the time.
+//   C  everybody copies the id of its lroot (a local root: from the root scan; an exit: from B).
+__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, u32 m, u32 lo, u32 *__restrict__ lroot,
+                                                     u32 *__restrict__ exits, u32 *__restrict__ n_exits) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  u32 r = i;
-  for (;;) {
-    const u32 p = parent[r];
-    if (p == RK_NONE32 || p < lo) break;  // a root, or the parent is on a lower GPU
-    r = p - lo;                           // p < own global rank: stays inside this GPU's range
+  bool is_exit = false;
+  if (i < m) {
+    u32 r = i, p;
+    for (;;) {
+      p = parent[r];
+      if (p == RK_NONE32 || p < lo) break;  // a root, or the parent is on a lower GPU
+      r = p - lo;                           // p < own global rank: stays inside this GPU's range
+    }
+    lroot[i] = r;
+    is_exit = r == i && p != RK_NONE32;
   }
-  lroot[i] = r;
+  // warp-aggregated append (the order of the list does not matter)
+  const u32 bal = __ballot_sync(0xFFFFFFFFu, is_exit);
+  if (bal) {
+    u32 base = 0;
+    const u32 lane = threadIdx.x & 31;
+    if (lane == (u32)(__ffs(bal) - 1)) base = atomicAdd(n_exits, (u32)__popc(bal));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(bal) - 1);
+    if (is_exit) exits[base + __popc(bal & lanemask_lt())] = i;
+  }
 }
 
-__global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__restrict__ nroots_all, u32 m, u32 *__restrict__ gid_l) {
+__global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__restrict__ nroots_all, const u32 *__restrict__ exits,
+                                                     const u32 *__restrict__ n_exits, u32 *__restrict__ gid_l) {
   __shared__ u32 s_groot[DIST_MAX_RANKS];
   if (threadIdx.x == 0) {
     u32 run = 0;
@@ -397,30 +414,43 @@ __global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__
     }
   }
   __syncthreads();
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m || pt.lroot[pt.me][i] != i) return;
-  int s = pt.me;
-  u32 loc = i;  // (s, loc): a node that is its own lroot on GPU s
-  for (;;) {
-    const u32 p = pt.parent[s][loc];
-    if (p == RK_NONE32) break;
-    while (p < pt.roff[s]) --s;  // global rank p lives on the last rank whose offset is <= p
-    loc = pt.lroot[s][p - pt.roff[s]];
+  const u32 n = *n_exits;
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const u32 i = exits[t];
+    int s = pt.me;
+    u32 loc = i;  // (s, loc): a node that is its own lroot on GPU s
+    for (;;) {
+      const u32 p = pt.parent[s][loc];
+      if (p == RK_NONE32) break;
+      while (p < pt.roff[s]) --s;  // global rank p lives on the last rank whose offset is <= p
+      loc = pt.lroot[s][p - pt.roff[s]];
+    }
+    gid_l[i] = s_groot[s] + pt.gidscan[s][loc];
   }
-  gid_l[i] = s_groot[s] + pt.gidscan[s][loc];
 }
 
-__global__ void __launch_bounds__(256) k_chase_map(const u32 *__restrict__ lroot, const u32 *__restrict__ gid_l, u32 m, u32 *__restrict__ gid_rank) {
+__global__ void __launch_bounds__(256) k_chase_map(const u32 *__restrict__ parent, const u32 *__restrict__ lroot, const u32 *__restrict__ gidscan,
+                                                   const u32 *__restrict__ gid_l, const u32 *__restrict__ nroots_all, int me, u32 m,
+                                                   u32 *__restrict__ gid_rank) {
+  __shared__ u32 s_base;
+  if (threadIdx.x == 0) {
+    u32 run = 0;
+    for (int r = 0; r < me; ++r) run += nroots_all[r];
+    s_base = run;
+  }
+  __syncthreads();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) gid_rank[i] = gid_l[lroot[i]];
+  if (i >= m) return;
+  const u32 lr = lroot[i];
+  gid_rank[i] = parent[lr] == RK_NONE32 ? s_base + gidscan[lr] : gid_l[lr];
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_or_rows(const u32 *__restrict__ all, int nr, u64 words, u32 *__restrict__ out) {
+__global__ void __launch_bounds__(256) k_or_rows(const u32 *__restrict__ all, u64 row_stride, int nr, u64 words, u32 *__restrict__ out) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= words) return;
   u32 v = 0;
-  for (int r = 0; r < nr; ++r) v |= all[(u64)r * words + i];
+  for (int r = 0; r < nr; ++r) v |= all[(u64)r * row_stride + i];
   out[i] = v;
 }
 
@@ -440,8 +470,8 @@ int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_
   k_coarse_hist<<<b > cap ? cap : b, 256, 0, st>>>(keys, n, shift, pre_shift, drop_key, hist);
   return 1;
 }
-int dist_cuts_from_hist(const u32 *hist_all, int nr, int shift, u32 *cuts, cudaStream_t st) {
-  k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, nr, shift, cuts);
+int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st) {
+  k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, row_stride, nr, shift, cuts);
   return 1;
 }
 int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st) {
@@ -545,22 +575,26 @@ int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *wo
   k_store_total<<<1, 32, 0, st>>>(bsum + nb, nroots);
   return l + 1;
 }
-int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, cudaStream_t st) {
+int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, u32 *exits, u32 *n_exits, cudaStream_t st) {
+  cudaMemsetAsync(n_exits, 0, sizeof(u32), st);
   if (m == 0) return 0;
   KScope ks(KID_CHASE, st, m);
-  k_chase_local<<<blocks_for(m), 256, 0, st>>>(parent, m, lo, lroot);
+  k_chase_local<<<blocks_for(m), 256, 0, st>>>(parent, m, lo, lroot, exits, n_exits);
   return 1;
 }
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *lroot, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *parent, const u32 *lroot, const u32 *gidscan,
+                     const u32 *exits, const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
   if (m == 0) return 0;
   KScope ks(KID_CHASE, st, m);
-  k_chase_exits<<<blocks_for(m), 256, 0, st>>>(pt, nroots_all, m, gid_l);
-  k_chase_map<<<blocks_for(m), 256, 0, st>>>(lroot, gid_l, m, gid_rank);
+  unsigned grid = blocks_for(m);
+  const unsigned cap = (unsigned)sm_count() * 8;  // every walk of a typical exit list is in flight at once
+  k_chase_exits<<<grid > cap ? cap : grid, 256, 0, st>>>(pt, nroots_all, exits, n_exits, gid_l);
+  k_chase_map<<<blocks_for(m), 256, 0, st>>>(parent, lroot, gidscan, gid_l, nroots_all, pt.me, m, gid_rank);
   return 2;
 }
-int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st) {
+int dist_or_rows(const u32 *all, u64 row_stride, int nr, u64 words, u32 *out, cudaStream_t st) {
   if (words == 0) return 0;
-  k_or_rows<<<blocks_for(words), 256, 0, st>>>(all, nr, words, out);
+  k_or_rows<<<blocks_for(words), 256, 0, st>>>(all, row_stride, nr, words, out);
   return 1;
 }
 

@@ -106,6 +106,13 @@ struct Transport {
   // rank p's receive buffer (used by the transports that write into the peer's memory).
   virtual int all_to_all(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt,
                          const u64 *poff, size_t elem, cudaStream_t st) = 0;
+  // The same in two halves, so that rows can travel while kernels run: begin() enqueues the transfers on `side`, ordered
+  // after everything queued on st so far; end() makes st wait for them and for every other rank's.  (Default: all in begin.)
+  virtual int a2a_begin(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt,
+                        const u64 *poff, size_t elem, cudaStream_t st, cudaStream_t) {
+    return all_to_all(send, soff, scnt, recv, roff, rcnt, poff, elem, st);
+  }
+  virtual int a2a_end(cudaStream_t) { return RK_OK; }
   // peer memory: every rank's partition arena has the same layout, so a local pointer translates to any peer's copy
   const u8 *my_base = nullptr;
   u8 *peer_base[DIST_MAX_RANKS] = {nullptr};
@@ -124,6 +131,8 @@ struct NcclTransport : Transport {
   }
   ~NcclTransport() override {
     if (comm && own_comm) nccl_api().CommDestroy(comm);
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
   }
   int gather_small(const u32 *d_row, u32 *d_all, u32 *h_all, cudaStream_t st) override {
     int rc = check(nccl_api().AllGather(d_row, d_all, SMALL_WORDS * sizeof(u32), ncclUint8, comm, st), "ncclAllGather");
@@ -179,6 +188,38 @@ struct NcclTransport : Transport {
     const int rc2 = check(N.GroupEnd(), "ncclGroupEnd");
     return rc ? rc : rc2;
   }
+  int a2a_begin(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *roff, const u64 *rcnt, const u64 *poff,
+                size_t elem, cudaStream_t st, cudaStream_t side) override {
+    if (!(peers_mapped && !getenv_nccl_rows())) return all_to_all(send, soff, scnt, recv, roff, rcnt, poff, elem, st);
+    if (!ev_a && (cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming) != cudaSuccess)) {
+      err = "a2a_begin: cudaEventCreate failed";
+      return RK_ERR_CUDA;
+    }
+    cudaEventRecord(ev_a, st);
+    cudaStreamWaitEvent(side, ev_a, 0);
+    for (int k = 0; k < world; ++k) {
+      const int p = (rank + k) % world;
+      if (!scnt[p]) continue;
+      u8 *dst = (p == rank ? (u8 *)recv : on_peer(p, (u8 *)recv)) + poff[p] * elem;
+      if (cudaMemcpyAsync(dst, (const u8 *)send + soff[p] * elem, scnt[p] * elem, cudaMemcpyDeviceToDevice, side) != cudaSuccess) {
+        err = std::string("a2a_begin: peer copy failed: ") + cudaGetErrorString(cudaGetLastError());
+        return RK_ERR_CUDA;
+      }
+      if (p != rank) bytes_sent += scnt[p] * elem;
+    }
+    cudaEventRecord(ev_b, side);
+    split_pending = true;
+    return RK_OK;
+  }
+  int a2a_end(cudaStream_t st) override {
+    if (!split_pending) return RK_OK;
+    split_pending = false;
+    cudaStreamWaitEvent(st, ev_b, 0);
+    return check(nccl_api().AllGather(d_flag, d_flag_all, 4, ncclUint8, comm, st), "ncclAllGather (barrier)");
+  }
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  bool split_pending = false;
   u32 *d_flag = nullptr, *d_flag_all = nullptr;  // barrier payload (set by the owner of the transport)
   static bool getenv_nccl_rows() {  // RK_DIST_NCCL_ROWS=1: rows through ncclSend/ncclRecv (tuning reference)
     static const bool v = getenv("RK_DIST_NCCL_ROWS") != nullptr;
@@ -353,10 +394,11 @@ struct Dist {
   u32 *h_small = nullptr;  // pinned [world][SMALL_WORDS]
   PeerTable pt{};
   Trace trace;
+  cudaStream_t side = nullptr;  // rows that travel while kernels run (the Y exchange beside the X sort)
   // grow-only side buffers whose size depends on the input, not on cap
   u8 *aos_buf = nullptr;
   u64 aos_bytes = 0;
-  u32 *link_buf = nullptr;  // [linkx_loc][linky_loc][linkx][linky][gather: world * max]
+  u32 *link_buf = nullptr;  // [hist0][linkx_loc][linky_loc] (one all-gather) [linkx][linky][gather: world * the first three]
   u64 link_words = 0;
   void *h_res = nullptr;
   u64 h_res_cap = 0;
@@ -391,7 +433,7 @@ struct Dist {
   u8 *xm_send = nullptr, *xm_a = nullptr;
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr, *worklist = nullptr;
   u32 work_cap = 0;
-  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr;
+  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr, *exits = nullptr;
   void *scan_work = nullptr;
   u32 *gid_a = nullptr, *sgid = nullptr, *srank_g = nullptr;
   void *order_scratch = nullptr;
@@ -461,6 +503,7 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.gidscan = (u32 *)take(M * 4);
   D.lroot = (u32 *)take(M * 4);
   D.gid_l = (u32 *)take(M * 4);
+  D.exits = (u32 *)take(M * 4 + 16);
   D.flag = (u32 *)take(16);
   D.flag_all = (u32 *)take(DIST_MAX_RANKS * 4);
   D.parent_y = (u32 *)take(M * 4);
@@ -543,6 +586,7 @@ static int dist_init_common(rk_ctx *ctx, int rank, int world, Transport *tr, u64
   D->trace.on = getenv("RK_DIST_TRACE") != nullptr;
   CK(cudaSetDevice(ctx->device));
   CK(cudaHostAlloc((void **)&D->h_small, (size_t)world * SMALL_WORDS * sizeof(u32), cudaHostAllocDefault));
+  CK(cudaStreamCreateWithFlags(&D->side, cudaStreamNonBlocking));
   return dist_allocate(ctx, cap);
 }
 
@@ -637,7 +681,9 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   D.bits_x = ceil_log2(2ull * g.nbx);
   D.bits_y = ceil_log2(2ull * g.nby);
   const u64 lxw = (2ull * g.nbx + 31) / 32 + 1, lyw = (2ull * g.nby + 31) / 32 + 1, lmax = lxw > lyw ? lxw : lyw;
-  const u64 link_need = 2 * (lxw + lyw) + (u64)nr * lmax + 64;
+  const u64 pub_words = DIST_BINS + lxw + lyw;  // what a rank publishes after K1: its xStart/10 histogram and its link maps
+  const u64 link_need = pub_words + lxw + lyw + (u64)nr * pub_words + 64;
+  (void)lmax;
   if (link_need > D.link_words) {
     CK(cudaStreamSynchronize(st));
     if (D.link_buf) cudaFree(D.link_buf);
@@ -645,7 +691,8 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
     CK(cudaMalloc((void **)&D.link_buf, link_need * 4));
     D.link_words = link_need;
   }
-  u32 *linkx_loc = D.link_buf, *linky_loc = linkx_loc + lxw, *linkx = linky_loc + lyw, *linky = linkx + lxw, *link_all = linky + lyw;
+  u32 *hist0 = D.link_buf, *linkx_loc = hist0 + DIST_BINS, *linky_loc = linkx_loc + lxw, *linkx = linky_loc + lyw, *linky = linkx + lxw,
+      *pub_all = linky + lyw;
 
   bool on_device = false;
   if (n_use) {
@@ -688,9 +735,13 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
                             &D.cnt->n_dropped, &D.cnt->err, st, D.rec4_loc, HistOut{nullptr, 0, 0}, (u32)file_off);
   // exchange 1: to the owner of the xStart/10 range
   const int shift0 = D.bits_rank > 12 ? D.bits_rank - 12 : 0;
-  launches += dist_coarse_hist(D.key0_loc, (u32)n_use, shift0, 0, g.vsize - 1, D.hist, st);
-  TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
-  launches += dist_cuts_from_hist(D.hist_all, nr, shift0, D.cuts0, st);
+  launches += dist_coarse_hist(D.key0_loc, (u32)n_use, shift0, 0, g.vsize - 1, hist0, st);
+  // one all-gather for everything K1 produced that the other ranks need: the histogram the cuts are made from and the link
+  // maps (OR-ed over the ranks below, so that a run of linked buckets has one key everywhere)
+  TR(D.tr->all_gather(hist0, pub_all, pub_words * 4, st));
+  launches += dist_cuts_from_hist(pub_all, pub_words, nr, shift0, D.cuts0, st);
+  launches += dist_or_rows(pub_all + DIST_BINS, pub_words, nr, lxw, linkx, st);
+  launches += dist_or_rows(pub_all + DIST_BINS + lxw, pub_words, nr, lyw, linky, st);
   launches += dist_split_records(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.rec4_loc, D.send_rows, D.tile_cnt, D.d_small + W_CNT_A, st);
   {
     const int rc = dist_gather_counts(ctx);  // host sync 1
@@ -731,11 +782,6 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   launches += launch_sort_pairs(D.key0a, nullptr, D.k0_r, D.aidx_r, D.tmp_k, D.tmp_v, m, D.bits_rank, D.sort_work, st, &D.cnt->err,
                                 m ? D.prehist : nullptr);
   CK(cudaEventRecord(ev[3], st));
-  // link maps: OR over the ranks, so that a run of linked buckets has one key everywhere
-  TR(D.tr->all_gather(linkx_loc, link_all, lxw * 4, st));
-  launches += dist_or_rows(link_all, nr, lxw, linkx, st);
-  TR(D.tr->all_gather(linky_loc, link_all, lyw * 4, st));
-  launches += dist_or_rows(link_all, nr, lyw, linky, st);
   launches += launch_keys(D.aidx_r, m, g, D.rec4_arr, linkx, linky, D.xl, D.yl_r, D.ys_r, D.kx2, D.ky, D.identity_r, st,
                           hist_of(1, D.bits_x + 1), HistOut{nullptr, 0, 0}, D.gfidx_r, 1u);
   launches += launch_hkey(D.k0_r, D.ys_r, m, nullptr, st, D.gfidx_r, D.identity_r, D.hfi_r);
@@ -748,7 +794,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   const int shift_y = D.bits_y > 12 ? D.bits_y - 12 : 0;
   launches += dist_coarse_hist(D.ky, m, shift_y, 0, 0xFFFFFFFFu, D.hist, st);
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
-  launches += dist_cuts_from_hist(D.hist_all, nr, shift_y, D.cuts_y, st);
+  launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_y, D.cuts_y, st);
   launches += dist_split_axis(D.ky, D.yl_r, m, D.cuts_y, nr, D.rank_off, D.send_rows, D.perm_y, D.tile_cnt, D.d_small + W_CNT_B, st);
   {
     const int rc = dist_gather_counts(ctx);  // host sync 2
@@ -774,12 +820,14 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   D.n_away = (u32)D.exh.n_send, D.n_halo = (u32)D.exh.n_recv, D.m_y = (u32)D.exy.n_recv;
 
   TR(D.tr->all_to_all(D.halo_send, D.exh.soff, D.exh.scnt, D.halo_recv, D.exh.roff, D.exh.rcnt, D.exh.poff, 16, st));
+  // the Y rows travel (copy engines, NVLink) while this GPU unpacks its halo and sorts its X buckets
+  TR(D.tr->a2a_begin(D.send_rows, D.exy.soff, D.exy.scnt, D.recv_rows, D.exy.roff, D.exy.rcnt, D.exy.poff, 16, st, D.side));
   launches += dist_unpack_axis_rows(D.halo_recv, D.n_halo, D.kx2 + m, D.xl + m, D.halo_grank, hist_of(1, D.bits_x + 1), st);
   CK(cudaEventRecord(ev[5], st));
   launches += launch_sort_pairs(D.kx2, nullptr, D.skx, D.rx, D.tmp_k, D.tmp_v, (u64)m + D.n_halo, D.bits_x + 1, D.sort_work, st, &D.cnt->err,
                                 (m + D.n_halo) ? D.prehist + 1024 : nullptr);
   CK(cudaEventRecord(ev[6], st));
-  TR(D.tr->all_to_all(D.send_rows, D.exy.soff, D.exy.scnt, D.recv_rows, D.exy.roff, D.exy.rcnt, D.exy.poff, 16, st));
+  TR(D.tr->a2a_end(st));
   launches += dist_unpack_axis_rows(D.recv_rows, D.m_y, D.ky_a, D.yl_a, D.grank_a, hist_of(2, D.bits_y), st);
   launches += launch_sort_pairs(D.ky_a, nullptr, D.sky_a, D.ry_a, D.tmp_k, D.tmp_v, D.m_y, D.bits_y, D.sort_work, st, &D.cnt->err,
                                 D.m_y ? D.prehist + 2048 : nullptr);
@@ -852,14 +900,21 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   CK(cudaEventRecord(ev[2], st));
   // forest: roots per rank, then every chain is followed to its root through the peers' parent arrays
   launches += dist_root_scan(D.parent, m, D.gidscan, D.d_small + W_X0, D.scan_work, st);
-  launches += dist_chase_local(D.parent, m, D.rank_off, D.lroot, st);
+  launches += dist_chase_local(D.parent, m, D.rank_off, D.lroot, D.exits + 4, D.exits, st);
   TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's parent, root scan and lroot are final)
-  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.lroot, D.gid_l, D.gid_rank, st);
+  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.parent, D.lroot, D.gidscan, D.exits + 4, D.exits, D.gid_l, D.gid_rank, st);
   // (no second barrier: the count exchange of the output stage below completes on a rank only after every rank has
   // entered it, i.e. finished chasing, and parent[] is not written again before the next rk_dist_group)
   CK(cudaEventRecord(ev[3], st));
-  // output exchange: to the owner of the group-id range
-  launches += dist_cuts_gid(D.nroots_all, nr, D.cuts_g, D.d_small + W_X1, st);
+  // output exchange: to the owner of the group-id range.  The ranges are cut so that every rank gets about the same
+  // number of output LINES (groups founded early are larger: equal numbers of groups would give rank 0 far more lines).
+  const int bits_gid = ceil_log2(D.m_total) < 1 ? 1 : ceil_log2(D.m_total);  // group ids are < number of fragments
+  const int shift_g = bits_gid > 12 ? bits_gid - 12 : 0;
+  launches += dist_cuts_gid(D.nroots_all, nr, D.cuts_g, D.d_small + W_X1, st);  // (the total; the cuts are replaced below)
+  launches += dist_coarse_hist(D.gid_rank, m, shift_g, 0, 0xFFFFFFFFu, D.hist, st);
+  TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
+  launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st);
+  CK(cudaMemcpyAsync(D.d_small + W_CNT_B, D.cuts_g, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   launches += dist_split_gid(D.gid_rank, D.hfi_r, m, D.cuts_g, nr, D.send_rows, D.tile_cnt, D.d_small + W_CNT_A, st);
   {
     const int rc = dist_gather_counts(ctx);  // host sync 3
@@ -879,8 +934,10 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
     if (d < me) line_off += in;
   }
   const u32 mg = (u32)exg.n_recv;
-  const u32 gid_base = (u32)(total_groups * (u64)me / (u64)nr);
-  const u64 local_groups = total_groups * (u64)(me + 1) / (u64)nr - gid_base;
+  const u32 *cuts_h = D.h_small + (size_t)me * SMALL_WORDS + W_CNT_B;
+  const u32 gid_base = cuts_h[me];
+  const u64 gid_end = (u64)cuts_h[me + 1] < total_groups ? (u64)cuts_h[me + 1] : total_groups;
+  const u64 local_groups = gid_end > gid_base ? gid_end - gid_base : 1;
   const int bits_g = ceil_log2(local_groups) < 1 ? 1 : ceil_log2(local_groups);
   TR(D.tr->all_to_all(D.send_rows, exg.soff, exg.scnt, D.recv_rows, exg.roff, exg.rcnt, exg.poff, 16, st));
   CK(cudaMemsetAsync(D.prehist + 3072, 0, 4 * 256 * 4, st));
@@ -977,6 +1034,7 @@ void dist_destroy(rk_ctx *c) {
   if (D->link_buf) cudaFree(D->link_buf);
   if (D->h_res) cudaFreeHost(D->h_res);
   if (D->h_small) cudaFreeHost(D->h_small);
+  if (D->side) cudaStreamSynchronize(D->side), cudaStreamDestroy(D->side);
   delete D->tr;
   delete D;
   c->dist = nullptr;

@@ -272,7 +272,7 @@ struct PeerTable {                    // what a rank needs to follow a parent ch
   int nr, me;
 };
 int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_key, u32 *hist, cudaStream_t st);
-int dist_cuts_from_hist(const u32 *hist_all, int nr, int shift, u32 *cuts, cudaStream_t st);
+int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st);
 int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st);
 int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st);
 u64 dist_split_work_bytes(u64 n);
@@ -294,9 +294,10 @@ int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaSt
 int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st);
 u64 dist_scan_work_bytes(u32 m);
 int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *work, cudaStream_t st);
-int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, cudaStream_t st);
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *lroot, u32 *gid_l, u32 *gid_rank, cudaStream_t st);
-int dist_or_rows(const u32 *all, int nr, u64 words, u32 *out, cudaStream_t st);
+int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, u32 *exits, u32 *n_exits, cudaStream_t st);
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *parent, const u32 *lroot, const u32 *gidscan,
+                     const u32 *exits, const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st);
+int dist_or_rows(const u32 *all, u64 row_stride, int nr, u64 words, u32 *out, cudaStream_t st);
 
 // sort_groups as a function of (groups, diag_func): h = |y - d| per member, member index, zero identity (sol.cu)
 int launch_member_keys(const u64 *y, const u64 *d, u32 m, u32 *h, u32 *idx, float *zero, u32 *err, cudaStream_t st);
