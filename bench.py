@@ -433,6 +433,13 @@ def ours(args):
         exchanged = 0
     stage_ms = {k: round(v, 4) for k, v in {**st.ms_stage, **{k2: v2 for k2, v2 in res.ms_stage.items() if v2}}.items() if v}
 
+    # partitioned: the per-kernel times of the LAST rank as well (its forest walks leave the GPU most often)
+    kernels_last = None
+    if partitioned and prof:
+        box = [None] * world
+        dist.all_gather_object(box, {k: round(v[1] / args.steps, 4) for k, v in prof.items()})
+        kernels_last = box[-1]
+
     line = None
     if rank == 0:
         kernels, total_alg, total_ms = {}, 0.0, 0.0
@@ -483,6 +490,7 @@ def ours(args):
             "pipeline_hbm_frac": round(total_alg / (ms_total / 1e3) / 1e9 / peak_gbs, 4),
             "stage_ms": stage_ms,
             "kernels": kernels,
+            "kernels_ms_per_step_last_rank": kernels_last,
         }
     if world > 1:
         dist.barrier()

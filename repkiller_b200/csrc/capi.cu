@@ -24,7 +24,7 @@ void set_create_error(const std::string &s) {
 const char *const kKernelNames[KID_COUNT] = {"k_decode", "k_radix_hist", "k_scan", "k_radix_scatter", "k_keys", "k_match_small",
                                              "k_match_long", "k_chase", "k_hkey", "k_pack", "k_order_tile",
                                              "k_groupsort_large", "k_finalize", "k_diag_table", "k_groupsort_warp", "k_format", "k_dist_rows",
-                                             "k_group_stats"};
+                                             "k_group_stats", "k_chase_exits"};
 
 thread_local Profiler *tl_prof = nullptr;
 

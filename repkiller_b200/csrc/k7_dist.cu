@@ -370,37 +370,61 @@ __global__ void k_store_total(const u32 *total, u32 *out) {
 }
 
 // Group ids in three steps, so that NVLink is only crossed where a chain really leaves the GPU:
-//   A  every fragment follows its parents while they are LOCAL: lroot[i] = the last local node of its chain — a root of the
-//      forest, or an "exit" whose parent lives on a lower GPU (parents always have a smaller global rank).  lroot[] is
-//      visible to the peers; the exits are collected in a list.
-//   B  every exit walks on through the peers' memory — per GPU it visits one read of lroot[] (jumps that GPU's whole local
-//      chain) and one of parent[] — to a root and takes its id.  Only the exits run here (a few per cent of the fragments),
-//      all of them in flight at once: the walk is a chain of NVLink round trips, so it is the number of concurrent walks
-//      that decides the time.
-//   C  everybody copies the id of its lroot (a local root: from the root scan; an exit: from B).
-__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, u32 m, u32 lo, u32 *__restrict__ lroot,
-                                                     u32 *__restrict__ exits, u32 *__restrict__ n_exits) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool is_exit = false;
-  if (i < m) {
-    u32 r = i, p;
-    for (;;) {
-      p = parent[r];
-      if (p == RK_NONE32 || p < lo) break;  // a root, or the parent is on a lower GPU
-      r = p - lo;                           // p < own global rank: stays inside this GPU's range
+//   A  every fragment follows its parents while they are LOCAL to the last local node of its chain (lroot) — a root of the
+//      forest, or an "exit" whose parent lives on a lower GPU (parents always have a smaller global rank) — and publishes
+//      what a walker arriving at this fragment needs as ONE 64-bit word: res[i] = ROOT | (roots before lroot on this GPU),
+//      or the global rank of the exit's parent.  The exits are collected in a list.
+//   B  every exit walks on through the peers' res[]: one 8-byte NVLink read per GPU it visits, until it meets a root.
+//      Only the exits run here (a few per cent of the fragments), all of them in flight at once: the walk is a chain of
+//      NVLink round trips, and fine-grained remote reads are what the link is slowest at (measured: ~2 M reads per ms).
+//   C  everybody takes the id of its lroot (a local root: from res; an exit: from B).
+constexpr u64 RES_ROOT = 1ull << 63;
+
+__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, const u32 *__restrict__ gidscan, u32 m, u32 lo,
+                                                     u32 *__restrict__ lroot, u64 *__restrict__ res, u32 *__restrict__ exits,
+                                                     u32 *__restrict__ n_exits) {
+  // The exits of a CTA are staged in shared memory and appended to the list a couple of thousand at a time: a global atomic
+  // per warp on the one list counter costs more than the whole chase (measured: +0.3 ms on the GPU with the most exits).
+  constexpr u32 CAP = 2048;
+  __shared__ u32 s_buf[CAP];
+  __shared__ u32 s_n, s_base;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31;
+  auto flush = [&]() {  // all threads of the CTA
+    if (threadIdx.x == 0) s_base = s_n ? atomicAdd(n_exits, s_n) : 0;
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < s_n; k += blockDim.x) exits[s_base + k] = s_buf[k];
+    __syncthreads();
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+  };
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < m; base += (u64)gridDim.x * blockDim.x) {
+    const u64 i = base + threadIdx.x;
+    bool is_exit = false;
+    if (i < m) {
+      u32 r = (u32)i, p;
+      for (;;) {
+        p = parent[r];
+        if (p == RK_NONE32 || p < lo) break;  // a root, or the parent is on a lower GPU
+        r = p - lo;                           // p < own global rank: stays inside this GPU's range
+      }
+      lroot[i] = r;
+      res[i] = p == RK_NONE32 ? (RES_ROOT | gidscan[r]) : (u64)p;
+      is_exit = r == (u32)i && p != RK_NONE32;
     }
-    lroot[i] = r;
-    is_exit = r == i && p != RK_NONE32;
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, is_exit);
+    if (bal) {
+      u32 off = 0;
+      const int leader = __ffs(bal) - 1;
+      if ((int)lane == leader) off = atomicAdd(&s_n, (u32)__popc(bal));
+      off = __shfl_sync(0xFFFFFFFFu, off, leader);
+      if (is_exit) s_buf[off + __popc(bal & lanemask_lt())] = (u32)i;
+    }
+    __syncthreads();
+    if (s_n > CAP - 256) flush();  // (uniform: s_n is read after the barrier by every thread)
   }
-  // warp-aggregated append (the order of the list does not matter)
-  const u32 bal = __ballot_sync(0xFFFFFFFFu, is_exit);
-  if (bal) {
-    u32 base = 0;
-    const u32 lane = threadIdx.x & 31;
-    if (lane == (u32)(__ffs(bal) - 1)) base = atomicAdd(n_exits, (u32)__popc(bal));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(bal) - 1);
-    if (is_exit) exits[base + __popc(bal & lanemask_lt())] = i;
-  }
+  flush();
 }
 
 __global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__restrict__ nroots_all, const u32 *__restrict__ exits,
@@ -418,20 +442,18 @@ __global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__
   for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const u32 i = exits[t];
     int s = pt.me;
-    u32 loc = i;  // (s, loc): a node that is its own lroot on GPU s
-    for (;;) {
-      const u32 p = pt.parent[s][loc];
-      if (p == RK_NONE32) break;
+    u64 w = pt.res[s][i];  // an exit: the global rank of its parent, on a lower GPU
+    do {
+      const u32 p = (u32)w;
       while (p < pt.roff[s]) --s;  // global rank p lives on the last rank whose offset is <= p
-      loc = pt.lroot[s][p - pt.roff[s]];
-    }
-    gid_l[i] = s_groot[s] + pt.gidscan[s][loc];
+      w = pt.res[s][p - pt.roff[s]];
+    } while (!(w & RES_ROOT));
+    gid_l[i] = s_groot[s] + (u32)w;
   }
 }
 
-__global__ void __launch_bounds__(256) k_chase_map(const u32 *__restrict__ parent, const u32 *__restrict__ lroot, const u32 *__restrict__ gidscan,
-                                                   const u32 *__restrict__ gid_l, const u32 *__restrict__ nroots_all, int me, u32 m,
-                                                   u32 *__restrict__ gid_rank) {
+__global__ void __launch_bounds__(256) k_chase_map(const u64 *__restrict__ res, const u32 *__restrict__ lroot, const u32 *__restrict__ gid_l,
+                                                   const u32 *__restrict__ nroots_all, int me, u32 m, u32 *__restrict__ gid_rank) {
   __shared__ u32 s_base;
   if (threadIdx.x == 0) {
     u32 run = 0;
@@ -441,8 +463,8 @@ __global__ void __launch_bounds__(256) k_chase_map(const u32 *__restrict__ paren
   __syncthreads();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const u32 lr = lroot[i];
-  gid_rank[i] = parent[lr] == RK_NONE32 ? s_base + gidscan[lr] : gid_l[lr];
+  const u64 w = res[i];
+  gid_rank[i] = (w & RES_ROOT) ? s_base + (u32)w : gid_l[lroot[i]];
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
@@ -575,21 +597,26 @@ int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *wo
   k_store_total<<<1, 32, 0, st>>>(bsum + nb, nroots);
   return l + 1;
 }
-int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, u32 *exits, u32 *n_exits, cudaStream_t st) {
+int dist_chase_local(const u32 *parent, const u32 *gidscan, u32 m, u32 lo, u32 *lroot, u64 *res, u32 *exits, u32 *n_exits, cudaStream_t st) {
   cudaMemsetAsync(n_exits, 0, sizeof(u32), st);
   if (m == 0) return 0;
   KScope ks(KID_CHASE, st, m);
-  k_chase_local<<<blocks_for(m), 256, 0, st>>>(parent, m, lo, lroot, exits, n_exits);
+  unsigned grid = blocks_for(m);
+  const unsigned cap = (unsigned)sm_count() * 8;
+  k_chase_local<<<grid > cap ? cap : grid, 256, 0, st>>>(parent, gidscan, m, lo, lroot, res, exits, n_exits);
   return 1;
 }
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *parent, const u32 *lroot, const u32 *gidscan,
-                     const u32 *exits, const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u64 *res, const u32 *lroot, const u32 *exits,
+                     const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
   if (m == 0) return 0;
-  KScope ks(KID_CHASE, st, m);
   unsigned grid = blocks_for(m);
   const unsigned cap = (unsigned)sm_count() * 8;  // every walk of a typical exit list is in flight at once
-  k_chase_exits<<<grid > cap ? cap : grid, 256, 0, st>>>(pt, nroots_all, exits, n_exits, gid_l);
-  k_chase_map<<<blocks_for(m), 256, 0, st>>>(parent, lroot, gidscan, gid_l, nroots_all, pt.me, m, gid_rank);
+  {
+    KScope ks(KID_CHASE_EXITS, st, m);
+    k_chase_exits<<<grid > cap ? cap : grid, 256, 0, st>>>(pt, nroots_all, exits, n_exits, gid_l);
+  }
+  KScope ks(KID_CHASE, st, m);
+  k_chase_map<<<blocks_for(m), 256, 0, st>>>(res, lroot, gid_l, nroots_all, pt.me, m, gid_rank);
   return 2;
 }
 int dist_or_rows(const u32 *all, u64 row_stride, int nr, u64 words, u32 *out, cudaStream_t st) {

@@ -434,6 +434,7 @@ struct Dist {
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr, *worklist = nullptr;
   u32 work_cap = 0;
   u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr, *exits = nullptr;
+  u64 *res = nullptr;  // per fragment: what a walker from another GPU needs (k_chase_local); the peers read it
   void *scan_work = nullptr;
   u32 *gid_a = nullptr, *sgid = nullptr, *srank_g = nullptr;
   void *order_scratch = nullptr;
@@ -504,6 +505,7 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.lroot = (u32 *)take(M * 4);
   D.gid_l = (u32 *)take(M * 4);
   D.exits = (u32 *)take(M * 4 + 16);
+  D.res = (u64 *)take(M * 8);
   D.flag = (u32 *)take(16);
   D.flag_all = (u32 *)take(DIST_MAX_RANKS * 4);
   D.parent_y = (u32 *)take(M * 4);
@@ -626,9 +628,7 @@ static int dist_import(rk_ctx *ctx, const u8 *blobs, size_t stride) {
     }
     D.tr->peer_base[r] = base;
     // the arenas are carved identically (same capacity, same number of ranks): local offsets hold on every peer
-    D.pt.parent[r] = (const u32 *)(base + ((const u8 *)D.parent - (const u8 *)D.arena));
-    D.pt.gidscan[r] = (const u32 *)(base + ((const u8 *)D.gidscan - (const u8 *)D.arena));
-    D.pt.lroot[r] = (const u32 *)(base + ((const u8 *)D.lroot - (const u8 *)D.arena));
+    D.pt.res[r] = (const u64 *)(base + ((const u8 *)D.res - (const u8 *)D.arena));
   }
   D.tr->my_base = (const u8 *)D.arena;
   D.tr->peers_mapped = true;
@@ -900,9 +900,9 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   CK(cudaEventRecord(ev[2], st));
   // forest: roots per rank, then every chain is followed to its root through the peers' parent arrays
   launches += dist_root_scan(D.parent, m, D.gidscan, D.d_small + W_X0, D.scan_work, st);
-  launches += dist_chase_local(D.parent, m, D.rank_off, D.lroot, D.exits + 4, D.exits, st);
-  TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's parent, root scan and lroot are final)
-  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.parent, D.lroot, D.gidscan, D.exits + 4, D.exits, D.gid_l, D.gid_rank, st);
+  launches += dist_chase_local(D.parent, D.gidscan, m, D.rank_off, D.lroot, D.res, D.exits + 4, D.exits, st);
+  TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's res[] is final)
+  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.res, D.lroot, D.exits + 4, D.exits, D.gid_l, D.gid_rank, st);
   // (no second barrier: the count exchange of the output stage below completes on a rank only after every rank has
   // entered it, i.e. finished chasing, and parent[] is not written again before the next rk_dist_group)
   CK(cudaEventRecord(ev[3], st));

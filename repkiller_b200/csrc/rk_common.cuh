@@ -132,7 +132,7 @@ __device__ __forceinline__ void hist_flush(u32 (*h)[HIST_RADIX], const HistOut &
 // ---- per-kernel timing (CUDA events around every launch; off unless rk_profile_enable) ---------------
 enum KernelId {
   KID_DECODE = 0, KID_RADIX_HIST, KID_SCAN, KID_RADIX_SCATTER, KID_KEYS, KID_MATCH_SMALL, KID_MATCH_LONG, KID_CHASE,
-  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_FORMAT, KID_DIST_ROWS, KID_STATS,
+  KID_HKEY, KID_PACK, KID_GSORT_SMALL, KID_GSORT_LARGE, KID_FINALIZE, KID_DIAG, KID_GSORT_WARP, KID_FORMAT, KID_DIST_ROWS, KID_STATS, KID_CHASE_EXITS,
   KID_COUNT
 };
 void prof_begin(int kid, cudaStream_t st, unsigned long long units);
@@ -265,9 +265,7 @@ int launch_format(FormatArgs a, void *work, cudaStream_t st);
 constexpr int DIST_BINS = 4096;       // coarse histogram bins a range partition is cut on
 constexpr int DIST_MAX_RANKS = 16;
 struct PeerTable {                    // what a rank needs to follow a parent chain across GPUs
-  const u32 *parent[DIST_MAX_RANKS];  // every rank's parent array (global ranks), mapped peer memory
-  const u32 *gidscan[DIST_MAX_RANKS]; // every rank's exclusive scan of root flags
-  const u32 *lroot[DIST_MAX_RANKS];   // every rank's last-local-node table (local indices)
+  const u64 *res[DIST_MAX_RANKS];     // every rank's per-fragment word (k_chase_local), mapped peer memory
   u32 roff[DIST_MAX_RANKS + 1];       // first global rank of every rank
   int nr, me;
 };
@@ -294,9 +292,9 @@ int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaSt
 int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st);
 u64 dist_scan_work_bytes(u32 m);
 int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *work, cudaStream_t st);
-int dist_chase_local(const u32 *parent, u32 m, u32 lo, u32 *lroot, u32 *exits, u32 *n_exits, cudaStream_t st);
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u32 *parent, const u32 *lroot, const u32 *gidscan,
-                     const u32 *exits, const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st);
+int dist_chase_local(const u32 *parent, const u32 *gidscan, u32 m, u32 lo, u32 *lroot, u64 *res, u32 *exits, u32 *n_exits, cudaStream_t st);
+int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u64 *res, const u32 *lroot, const u32 *exits,
+                     const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st);
 int dist_or_rows(const u32 *all, u64 row_stride, int nr, u64 words, u32 *out, cudaStream_t st);
 
 // sort_groups as a function of (groups, diag_func): h = |y - d| per member, member index, zero identity (sol.cu)
