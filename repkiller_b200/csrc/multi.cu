@@ -133,6 +133,8 @@ struct NcclTransport : Transport {
     if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
+    for (auto &a : aux) if (a) cudaStreamDestroy(a);
+    for (auto &e : aux_ev) if (e) cudaEventDestroy(e);
   }
   int gather_small(const u32 *d_row, u32 *d_all, u32 *h_all, cudaStream_t st) override {
     int rc = check(nccl_api().AllGather(d_row, d_all, SMALL_WORDS * sizeof(u32), ncclUint8, comm, st), "ncclAllGather");
@@ -157,16 +159,8 @@ struct NcclTransport : Transport {
                  const u64 *poff, size_t elem, cudaStream_t st) override {
     const NcclApi &N = nccl_api();
     if (peers_mapped && !getenv_nccl_rows()) {
-      for (int k = 0; k < world; ++k) {
-        const int p = (rank + k) % world;
-        if (!scnt[p]) continue;
-        u8 *dst = (p == rank ? (u8 *)recv : on_peer(p, (u8 *)recv)) + poff[p] * elem;
-        if (cudaMemcpyAsync(dst, (const u8 *)send + soff[p] * elem, scnt[p] * elem, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-          err = std::string("all_to_all: peer copy failed: ") + cudaGetErrorString(cudaGetLastError());
-          return RK_ERR_CUDA;
-        }
-        if (p != rank) bytes_sent += scnt[p] * elem;
-      }
+      const int rc = push_blocks(send, soff, scnt, recv, poff, elem, st, st);
+      if (rc) return rc;
       return check(N.AllGather(d_flag, d_flag_all, 4, ncclUint8, comm, st), "ncclAllGather (barrier)");
     }
     if (scnt[rank]) {
@@ -198,16 +192,8 @@ struct NcclTransport : Transport {
     }
     cudaEventRecord(ev_a, st);
     cudaStreamWaitEvent(side, ev_a, 0);
-    for (int k = 0; k < world; ++k) {
-      const int p = (rank + k) % world;
-      if (!scnt[p]) continue;
-      u8 *dst = (p == rank ? (u8 *)recv : on_peer(p, (u8 *)recv)) + poff[p] * elem;
-      if (cudaMemcpyAsync(dst, (const u8 *)send + soff[p] * elem, scnt[p] * elem, cudaMemcpyDeviceToDevice, side) != cudaSuccess) {
-        err = std::string("a2a_begin: peer copy failed: ") + cudaGetErrorString(cudaGetLastError());
-        return RK_ERR_CUDA;
-      }
-      if (p != rank) bytes_sent += scnt[p] * elem;
-    }
+    const int rc = push_blocks(send, soff, scnt, recv, poff, elem, side, side);
+    if (rc) return rc;
     cudaEventRecord(ev_b, side);
     split_pending = true;
     return RK_OK;
@@ -217,6 +203,47 @@ struct NcclTransport : Transport {
     split_pending = false;
     cudaStreamWaitEvent(st, ev_b, 0);
     return check(nccl_api().AllGather(d_flag, d_flag_all, 4, ncclUint8, comm, st), "ncclAllGather (barrier)");
+  }
+  // This rank's blocks into the peers' receive buffers, peers in staggered order.  Large exchanges are spread over a few
+  // copy streams (one copy engine each), forked from `from` and joined into `into`: a single peer copy does not fill the
+  // links of a GPU (measured 550 GB/s for one copy at a time).
+  static constexpr int NAUX = 3;
+  cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
+  cudaEvent_t aux_ev[NAUX + 1] = {nullptr, nullptr, nullptr, nullptr};
+  int push_blocks(const void *send, const u64 *soff, const u64 *scnt, void *recv, const u64 *poff, size_t elem, cudaStream_t from,
+                  cudaStream_t into) {
+    u64 total = 0;
+    int peers = 0;
+    for (int p = 0; p < world; ++p)
+      if (p != rank && scnt[p]) total += scnt[p] * elem, ++peers;
+    const bool spread = peers > 1 && total >= (8u << 20);
+    if (spread && !aux[0]) {
+      for (int a = 0; a < NAUX; ++a) cudaStreamCreateWithFlags(&aux[a], cudaStreamNonBlocking);
+      for (int a = 0; a <= NAUX; ++a) cudaEventCreateWithFlags(&aux_ev[a], cudaEventDisableTiming);
+    }
+    if (spread) {
+      cudaEventRecord(aux_ev[NAUX], from);
+      for (int a = 0; a < NAUX; ++a) cudaStreamWaitEvent(aux[a], aux_ev[NAUX], 0);
+    }
+    int turn = 0;
+    for (int k = 0; k < world; ++k) {
+      const int p = (rank + k) % world;
+      if (!scnt[p]) continue;
+      u8 *dst = (p == rank ? (u8 *)recv : on_peer(p, (u8 *)recv)) + poff[p] * elem;
+      cudaStream_t cs = from;
+      if (spread && p != rank) cs = (turn % (NAUX + 1)) == NAUX ? from : aux[turn % (NAUX + 1)], ++turn;
+      if (cudaMemcpyAsync(dst, (const u8 *)send + soff[p] * elem, scnt[p] * elem, cudaMemcpyDeviceToDevice, cs) != cudaSuccess) {
+        err = std::string("all_to_all: peer copy failed: ") + cudaGetErrorString(cudaGetLastError());
+        return RK_ERR_CUDA;
+      }
+      if (p != rank) bytes_sent += scnt[p] * elem;
+    }
+    if (spread)
+      for (int a = 0; a < NAUX; ++a) {
+        cudaEventRecord(aux_ev[a], aux[a]);
+        cudaStreamWaitEvent(into, aux_ev[a], 0);
+      }
+    return RK_OK;
   }
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   bool split_pending = false;
