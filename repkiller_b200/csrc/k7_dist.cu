@@ -172,13 +172,21 @@ __global__ void __launch_bounds__(256) k_route_count(RouteArgs a, u32 *__restric
   }
 }
 
-// block d: tile_cnt[.][d] -> exclusive prefix over the tiles + start of destination d in the send buffer
-__global__ void __launch_bounds__(1024) k_tile_offsets(u32 *__restrict__ tile_cnt, u32 tiles, const u32 *__restrict__ counts) {
+// block d: tile_cnt[.][d] -> exclusive prefix over the tiles + where this rank's block for destination d starts:
+//   in the local send buffer (counts_all == nullptr): after the blocks for the lower destinations;
+//   in rank d's receive buffer (pushing straight into peer memory): after the blocks of the lower SOURCE ranks, from the
+//   all-gathered count matrix counts_all[s * row_stride + d] = what rank s sends to d.
+__global__ void __launch_bounds__(1024) k_tile_offsets(u32 *__restrict__ tile_cnt, u32 tiles, const u32 *__restrict__ counts,
+                                                       const u32 *__restrict__ counts_all, u32 row_stride, int me) {
   const int d = blockIdx.x;
   __shared__ u32 s_carry;
   if (threadIdx.x == 0) {
     u32 base = 0;
-    for (int r = 0; r < d; ++r) base += counts[r];
+    if (counts_all) {
+      for (int r = 0; r < me; ++r) base += counts_all[(u64)r * row_stride + d];
+    } else {
+      for (int r = 0; r < d; ++r) base += counts[r];
+    }
     s_carry = base;
   }
   __syncthreads();
@@ -195,13 +203,19 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(u32 *__restrict__ tile_cn
   }
 }
 
+// `out` of a payload: one pointer per destination — the local send buffer for all of them, or every rank's receive buffer
+// (mapped peer memory: the rows then cross NVLink as the stores of this kernel, no send buffer and no copy in between)
+struct RowOuts {
+  uint4 *p[DIST_MAX_RANKS];
+};
 struct PayRec32 {  // exchange 1: the whole 32-byte record
   const uint4 *rec;
-  uint4 *out;
-  __device__ __forceinline__ void operator()(u32 i, u32 pos) const {
+  RowOuts out;
+  __device__ __forceinline__ void operator()(u32 i, int d, u32 pos) const {
     const uint4 a = rec[2 * (u64)i], b = rec[2 * (u64)i + 1];
-    out[2 * (u64)pos] = a;
-    out[2 * (u64)pos + 1] = b;
+    uint4 *o = out.p[d] + 2 * (u64)pos;
+    o[0] = a;
+    o[1] = b;
   }
 };
 struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
@@ -209,7 +223,7 @@ struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
   const uint2 *cl;
   u32 rank_off, key_and;
   uint4 *out;
-  __device__ __forceinline__ void operator()(u32 i, u32 pos) const {
+  __device__ __forceinline__ void operator()(u32 i, int, u32 pos) const {
     const uint2 c = cl[i];
     out[pos] = make_uint4(keys[i] & key_and, c.x, c.y, rank_off + i);
   }
@@ -217,11 +231,11 @@ struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
 struct PayGidRow {  // output exchange: {h, file index, identity bits, gid}
   const uint4 *hfi_r;
   const u32 *gid_rank;
-  uint4 *out;
-  __device__ __forceinline__ void operator()(u32 i, u32 pos) const {
+  RowOuts out;
+  __device__ __forceinline__ void operator()(u32 i, int d, u32 pos) const {
     uint4 v = hfi_r[i];
     v.w = gid_rank[i];
-    out[pos] = v;
+    out.p[d][pos] = v;
   }
 };
 
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(256) k_split_pack(RouteArgs a, const u32 *__re
       u32 pos = s_run[d] + before;
       for (u32 q = 0; q < w; ++q) pos += s_w[q][d];
       if (pos < a.out_cap) {
-        pay((u32)i, pos);
+        pay((u32)i, d, pos);
         if (perm) perm[pos] = (u32)i;
       }
     }
@@ -513,14 +527,45 @@ static int split_pack(const RouteArgs &a, u32 *tile_cnt, u32 *counts, const Pay 
   const u32 tiles = (a.n + SPLIT_TILE - 1) / SPLIT_TILE;
   KScope ks(KID_DIST_ROWS, st, a.n);
   k_route_count<MODE><<<tiles, 256, 0, st>>>(a, tile_cnt, counts);
-  k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, counts);
+  k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, counts, nullptr, 0, 0);
   k_split_pack<MODE, Pay><<<tiles, 256, 0, st>>>(a, tile_cnt, pay, perm);
   return 3;
 }
-// exchange 1: local records (file order) -> send buffer ordered by destination; counts[nr] = dropped records
-int dist_split_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *out, u32 *tile_cnt,
-                       u32 *counts, cudaStream_t st) {
-  return split_pack<0>(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu}, tile_cnt, counts, PayRec32{rec, out}, nullptr, st);
+
+// The two big exchanges (records to the owner of their xStart/10 range; rows to the owner of their group-id range) in two
+// halves: count (per tile and per destination) — the counts of all ranks are then all-gathered on the device — and push:
+// every tile stores its rows straight into the destination ranks' receive buffers at the place the count matrix gives it.
+int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *tile_cnt, u32 *counts, cudaStream_t st) {
+  cudaMemsetAsync(counts, 0, (nr + 1) * sizeof(u32), st);
+  if (n == 0) return 0;
+  const u32 tiles = (n + SPLIT_TILE - 1) / SPLIT_TILE;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_route_count<0><<<tiles, 256, 0, st>>>(RouteArgs{keys, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu}, tile_cnt, counts);
+  return 1;
+}
+template <class Pay>
+static int push_rows(const RouteArgs &a, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, const Pay &pay, cudaStream_t st) {
+  if (a.n == 0) return 0;
+  const u32 tiles = (a.n + SPLIT_TILE - 1) / SPLIT_TILE;
+  KScope ks(KID_DIST_ROWS, st, a.n);
+  k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, nullptr, counts_all, row_stride, me);
+  k_split_pack<0, Pay><<<tiles, 256, 0, st>>>(a, tile_cnt, pay, nullptr);
+  return 2;
+}
+static RowOuts row_outs(uint4 *const *outs, int nr) {
+  RowOuts o{};
+  for (int d = 0; d < nr; ++d) o.p[d] = outs[d];
+  return o;
+}
+int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *const *outs, u32 out_cap,
+                      u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
+  return push_rows(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
+                   PayRec32{rec, row_outs(outs, nr)}, st);
+}
+int dist_push_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *const *outs, u32 out_cap, u32 *tile_cnt,
+                  const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
+  return push_rows(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
+                   PayGidRow{hfi_r, gid_rank, row_outs(outs, nr)}, st);
 }
 // X halo: the fragments whose X super-bucket belongs to another rank; perm[t] = local rank of the t-th row sent
 int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 rank_off, uint4 *out,
@@ -533,11 +578,6 @@ int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, in
                     u32 *tile_cnt, u32 *counts, cudaStream_t st) {
   return split_pack<0>(RouteArgs{keys, n, cuts, nr, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu}, tile_cnt, counts,
                        PayAxisRow{keys, cl, rank_off, 0xFFFFFFFFu, out}, perm, st);
-}
-// output exchange: every fragment to the owner of its group-id range
-int dist_split_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *out, u32 *tile_cnt, u32 *counts,
-                   cudaStream_t st) {
-  return split_pack<0>(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu}, tile_cnt, counts, PayGidRow{hfi_r, gid_rank, out}, nullptr, st);
 }
 static unsigned hist_grid(u64 n) {  // few CTAs: few histogram flushes
   const unsigned b = blocks_for(n), cap = (unsigned)sm_count() * 8;

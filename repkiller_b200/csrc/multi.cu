@@ -100,6 +100,12 @@ struct Transport {
   // every rank contributes SMALL_WORDS u32 from device memory; all rows land in h_all[world][SMALL_WORDS] (pinned).
   // Synchronises the stream.
   virtual int gather_small(const u32 *d_row, u32 *d_all, u32 *h_all, cudaStream_t st) = 0;
+  // The same in two halves: begin() leaves all rows in DEVICE memory d_all (stream-ordered: kernels queued behind it may
+  // read the other ranks' counts), end() brings them to the host and synchronises.
+  virtual int gather_small_begin(const u32 *d_row, u32 *d_all, u32 *h_all, cudaStream_t st) = 0;
+  virtual int gather_small_end(const u32 *d_all, u32 *h_all, cudaStream_t st) = 0;
+  // all ranks' streams meet: work queued behind it starts after every rank's work queued before it is complete
+  virtual int barrier(cudaStream_t st) = 0;
   // recv[world][bytes] <- every rank's send[bytes]; stream-ordered; doubles as a barrier between the ranks' streams
   virtual int all_gather(const void *send, void *recv, size_t bytes, cudaStream_t st) = 0;
   // variable all-to-all; offsets and counts in elements of `elem` bytes.  poff[p] = where this rank's block starts in
@@ -147,6 +153,19 @@ struct NcclTransport : Transport {
     }
     return RK_OK;
   }
+  int gather_small_begin(const u32 *d_row, u32 *d_all, u32 *, cudaStream_t st) override {
+    return check(nccl_api().AllGather(d_row, d_all, SMALL_WORDS * sizeof(u32), ncclUint8, comm, st), "ncclAllGather");
+  }
+  int gather_small_end(const u32 *d_all, u32 *h_all, cudaStream_t st) override {
+    cudaError_t e = cudaMemcpyAsync(h_all, d_all, (size_t)world * SMALL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      err = std::string("count exchange: ") + cudaGetErrorString(e);
+      return RK_ERR_CUDA;
+    }
+    return RK_OK;
+  }
+  int barrier(cudaStream_t st) override { return check(nccl_api().AllGather(d_flag, d_flag_all, 4, ncclUint8, comm, st), "ncclAllGather (barrier)"); }
   int all_gather(const void *send, void *recv, size_t bytes, cudaStream_t st) override {
     bytes_sent += bytes * (u64)(world - 1);
     return check(nccl_api().AllGather(send, recv, bytes, ncclUint8, comm, st), "ncclAllGather");
@@ -293,6 +312,17 @@ struct LocalTransport : Transport {
     for (int r = 0; r < world; ++r) memcpy(h_all + (size_t)r * SMALL_WORDS, g->small[r], SMALL_WORDS * sizeof(u32));
     g->barrier();
     return cuda(e, "count exchange");
+  }
+  int gather_small_begin(const u32 *d_row, u32 *d_all, u32 *h_all, cudaStream_t st) override {
+    const int rc = gather_small(d_row, d_all, h_all, st);  // the host exchange, then the matrix goes back to the device
+    if (rc) return rc;
+    return cuda(cudaMemcpyAsync(d_all, h_all, (size_t)world * SMALL_WORDS * sizeof(u32), cudaMemcpyHostToDevice, st), "count upload");
+  }
+  int gather_small_end(const u32 *, u32 *, cudaStream_t st) override { return cuda(cudaStreamSynchronize(st), "count exchange"); }
+  int barrier(cudaStream_t st) override {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    g->barrier();
+    return cuda(e, "barrier");
   }
   int all_gather(const void *send, void *recv, size_t bytes, cudaStream_t st) override {
     cudaError_t e = cudaStreamSynchronize(st);
@@ -674,6 +704,9 @@ static int dist_check_small(rk_ctx *ctx, bool range_errors) {
   return fail(ctx, (range_errors && !(e & (ERR_WORKLIST | ERR_SPIN))) ? RK_ERR_RANGE : RK_ERR_INTERNAL, "%s", err_bits_text(e));
 }
 
+// every rank's copy of one of this rank's arena buffers (the rows of the big exchanges are stored there by the kernels)
+static void peer_rows(const Dist &D, uint4 *local, uint4 **outs);
+
 static int dist_gather_counts(rk_ctx *ctx) {
   Dist &D = *ctx->dist;
   CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -769,11 +802,17 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   launches += dist_cuts_from_hist(pub_all, pub_words, nr, shift0, D.cuts0, st);
   launches += dist_or_rows(pub_all + DIST_BINS, pub_words, nr, lxw, linkx, st);
   launches += dist_or_rows(pub_all + DIST_BINS + lxw, pub_words, nr, lyw, linky, st);
-  launches += dist_split_records(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.rec4_loc, D.send_rows, D.tile_cnt, D.d_small + W_CNT_A, st);
-  {
-    const int rc = dist_gather_counts(ctx);  // host sync 1
-    if (rc) return rc;
-  }
+  // count per destination -> all ranks' counts on the device -> every tile stores its records straight into the owners'
+  // receive buffers (peer memory over NVLink) -> barrier; the host reads the count matrix while the rows travel
+  uint4 *outs[DIST_MAX_RANKS];
+  peer_rows(D, D.rec4_arr, outs);
+  launches += dist_count_plain(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.tile_cnt, D.d_small + W_CNT_A, st);
+  CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  TR(D.tr->gather_small_begin(D.d_small, D.d_small_all, D.h_small, st));
+  launches += dist_push_records(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.rec4_loc, outs, (u32)D.cap, D.tile_cnt, D.d_small_all,
+                                SMALL_WORDS, me, st);
+  TR(D.tr->barrier(st));
+  TR(D.tr->gather_small_end(D.d_small_all, D.h_small, st));  // host sync 1
   if (too_many || dist_check_small(ctx, true) != RK_OK) {
     u32 e = 0;
     for (int r = 0; r < nr; ++r) e |= D.h_small[(size_t)r * SMALL_WORDS + W_ERR];
@@ -782,6 +821,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
     return dist_check_small(ctx, true);
   }
   D.ex1.from_matrix(D.h_small, W_CNT_A, nr, me);
+  D.tr->bytes_sent += (D.ex1.n_send - D.ex1.scnt[me]) * 32;  // (the rows this rank's kernels stored into peer memory)
   u64 m_total = 0, loaded_total = 0;
   u64 m_of[DIST_MAX_RANKS] = {0};
   for (int s = 0; s < nr; ++s) {
@@ -802,7 +842,6 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   const u32 m = (u32)m_of[me];
   D.m_loc = m;
 
-  TR(D.tr->all_to_all(D.send_rows, D.ex1.soff, D.ex1.scnt, D.rec4_arr, D.ex1.roff, D.ex1.rcnt, D.ex1.poff, 32, st));
   CK(cudaEventRecord(ev[2], st));
   // processing order: sources arrive in file order, so a stable sort by xStart/10 is the global order
   launches += dist_key0_of_rec(D.rec4_arr, m, D.key0a, hist_of(0, D.bits_rank), st);
@@ -942,15 +981,21 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
   launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st);
   CK(cudaMemcpyAsync(D.d_small + W_CNT_B, D.cuts_g, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-  launches += dist_split_gid(D.gid_rank, D.hfi_r, m, D.cuts_g, nr, D.send_rows, D.tile_cnt, D.d_small + W_CNT_A, st);
+  uint4 *outs[DIST_MAX_RANKS];
+  peer_rows(D, D.recv_rows, outs);
+  launches += dist_count_plain(D.gid_rank, m, D.cuts_g, nr, 0xFFFFFFFFu, D.tile_cnt, D.d_small + W_CNT_A, st);
+  CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  TR(D.tr->gather_small_begin(D.d_small, D.d_small_all, D.h_small, st));
+  launches += dist_push_gid(D.gid_rank, D.hfi_r, m, D.cuts_g, nr, outs, (u32)D.cap, D.tile_cnt, D.d_small_all, SMALL_WORDS, me, st);
+  TR(D.tr->barrier(st));
+  TR(D.tr->gather_small_end(D.d_small_all, D.h_small, st));  // host sync 3
   {
-    const int rc = dist_gather_counts(ctx);  // host sync 3
-    if (rc) return rc;
     const int rc2 = dist_check_small(ctx, false);
     if (rc2) return rc2;
   }
   Exchange exg;
   exg.from_matrix(D.h_small, W_CNT_A, nr, me);
+  D.tr->bytes_sent += (exg.n_send - exg.scnt[me]) * 16;
   const u64 total_groups = D.h_small[(size_t)me * SMALL_WORDS + W_X1];
   u64 line_off = 0;
   for (int d = 0; d < nr; ++d) {
@@ -966,7 +1011,6 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   const u64 gid_end = (u64)cuts_h[me + 1] < total_groups ? (u64)cuts_h[me + 1] : total_groups;
   const u64 local_groups = gid_end > gid_base ? gid_end - gid_base : 1;
   const int bits_g = ceil_log2(local_groups) < 1 ? 1 : ceil_log2(local_groups);
-  TR(D.tr->all_to_all(D.send_rows, exg.soff, exg.scnt, D.recv_rows, exg.roff, exg.rcnt, exg.poff, 16, st));
   CK(cudaMemsetAsync(D.prehist + 3072, 0, 4 * 256 * 4, st));
   launches += dist_gid_keys(D.recv_rows, mg, gid_base, D.gid_a, HistOut{D.prehist + 3072, (bits_g + 7) / 8, bits_g}, st);
   CK(cudaEventRecord(ev[4], st));
@@ -1049,6 +1093,10 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
     info->bytes_sent = D.tr->bytes_sent - sent0;
   }
   return RK_OK;
+}
+
+static void peer_rows(const Dist &D, uint4 *local, uint4 **outs) {
+  for (int d = 0; d < D.world; ++d) outs[d] = d == D.rank ? local : D.tr->on_peer(d, local);
 }
 
 void dist_destroy(rk_ctx *c) {

@@ -274,14 +274,15 @@ int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, 
 int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st);
 int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st);
 u64 dist_split_work_bytes(u64 n);
-int dist_split_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *out, u32 *tile_cnt,
-                       u32 *counts, cudaStream_t st);
+int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *tile_cnt, u32 *counts, cudaStream_t st);
+int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *const *outs, u32 out_cap,
+                      u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st);
+int dist_push_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *const *outs, u32 out_cap, u32 *tile_cnt,
+                  const u32 *counts_all, u32 row_stride, int me, cudaStream_t st);
 int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 rank_off, uint4 *out,
                     u32 out_cap, u32 *perm, u32 *tile_cnt, u32 *counts, cudaStream_t st);
 int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, int nr, u32 rank_off, uint4 *out, u32 *perm,
                     u32 *tile_cnt, u32 *counts, cudaStream_t st);
-int dist_split_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *out, u32 *tile_cnt, u32 *counts,
-                   cudaStream_t st);
 int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, HistOut ho, cudaStream_t st);
 int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st);
 int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho, cudaStream_t st);
