@@ -248,7 +248,8 @@ rk_ctx *rk_create(int device) {
   if (cudaMalloc((void **)&c->st_cnt, sizeof(Counters)) != cudaSuccess) c->st_cnt = nullptr;
   // function attributes are per device: every context sets them for its own device (a process-wide flag would leave
   // the second device of a process without the shared-memory opt-in)
-  if ((e = decode_init_device()) != cudaSuccess || (e = sort_init_device()) != cudaSuccess || (e = order_init_device()) != cudaSuccess) {
+  if ((e = decode_init_device()) != cudaSuccess || (e = sort_init_device()) != cudaSuccess || (e = order_init_device()) != cudaSuccess ||
+      (e = dist_init_device()) != cudaSuccess) {
     set_create_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     rk_destroy(c);
     return nullptr;

@@ -211,12 +211,7 @@ struct RowOuts {
 struct PayRec32 {  // exchange 1: the whole 32-byte record
   const uint4 *rec;
   RowOuts out;
-  __device__ __forceinline__ void operator()(u32 i, int d, u32 pos) const {
-    const uint4 a = rec[2 * (u64)i], b = rec[2 * (u64)i + 1];
-    uint4 *o = out.p[d] + 2 * (u64)pos;
-    o[0] = a;
-    o[1] = b;
-  }
+  __device__ __forceinline__ void load(u32 i, uint4 *v) const { v[0] = rec[2 * (u64)i], v[1] = rec[2 * (u64)i + 1]; }
 };
 struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
   const u32 *keys;
@@ -232,10 +227,9 @@ struct PayGidRow {  // output exchange: {h, file index, identity bits, gid}
   const uint4 *hfi_r;
   const u32 *gid_rank;
   RowOuts out;
-  __device__ __forceinline__ void operator()(u32 i, int d, u32 pos) const {
-    uint4 v = hfi_r[i];
-    v.w = gid_rank[i];
-    out.p[d][pos] = v;
+  __device__ __forceinline__ void load(u32 i, uint4 *v) const {
+    v[0] = hfi_r[i];
+    v[0].w = gid_rank[i];
   }
 };
 
@@ -277,6 +271,94 @@ __global__ void __launch_bounds__(256) k_split_pack(RouteArgs a, const u32 *__re
       s_run[tid] += t;
     }
     __syncthreads();
+  }
+}
+
+// The push form of the split: rows of a tile are first gathered in shared memory, destination by destination, and then
+// stored to the destination ranks' receive buffers as contiguous runs (consecutive threads -> consecutive 16-byte words).
+// Row-by-row stores from the routing loop reach a peer as scattered 32-byte writes, which NVLink moves at a fraction of
+// its rate (measured at 8 GPUs: 1.7 ms per step in these kernels against 1.05 ms for the same rows through the copy engines).
+template <int WPR>
+struct PushSmem {
+  uint4 rows[SPLIT_TILE * WPR];
+  unsigned char dest[SPLIT_TILE];
+};
+template <int WPR, class Pay>
+__global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__restrict__ tile_off, Pay pay) {
+  extern __shared__ __align__(16) unsigned char push_smem_raw[];
+  PushSmem<WPR> &sm = *reinterpret_cast<PushSmem<WPR> *>(push_smem_raw);
+  __shared__ u32 s_cuts[DIST_MAX_RANKS + 2];
+  __shared__ u32 s_run[NRP], s_start[NRP], s_goff[NRP];
+  __shared__ u32 s_w[8][NRP];
+  const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < (u32)(a.nr + 1)) s_cuts[tid] = a.cuts[tid];
+  if (tid < (u32)NRP) {
+    s_run[tid] = 0;
+    s_goff[tid] = tid < (u32)a.nr ? tile_off[(u64)blockIdx.x * NRP + tid] : 0;
+  }
+  __syncthreads();
+  const u32 lt = lanemask_lt();
+  const u64 base = (u64)blockIdx.x * SPLIT_TILE;
+  int dsts[SPLIT_ROUNDS];
+  u32 ranks[SPLIT_ROUNDS];
+  // pass 1: destination and stable rank inside the destination (within the tile) of every element
+#pragma unroll
+  for (int j = 0; j < SPLIT_ROUNDS; ++j) {
+    const u64 i = base + (u64)j * 256 + tid;
+    const int d = i < a.n ? route_of<0>(a.keys[i], s_cuts, a) : -1;
+    u32 before = 0, cnt = 0;
+    for (int r = 0; r < a.nr; ++r) {
+      const u32 b = __ballot_sync(0xFFFFFFFFu, d == r);
+      if (d == r) before = __popc(b & lt);
+      if (lane == (u32)r) cnt = __popc(b);
+    }
+    if (lane < (u32)a.nr) s_w[w][lane] = cnt;
+    __syncthreads();
+    u32 pos = 0;
+    if (d >= 0 && d < a.nr) {
+      pos = s_run[d] + before;
+      for (u32 q = 0; q < w; ++q) pos += s_w[q][d];
+    }
+    dsts[j] = d;
+    ranks[j] = pos;
+    __syncthreads();
+    if (tid < (u32)a.nr) {
+      u32 t = 0;
+      for (int q = 0; q < 8; ++q) t += s_w[q][tid];
+      s_run[tid] += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    u32 run = 0;
+    for (int r = 0; r < a.nr; ++r) {
+      s_start[r] = run;
+      run += s_run[r];
+    }
+    s_start[a.nr] = run;
+  }
+  __syncthreads();
+  // pass 2: the rows into shared memory, grouped by destination
+#pragma unroll
+  for (int j = 0; j < SPLIT_ROUNDS; ++j) {
+    const int d = dsts[j];
+    if (d >= 0 && d < a.nr) {
+      const u32 slot = s_start[d] + ranks[j];
+      uint4 v[WPR];
+      pay.load((u32)(base + (u64)j * 256 + tid), v);
+#pragma unroll
+      for (int q = 0; q < WPR; ++q) sm.rows[slot * WPR + q] = v[q];
+      sm.dest[slot] = (unsigned char)d;
+    }
+  }
+  __syncthreads();
+  // copy-out: consecutive threads store consecutive 16-byte words of a destination's run
+  const u32 total = s_start[a.nr];
+  for (u32 x = tid; x < total * WPR; x += 256) {
+    const u32 slot = x / WPR, q = x % WPR;
+    const int d = sm.dest[slot];
+    const u32 pos = s_goff[d] + (slot - s_start[d]);
+    if (pos < a.out_cap) pay.out.p[d][(u64)pos * WPR + q] = sm.rows[x];
   }
 }
 
@@ -543,14 +625,19 @@ int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_k
   k_route_count<0><<<tiles, 256, 0, st>>>(RouteArgs{keys, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu}, tile_cnt, counts);
   return 1;
 }
-template <class Pay>
+template <int WPR, class Pay>
 static int push_rows(const RouteArgs &a, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, const Pay &pay, cudaStream_t st) {
   if (a.n == 0) return 0;
   const u32 tiles = (a.n + SPLIT_TILE - 1) / SPLIT_TILE;
   KScope ks(KID_DIST_ROWS, st, a.n);
   k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, nullptr, counts_all, row_stride, me);
-  k_split_pack<0, Pay><<<tiles, 256, 0, st>>>(a, tile_cnt, pay, nullptr);
+  k_push_rows<WPR, Pay><<<tiles, 256, sizeof(PushSmem<WPR>), st>>>(a, tile_cnt, pay);
   return 2;
+}
+cudaError_t dist_init_device() {  // dynamic shared memory opt-in of the push kernels (per device)
+  cudaError_t e = cudaFuncSetAttribute(k_push_rows<2, PayRec32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<2>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_push_rows<1, PayGidRow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<1>));
 }
 static RowOuts row_outs(uint4 *const *outs, int nr) {
   RowOuts o{};
@@ -559,13 +646,13 @@ static RowOuts row_outs(uint4 *const *outs, int nr) {
 }
 int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *const *outs, u32 out_cap,
                       u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
-                   PayRec32{rec, row_outs(outs, nr)}, st);
+  return push_rows<2>(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
+                      PayRec32{rec, row_outs(outs, nr)}, st);
 }
 int dist_push_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *const *outs, u32 out_cap, u32 *tile_cnt,
                   const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
-                   PayGidRow{hfi_r, gid_rank, row_outs(outs, nr)}, st);
+  return push_rows<1>(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
+                      PayGidRow{hfi_r, gid_rank, row_outs(outs, nr)}, st);
 }
 // X halo: the fragments whose X super-bucket belongs to another rank; perm[t] = local rank of the t-th row sent
 int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 rank_off, uint4 *out,

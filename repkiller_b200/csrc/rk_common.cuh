@@ -147,6 +147,7 @@ struct KScope {
 cudaError_t decode_init_device();
 cudaError_t sort_init_device();
 cudaError_t order_init_device();
+cudaError_t dist_init_device();
 
 // ---- launchers (each returns the number of kernels it launched) -------------------------------------
 
