@@ -368,14 +368,14 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
 // (HistOut), so that the sort needs no histogram pass of its own.  Warp-uniform loops: every lane votes in hist_add.
 
 // key0 = xStart / 10 of the arrived records (the sort key of the processing order)
-__global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ rec, u32 n, u32 *__restrict__ key0, HistOut ho) {
+__global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ rec, u32 n, u32 key_base, u32 *__restrict__ key0, HistOut ho) {
   __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
   hist_zero(s_h);
   __syncthreads();
   for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
     const u64 i = base + threadIdx.x;
     u32 k = 0;
-    if (i < n) key0[i] = k = rec[2 * i].x / XBUCKET;
+    if (i < n) key0[i] = k = rec[2 * i].x / XBUCKET - key_base;  // relative to the rank's first key: fewer sort passes
     hist_add(s_h, k, i < n, ho);
   }
   __syncthreads();
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ r
 }
 
 // arrival of the rows of one axis pass: keys[j], cl[j], grank[j] of row j
-__global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restrict__ rows, u32 n, u32 *__restrict__ keys,
+__global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restrict__ rows, u32 n, u32 key_base, u32 *__restrict__ keys,
                                                           uint2 *__restrict__ cl, u32 *__restrict__ grank, HistOut ho) {
   __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
   hist_zero(s_h);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restric
     u32 k = 0;
     if (j < n) {
       const uint4 r = rows[j];
-      keys[j] = k = r.x;
+      keys[j] = k = r.x - key_base;
       cl[j] = make_uint2(r.y, r.z);
       grank[j] = r.w;
     }
@@ -421,14 +421,24 @@ __global__ void __launch_bounds__(256) k_gid_keys(const uint4 *__restrict__ rows
 
 // X pass: the working list is [own fragments 0..m) ++ [halo m..m+nh).  parent_x[i] = list index of the owner or NONE.
 //   own i  -> parent[i] (global rank) ; halo j -> halo_res[j] (travels back to the fragment's home rank)
+// The three small per-pair exchanges (halo owners home, "matched in X" flags to the Y owners, Y owners home) have no
+// send buffer either: their values are already grouped by the rank they go to (arrival order = blocks by source, send
+// order = blocks by destination), so the kernel that produces them stores each block straight into its rank's buffer.
+template <class T>
+__device__ __forceinline__ void scatter_store(const ScatterTable &t, u32 j, T v) {
+  int d = 0;
+  for (int r = 1; r < t.nr; ++r) d = t.start[r] <= j ? r : d;  // block of position j
+  reinterpret_cast<T *>(t.out[d])[t.dst_off[d] + (j - t.start[d])] = v;
+}
+
 __global__ void __launch_bounds__(256) k_x_owners(const u32 *__restrict__ parent_x, u32 m, u32 nh, u32 rank_off,
-                                                  const u32 *__restrict__ halo_grank, u32 *__restrict__ parent, u32 *__restrict__ halo_res) {
+                                                  const u32 *__restrict__ halo_grank, u32 *__restrict__ parent, ScatterTable home) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m + nh) return;
   u32 o = parent_x[i];
   if (o != RK_NONE32) o = o < m ? rank_off + o : halo_grank[o - m];
   if (i < m) parent[i] = o;
-  else halo_res[i - m] = o;
+  else scatter_store<u32>(home, i - m, o);  // a halo fragment: its owner goes to the rank it came from
 }
 // the owners of the fragments this rank sent away come back in send order: away_perm[t] = local rank of the t-th
 __global__ void __launch_bounds__(256) k_apply_away(const u32 *__restrict__ away_res, const u32 *__restrict__ away_perm, u32 n,
@@ -436,17 +446,17 @@ __global__ void __launch_bounds__(256) k_apply_away(const u32 *__restrict__ away
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) parent[away_perm[t]] = away_res[t];
 }
-// "matched in the X pass" flags in the order the Y rows were sent
-__global__ void __launch_bounds__(256) k_pack_xm(const u32 *__restrict__ parent, const u32 *__restrict__ perm, u32 n, u8 *__restrict__ xm) {
+// "matched in the X pass" flags in the order the Y rows were sent, stored at the Y owners
+__global__ void __launch_bounds__(256) k_pack_xm(const u32 *__restrict__ parent, const u32 *__restrict__ perm, u32 n, ScatterTable owners) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) xm[t] = parent[perm[t]] != RK_NONE32 ? 1 : 0;
+  if (t < n) scatter_store<u8>(owners, t, parent[perm[t]] != RK_NONE32 ? 1 : 0);
 }
-// Y pass: parent_y[j] = arrival index of the owner or NONE -> its global rank
-__global__ void __launch_bounds__(256) k_y_owners(const u32 *__restrict__ parent_y, const u32 *__restrict__ grank, u32 n, u32 *__restrict__ out) {
+// Y pass: parent_y[j] = arrival index of the owner or NONE -> its global rank, stored at the fragment's home rank
+__global__ void __launch_bounds__(256) k_y_owners(const u32 *__restrict__ parent_y, const u32 *__restrict__ grank, u32 n, ScatterTable home) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const u32 o = parent_y[j];
-  out[j] = o == RK_NONE32 ? RK_NONE32 : grank[o];
+  scatter_store<u32>(home, j, o == RK_NONE32 ? RK_NONE32 : grank[o]);
 }
 // the Y owners come back in send order; a fragment matched in X keeps its X owner (commonFunctions.cpp:56-61)
 __global__ void __launch_bounds__(256) k_merge_y(const u32 *__restrict__ yo_back, const u32 *__restrict__ perm, u32 n, u32 *__restrict__ parent) {
@@ -670,15 +680,15 @@ static unsigned hist_grid(u64 n) {  // few CTAs: few histogram flushes
   const unsigned b = blocks_for(n), cap = (unsigned)sm_count() * 8;
   return b > cap ? cap : b;
 }
-int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, HistOut ho, cudaStream_t st) {
+int dist_key0_of_rec(const uint4 *rec, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
-  k_key0_of_rec<<<hist_grid(n), 256, 0, st>>>(rec, n, key0, ho);
+  k_key0_of_rec<<<hist_grid(n), 256, 0, st>>>(rec, n, key_base, key0, ho);
   return 1;
 }
-int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st) {
+int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 key_base, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
   KScope ks(KID_DIST_ROWS, st, n);
-  k_unpack_axis_rows<<<hist_grid(n), 256, 0, st>>>(rows, n, keys, cl, grank, ho);
+  k_unpack_axis_rows<<<hist_grid(n), 256, 0, st>>>(rows, n, key_base, keys, cl, grank, ho);
   return 1;
 }
 int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho, cudaStream_t st) {
@@ -686,9 +696,10 @@ int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho,
   k_gid_keys<<<hist_grid(n), 256, 0, st>>>(rows, n, gid_base, keys, ho);
   return 1;
 }
-int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, u32 *halo_res, cudaStream_t st) {
+int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, const ScatterTable &home,
+                  cudaStream_t st) {
   if (m + nh == 0) return 0;
-  k_x_owners<<<blocks_for((u64)m + nh), 256, 0, st>>>(parent_x, m, nh, rank_off, halo_grank, parent, halo_res);
+  k_x_owners<<<blocks_for((u64)m + nh), 256, 0, st>>>(parent_x, m, nh, rank_off, halo_grank, parent, home);
   return 1;
 }
 int dist_apply_away(const u32 *away_res, const u32 *away_perm, u32 n, u32 *parent, cudaStream_t st) {
@@ -696,14 +707,14 @@ int dist_apply_away(const u32 *away_res, const u32 *away_perm, u32 n, u32 *paren
   k_apply_away<<<blocks_for(n), 256, 0, st>>>(away_res, away_perm, n, parent);
   return 1;
 }
-int dist_pack_xm(const u32 *parent, const u32 *perm, u32 n, u8 *xm, cudaStream_t st) {
+int dist_pack_xm(const u32 *parent, const u32 *perm, u32 n, const ScatterTable &owners, cudaStream_t st) {
   if (n == 0) return 0;
-  k_pack_xm<<<blocks_for(n), 256, 0, st>>>(parent, perm, n, xm);
+  k_pack_xm<<<blocks_for(n), 256, 0, st>>>(parent, perm, n, owners);
   return 1;
 }
-int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaStream_t st) {
+int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, const ScatterTable &home, cudaStream_t st) {
   if (n == 0) return 0;
-  k_y_owners<<<blocks_for(n), 256, 0, st>>>(parent_y, grank, n, out);
+  k_y_owners<<<blocks_for(n), 256, 0, st>>>(parent_y, grank, n, home);
   return 1;
 }
 int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st) {

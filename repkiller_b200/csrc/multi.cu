@@ -85,12 +85,13 @@ static NcclApi &nccl_api() {
 // ---------------------------------------------------------------------------------------------------------------------
 // transports
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SMALL_WORDS = 48;  // per-rank row of the count exchanges
+constexpr int SMALL_WORDS = 64;  // per-rank row of the count exchanges
 constexpr int W_CNT_A = 0;       // [nr+1] destination counts (exchange 1 / X halo / output exchange)
 constexpr int W_CNT_B = 17;      // [nr+1] destination counts of the Y exchange
 constexpr int W_ERR = 40;        // device error word of the rank
 constexpr int W_X0 = 41;         // roots on the rank
 constexpr int W_X1 = 42;         // total groups
+constexpr int W_CUTS = 44;       // [nr+1] the cuts of the exchange (identical on every rank; the host sizes the local sort keys from them)
 
 struct Transport {
   int rank = 0, world = 1;
@@ -707,6 +708,24 @@ static int dist_check_small(rk_ctx *ctx, bool range_errors) {
 // every rank's copy of one of this rank's arena buffers (the rows of the big exchanges are stored there by the kernels)
 static void peer_rows(const Dist &D, uint4 *local, uint4 **outs);
 
+// block table of a per-pair exchange whose values the producing kernel stores straight into the peers' buffers:
+// forward = in send order (blocks by destination, landing where the rows of the load-time exchange landed),
+// back = in arrival order (blocks by source, landing in the order this rank's rows were sent)
+template <class T>
+static ScatterTable scatter_table(const Dist &D, const Exchange &ex, bool back, T *local_buf) {
+  ScatterTable t{};
+  t.nr = D.world;
+  u64 run = 0;
+  for (int d = 0; d < D.world; ++d) {
+    t.start[d] = (u32)run;
+    run += back ? ex.rcnt[d] : ex.scnt[d];
+    t.dst_off[d] = (u32)(back ? ex.rpoff[d] : ex.poff[d]);
+    t.out[d] = d == D.rank ? (void *)local_buf : (void *)D.tr->on_peer(d, local_buf);
+  }
+  t.start[D.world] = (u32)run;
+  return t;
+}
+
 static int dist_gather_counts(rk_ctx *ctx) {
   Dist &D = *ctx->dist;
   CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -808,6 +827,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   peer_rows(D, D.rec4_arr, outs);
   launches += dist_count_plain(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.tile_cnt, D.d_small + W_CNT_A, st);
   CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(D.d_small + W_CUTS, D.cuts0, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   TR(D.tr->gather_small_begin(D.d_small, D.d_small_all, D.h_small, st));
   launches += dist_push_records(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.rec4_loc, outs, (u32)D.cap, D.tile_cnt, D.d_small_all,
                                 SMALL_WORDS, me, st);
@@ -844,8 +864,13 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
 
   CK(cudaEventRecord(ev[2], st));
   // processing order: sources arrive in file order, so a stable sort by xStart/10 is the global order
-  launches += dist_key0_of_rec(D.rec4_arr, m, D.key0a, hist_of(0, D.bits_rank), st);
-  launches += launch_sort_pairs(D.key0a, nullptr, D.k0_r, D.aidx_r, D.tmp_k, D.tmp_v, m, D.bits_rank, D.sort_work, st, &D.cnt->err,
+  // the sort keys are taken relative to the rank's first xStart/10 bucket: log2(range of the rank) bits instead of log2(vsize)
+  const u32 *cuts0_h = D.h_small + (size_t)me * SMALL_WORDS + W_CUTS;
+  const u32 key0_base = cuts0_h[me];
+  const u64 key0_end = (me + 1 < nr && cuts0_h[me + 1] < g.vsize) ? cuts0_h[me + 1] : g.vsize;
+  const int bits_rank_l = ceil_log2(key0_end > key0_base ? key0_end - key0_base : 1) < 1 ? 1 : ceil_log2(key0_end - key0_base);
+  launches += dist_key0_of_rec(D.rec4_arr, m, key0_base, D.key0a, hist_of(0, bits_rank_l), st);
+  launches += launch_sort_pairs(D.key0a, nullptr, D.k0_r, D.aidx_r, D.tmp_k, D.tmp_v, m, bits_rank_l, D.sort_work, st, &D.cnt->err,
                                 m ? D.prehist : nullptr);
   CK(cudaEventRecord(ev[3], st));
   launches += launch_keys(D.aidx_r, m, g, D.rec4_arr, linkx, linky, D.xl, D.yl_r, D.ys_r, D.kx2, D.ky, D.identity_r, st,
@@ -862,6 +887,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
   launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_y, D.cuts_y, st);
   launches += dist_split_axis(D.ky, D.yl_r, m, D.cuts_y, nr, D.rank_off, D.send_rows, D.perm_y, D.tile_cnt, D.d_small + W_CNT_B, st);
+  CK(cudaMemcpyAsync(D.d_small + W_CUTS, D.cuts_y, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   {
     const int rc = dist_gather_counts(ctx);  // host sync 2
     if (rc) return rc;
@@ -884,18 +910,23 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
                                   (unsigned long long)y_in, (unsigned long long)D.cap);
   }
   D.n_away = (u32)D.exh.n_send, D.n_halo = (u32)D.exh.n_recv, D.m_y = (u32)D.exy.n_recv;
+  // Y sort keys relative to the first key of the rank's Y range
+  const u32 *cutsy_h = D.h_small + (size_t)me * SMALL_WORDS + W_CUTS;
+  const u32 ky_base = cutsy_h[me];
+  const u64 ky_end = (me + 1 < nr && cutsy_h[me + 1] < 2ull * g.nby) ? cutsy_h[me + 1] : 2ull * g.nby;
+  const int bits_y_l = ceil_log2(ky_end > ky_base ? ky_end - ky_base : 1) < 1 ? 1 : ceil_log2(ky_end - ky_base);
 
   TR(D.tr->all_to_all(D.halo_send, D.exh.soff, D.exh.scnt, D.halo_recv, D.exh.roff, D.exh.rcnt, D.exh.poff, 16, st));
   // the Y rows travel (copy engines, NVLink) while this GPU unpacks its halo and sorts its X buckets
   TR(D.tr->a2a_begin(D.send_rows, D.exy.soff, D.exy.scnt, D.recv_rows, D.exy.roff, D.exy.rcnt, D.exy.poff, 16, st, D.side));
-  launches += dist_unpack_axis_rows(D.halo_recv, D.n_halo, D.kx2 + m, D.xl + m, D.halo_grank, hist_of(1, D.bits_x + 1), st);
+  launches += dist_unpack_axis_rows(D.halo_recv, D.n_halo, 0, D.kx2 + m, D.xl + m, D.halo_grank, hist_of(1, D.bits_x + 1), st);
   CK(cudaEventRecord(ev[5], st));
   launches += launch_sort_pairs(D.kx2, nullptr, D.skx, D.rx, D.tmp_k, D.tmp_v, (u64)m + D.n_halo, D.bits_x + 1, D.sort_work, st, &D.cnt->err,
                                 (m + D.n_halo) ? D.prehist + 1024 : nullptr);
   CK(cudaEventRecord(ev[6], st));
   TR(D.tr->a2a_end(st));
-  launches += dist_unpack_axis_rows(D.recv_rows, D.m_y, D.ky_a, D.yl_a, D.grank_a, hist_of(2, D.bits_y), st);
-  launches += launch_sort_pairs(D.ky_a, nullptr, D.sky_a, D.ry_a, D.tmp_k, D.tmp_v, D.m_y, D.bits_y, D.sort_work, st, &D.cnt->err,
+  launches += dist_unpack_axis_rows(D.recv_rows, D.m_y, ky_base, D.ky_a, D.yl_a, D.grank_a, hist_of(2, bits_y_l), st);
+  launches += launch_sort_pairs(D.ky_a, nullptr, D.sky_a, D.ry_a, D.tmp_k, D.tmp_v, D.m_y, bits_y_l, D.sort_work, st, &D.cnt->err,
                                 D.m_y ? D.prehist + 2048 : nullptr);
   CK(cudaEventRecord(ev[7], st));
   D.loaded = true;
@@ -948,20 +979,20 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   mx.ent_rank = D.ent_rank, mx.ent_c = D.ent_c, mx.ent_len = D.ent_len, mx.err = &D.cnt->err;
   mx.key_shift = 1;
   launches += launch_match(mx, st);
-  launches += dist_x_owners(D.parent_x, m, nh, D.rank_off, D.halo_grank, D.parent, D.halo_res, st);
-  TR(D.tr->all_to_all(D.halo_res, D.exh.roff, D.exh.rcnt, D.away_res, D.exh.soff, D.exh.scnt, D.exh.rpoff, 4, st));
+  launches += dist_x_owners(D.parent_x, m, nh, D.rank_off, D.halo_grank, D.parent, scatter_table(D, D.exh, true, D.away_res), st);
+  TR(D.tr->barrier(st));  // the halo owners are stored by the kernel above straight into their home ranks' away_res
   launches += dist_apply_away(D.away_res, D.perm_x, D.n_away, D.parent, st);
   CK(cudaEventRecord(ev[1], st));
   // Y pass on the owners of the Y ranges: X-matched fragments insert without a query (commonFunctions.cpp:59)
-  launches += dist_pack_xm(D.parent, D.perm_y, m, D.xm_send, st);
-  TR(D.tr->all_to_all(D.xm_send, D.exy.soff, D.exy.scnt, D.xm_a, D.exy.roff, D.exy.rcnt, D.exy.poff, 1, st));
+  launches += dist_pack_xm(D.parent, D.perm_y, m, scatter_table(D, D.exy, false, D.xm_a), st);
+  TR(D.tr->barrier(st));
   if (D.m_y) CK(cudaMemsetAsync(D.parent_y, 0xFF, (size_t)D.m_y * 4, st));
   MatchArgs my = mx;
   my.skey = D.sky_a, my.srank = D.ry_a, my.cl_r = D.yl_a, my.parent = D.parent_y, my.m = D.m_y, my.max_index = D.g.my, my.is_y = 1;
   my.work_count = D.cnt->work_y, my.key_shift = 0, my.xm_bytes = D.xm_a;
   launches += launch_match(my, st);
-  launches += dist_y_owners(D.parent_y, D.grank_a, D.m_y, D.yo_a, st);
-  TR(D.tr->all_to_all(D.yo_a, D.exy.roff, D.exy.rcnt, D.yo_s, D.exy.soff, D.exy.scnt, D.exy.rpoff, 4, st));
+  launches += dist_y_owners(D.parent_y, D.grank_a, D.m_y, scatter_table(D, D.exy, true, D.yo_s), st);
+  TR(D.tr->barrier(st));
   launches += dist_merge_y(D.yo_s, D.perm_y, m, D.parent, st);
   CK(cudaEventRecord(ev[2], st));
   // forest: roots per rank, then every chain is followed to its root through the peers' parent arrays

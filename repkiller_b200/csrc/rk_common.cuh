@@ -270,6 +270,12 @@ struct PeerTable {                    // what a rank needs to follow a parent ch
   u32 roff[DIST_MAX_RANKS + 1];       // first global rank of every rank
   int nr, me;
 };
+struct ScatterTable {                 // positions 0..n of a kernel's output in nr consecutive blocks, block d stored on rank d
+  u32 start[DIST_MAX_RANKS + 1];      // first position of every block
+  u32 dst_off[DIST_MAX_RANKS];        // where block d starts in rank d's buffer
+  void *out[DIST_MAX_RANKS];          // that buffer on every rank (mapped peer memory; this rank's own for d == me)
+  int nr;
+};
 int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_key, u32 *hist, cudaStream_t st);
 int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st);
 int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st);
@@ -284,13 +290,14 @@ int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x,
                     u32 out_cap, u32 *perm, u32 *tile_cnt, u32 *counts, cudaStream_t st);
 int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, int nr, u32 rank_off, uint4 *out, u32 *perm,
                     u32 *tile_cnt, u32 *counts, cudaStream_t st);
-int dist_key0_of_rec(const uint4 *rec, u32 n, u32 *key0, HistOut ho, cudaStream_t st);
-int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st);
+int dist_key0_of_rec(const uint4 *rec, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st);
+int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 key_base, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st);
 int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho, cudaStream_t st);
-int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, u32 *halo_res, cudaStream_t st);
+int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, const ScatterTable &home,
+                  cudaStream_t st);
 int dist_apply_away(const u32 *away_res, const u32 *away_perm, u32 n, u32 *parent, cudaStream_t st);
-int dist_pack_xm(const u32 *parent, const u32 *perm, u32 n, u8 *xm, cudaStream_t st);
-int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, u32 *out, cudaStream_t st);
+int dist_pack_xm(const u32 *parent, const u32 *perm, u32 n, const ScatterTable &owners, cudaStream_t st);
+int dist_y_owners(const u32 *parent_y, const u32 *grank, u32 n, const ScatterTable &home, cudaStream_t st);
 int dist_merge_y(const u32 *yo_back, const u32 *perm, u32 n, u32 *parent, cudaStream_t st);
 u64 dist_scan_work_bytes(u32 m);
 int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *work, cudaStream_t st);
