@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(256) k_y_owners(const u32 *__restrict__ parent
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const u32 o = parent_y[j];
-  scatter_store<u32>(home, j, o == RK_NONE32 ? RK_NONE32 : grank[o]);
+  // only the matches travel: every rank fills its yo buffer with NONE before the ranks meet (a few per cent of the
+  // fragments have a Y owner)
+  if (o != RK_NONE32) scatter_store<u32>(home, j, grank[o]);
 }
 // the Y owners come back in send order; a fragment matched in X keeps its X owner (commonFunctions.cpp:56-61)
 __global__ void __launch_bounds__(256) k_merge_y(const u32 *__restrict__ yo_back, const u32 *__restrict__ perm, u32 n, u32 *__restrict__ parent) {

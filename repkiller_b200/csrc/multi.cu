@@ -985,6 +985,7 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   CK(cudaEventRecord(ev[1], st));
   // Y pass on the owners of the Y ranges: X-matched fragments insert without a query (commonFunctions.cpp:59)
   launches += dist_pack_xm(D.parent, D.perm_y, m, scatter_table(D, D.exy, false, D.xm_a), st);
+  if (m) CK(cudaMemsetAsync(D.yo_s, 0xFF, (size_t)m * 4, st));  // "no Y owner" until a peer stores one (after the barrier)
   TR(D.tr->barrier(st));
   if (D.m_y) CK(cudaMemsetAsync(D.parent_y, 0xFF, (size_t)D.m_y * 4, st));
   MatchArgs my = mx;
