@@ -33,8 +33,9 @@ METRIC = "fragments grouped/sec (device-timed)"
 UNIT = "fragments/s"
 CPU_SAMPLE_N = 1_000_000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {  # profiles/r01b_ncu_full_top_kernels.json (C2, 10M fragments), mean over the launches of a step
-    "k_match_small": 472000000, "k_radix_scatter": 98000000, "k_keys": 1429000000, "k_decode": 1430000000,
+NCU_TRAFFIC = {  # profiles/r02_ncu_full_top_kernels.json (C2, 10M fragments), mean over the captured launches
+    "k_radix_scatter": 98700000, "k_match_small": 441900000, "k_keys": 947500000, "k_decode": 1428600000,
+    "k_order_tile": 416200000, "k_hkey": 313600000, "k_chase": 118700000, "k_groupsort_warp": 133600000,
 }
 
 

@@ -84,10 +84,10 @@ __global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__
 }
 
 // group-id cuts: cuts[r] = floor(total_groups * r / nr) from the all-gathered root counts; also the total
-__global__ void k_cuts_gid(const u32 *__restrict__ nroots_all, int nr, u32 *__restrict__ cuts, u32 *__restrict__ total_out) {
+__global__ void k_cuts_gid(const u32 *__restrict__ nroots, u32 stride, int nr, u32 *__restrict__ cuts, u32 *__restrict__ total_out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     unsigned long long total = 0;
-    for (int r = 0; r < nr; ++r) total += nroots_all[r];
+    for (int r = 0; r < nr; ++r) total += nroots[(u64)r * stride];
     for (int r = 0; r < nr; ++r) cuts[r] = (u32)(total * (unsigned long long)r / (unsigned long long)nr);
     cuts[nr] = 0xFFFFFFFFu;
     *total_out = (u32)total;
@@ -122,7 +122,9 @@ struct RouteArgs {
   int nr, me;
   u32 drop_key, nbx;
   u32 out_cap;  // rows the send buffer holds: nothing is written past it (the host checks the counts afterwards)
+  const u32 *n_ptr;  // when set: the number of elements lives on the device (n is then the launch bound)
 };
+__device__ __forceinline__ u32 route_n(const RouteArgs &a) { return a.n_ptr ? min(*a.n_ptr, a.n) : a.n; }
 constexpr int SPLIT_ROUNDS = 8;
 constexpr int SPLIT_TILE = 256 * SPLIT_ROUNDS;
 constexpr int NRP = DIST_MAX_RANKS + 1;
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) k_route_count(RouteArgs a, u32 *__restric
 #pragma unroll
   for (int j = 0; j < SPLIT_ROUNDS; ++j) {
     const u64 i = base + (u64)j * 256 + threadIdx.x;
-    const int d = i < a.n ? route_of<MODE>(a.keys[i], s_cuts, a) : -1;
+    const int d = i < route_n(a) ? route_of<MODE>(a.keys[i], s_cuts, a) : -1;
     for (int r = 0; r <= a.nr; ++r) {
       const u32 b = __ballot_sync(0xFFFFFFFFu, d == r);
       if (lane == (u32)r) acc += __popc(b);
@@ -233,6 +235,12 @@ struct PayGidRow {  // output exchange: {h, file index, identity bits, gid}
   }
 };
 
+struct PayQuery {  // forest: "what is behind global rank keys[i]?" asked of the rank that owns it
+  const u32 *keys;
+  RowOuts out;
+  __device__ __forceinline__ void load(u32 i, uint4 *v) const { v[0] = make_uint4(keys[i], 0u, 0u, 0u); }
+};
+
 template <int MODE, class Pay>
 __global__ void __launch_bounds__(256) k_split_pack(RouteArgs a, const u32 *__restrict__ tile_off, Pay pay, u32 *__restrict__ perm) {
   __shared__ u32 s_cuts[2 * DIST_MAX_RANKS + 2];
@@ -283,8 +291,11 @@ struct PushSmem {
   uint4 rows[SPLIT_TILE * WPR];
   unsigned char dest[SPLIT_TILE];
 };
+// apos (optional): for every element, the position of its row in this rank's SEND order (blocks by destination) — where
+// a value that the destination returns block by block will land; needs the count matrix to undo the receiver offsets.
 template <int WPR, class Pay>
-__global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__restrict__ tile_off, Pay pay) {
+__global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__restrict__ tile_off, Pay pay, u32 *__restrict__ apos,
+                                                   const u32 *__restrict__ counts_all, u32 row_stride) {
   extern __shared__ __align__(16) unsigned char push_smem_raw[];
   PushSmem<WPR> &sm = *reinterpret_cast<PushSmem<WPR> *>(push_smem_raw);
   __shared__ u32 s_cuts[DIST_MAX_RANKS + 2];
@@ -292,9 +303,16 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
   __shared__ u32 s_w[8][NRP];
   const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid < (u32)(a.nr + 1)) s_cuts[tid] = a.cuts[tid];
+  __shared__ u32 s_back[NRP];  // send-order position minus receiver position of this rank's block for destination d
   if (tid < (u32)NRP) {
     s_run[tid] = 0;
     s_goff[tid] = tid < (u32)a.nr ? tile_off[(u64)blockIdx.x * NRP + tid] : 0;
+    u32 soff = 0, poff = 0;
+    if (apos && tid < (u32)a.nr) {
+      for (int r = 0; r < a.me; ++r) poff += counts_all[(u64)r * row_stride + tid];
+      for (u32 r = 0; r < tid; ++r) soff += counts_all[(u64)a.me * row_stride + r];
+    }
+    s_back[tid] = soff - poff;
   }
   __syncthreads();
   const u32 lt = lanemask_lt();
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
 #pragma unroll
   for (int j = 0; j < SPLIT_ROUNDS; ++j) {
     const u64 i = base + (u64)j * 256 + tid;
-    const int d = i < a.n ? route_of<0>(a.keys[i], s_cuts, a) : -1;
+    const int d = i < route_n(a) ? route_of<0>(a.keys[i], s_cuts, a) : -1;
     u32 before = 0, cnt = 0;
     for (int r = 0; r < a.nr; ++r) {
       const u32 b = __ballot_sync(0xFFFFFFFFu, d == r);
@@ -346,6 +364,7 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
       const u32 slot = s_start[d] + ranks[j];
       uint4 v[WPR];
       pay.load((u32)(base + (u64)j * 256 + tid), v);
+      if (apos) apos[base + (u64)j * 256 + tid] = s_goff[d] + ranks[j] + s_back[d];
 #pragma unroll
       for (int q = 0; q < WPR; ++q) sm.rows[slot * WPR + q] = v[q];
       sm.dest[slot] = (unsigned char)d;
@@ -477,41 +496,66 @@ __global__ void k_store_total(const u32 *total, u32 *out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *out = *total;
 }
 
-// Group ids in three steps, so that NVLink is only crossed where a chain really leaves the GPU:
+// Group ids, so that NVLink is only crossed where a chain really leaves the GPU:
 //   A  every fragment follows its parents while they are LOCAL to the last local node of its chain (lroot) — a root of the
 //      forest, or an "exit" whose parent lives on a lower GPU (parents always have a smaller global rank) — and publishes
 //      what a walker arriving at this fragment needs as ONE 64-bit word: res[i] = ROOT | (roots before lroot on this GPU),
-//      or the global rank of the exit's parent.  The exits are collected in a list.
-//   B  every exit walks on through the peers' res[]: one 8-byte NVLink read per GPU it visits, until it meets a root.
-//      Only the exits run here (a few per cent of the fragments), all of them in flight at once: the walk is a chain of
-//      NVLink round trips, and fine-grained remote reads are what the link is slowest at (measured: ~2 M reads per ms).
+//      or the global rank of the exit's parent.  The exits are collected in a pending list (fragment, rank to ask about).
+//   B  the pending list is resolved.  In bulk rounds while it is long: the ranks asked about are pushed to their owners
+//      (the split/push kernels of the row exchanges), the owners answer with their res[] word, block by block, and an
+//      answer is either a root (done) or the next rank to ask about.  A short list is walked by its own threads through
+//      the peers' res[] — one 8-byte NVLink read per GPU visited; fine-grained remote reads run at about 1 M per ms, which
+//      is fine for a few hundred thousand exits and hopeless for the tens of millions of a dense 1e9-fragment comparison
+//      (measured: 412 ms there).
 //   C  everybody takes the id of its lroot (a local root: from res; an exit: from B).
 constexpr u64 RES_ROOT = 1ull << 63;
 
-__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, const u32 *__restrict__ gidscan, u32 m, u32 lo,
-                                                     u32 *__restrict__ lroot, u64 *__restrict__ res, u32 *__restrict__ exits,
-                                                     u32 *__restrict__ n_exits) {
-  // The exits of a CTA are staged in shared memory and appended to the list a couple of thousand at a time: a global atomic
-  // per warp on the one list counter costs more than the whole chase (measured: +0.3 ms on the GPU with the most exits).
-  constexpr u32 CAP = 2048;
-  __shared__ u32 s_buf[CAP];
-  __shared__ u32 s_n, s_base;
-  if (threadIdx.x == 0) s_n = 0;
+// appends (idx, key) pairs of a CTA to a global list through a shared-memory stage (a global atomic per warp on the one list
+// counter costs more than the whole chase: measured +0.3 ms on the GPU with the most exits)
+struct PendStage {
+  static constexpr u32 CAP = 2048;
+  u32 idx[CAP], key[CAP];
+  u32 n, base;
+};
+__device__ __forceinline__ void pend_flush(PendStage &sg, u32 *__restrict__ out_idx, u32 *__restrict__ out_key, u32 *__restrict__ n_out) {
+  if (threadIdx.x == 0) sg.base = sg.n ? atomicAdd(n_out, sg.n) : 0;
   __syncthreads();
+  for (u32 k = threadIdx.x; k < sg.n; k += blockDim.x) out_idx[sg.base + k] = sg.idx[k], out_key[sg.base + k] = sg.key[k];
+  __syncthreads();
+  if (threadIdx.x == 0) sg.n = 0;
+  __syncthreads();
+}
+// every thread of the CTA calls this once per loop iteration (uniform control flow); 256 threads add at most 256 pairs
+__device__ __forceinline__ void pend_push(PendStage &sg, bool add, u32 idx, u32 key, u32 *__restrict__ out_idx, u32 *__restrict__ out_key,
+                                          u32 *__restrict__ n_out) {
   const u32 lane = threadIdx.x & 31;
-  auto flush = [&]() {  // all threads of the CTA
-    if (threadIdx.x == 0) s_base = s_n ? atomicAdd(n_exits, s_n) : 0;
-    __syncthreads();
-    for (u32 k = threadIdx.x; k < s_n; k += blockDim.x) exits[s_base + k] = s_buf[k];
-    __syncthreads();
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-  };
+  const u32 bal = __ballot_sync(0xFFFFFFFFu, add);
+  if (bal) {
+    u32 off = 0;
+    const int leader = __ffs(bal) - 1;
+    if ((int)lane == leader) off = atomicAdd(&sg.n, (u32)__popc(bal));
+    off = __shfl_sync(0xFFFFFFFFu, off, leader);
+    if (add) {
+      const u32 slot = off + __popc(bal & lanemask_lt());
+      sg.idx[slot] = idx, sg.key[slot] = key;
+    }
+  }
+  __syncthreads();
+  if (sg.n > PendStage::CAP - 256) pend_flush(sg, out_idx, out_key, n_out);
+}
+
+__global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ parent, const u32 *__restrict__ gidscan, u32 m, u32 lo,
+                                                     u32 *__restrict__ lroot, u64 *__restrict__ res, u32 *__restrict__ pend_idx,
+                                                     u32 *__restrict__ pend_key, u32 *__restrict__ n_pend) {
+  __shared__ PendStage sg;
+  if (threadIdx.x == 0) sg.n = 0;
+  __syncthreads();
   for (u64 base = (u64)blockIdx.x * blockDim.x; base < m; base += (u64)gridDim.x * blockDim.x) {
     const u64 i = base + threadIdx.x;
     bool is_exit = false;
+    u32 p = RK_NONE32;
     if (i < m) {
-      u32 r = (u32)i, p;
+      u32 r = (u32)i;
       for (;;) {
         p = parent[r];
         if (p == RK_NONE32 || p < lo) break;  // a root, or the parent is on a lower GPU
@@ -521,51 +565,86 @@ __global__ void __launch_bounds__(256) k_chase_local(const u32 *__restrict__ par
       res[i] = p == RK_NONE32 ? (RES_ROOT | gidscan[r]) : (u64)p;
       is_exit = r == (u32)i && p != RK_NONE32;
     }
-    const u32 bal = __ballot_sync(0xFFFFFFFFu, is_exit);
-    if (bal) {
-      u32 off = 0;
-      const int leader = __ffs(bal) - 1;
-      if ((int)lane == leader) off = atomicAdd(&s_n, (u32)__popc(bal));
-      off = __shfl_sync(0xFFFFFFFFu, off, leader);
-      if (is_exit) s_buf[off + __popc(bal & lanemask_lt())] = (u32)i;
-    }
-    __syncthreads();
-    if (s_n > CAP - 256) flush();  // (uniform: s_n is read after the barrier by every thread)
+    pend_push(sg, is_exit, (u32)i, p, pend_idx, pend_key, n_pend);
   }
-  flush();
+  pend_flush(sg, pend_idx, pend_key, n_pend);
 }
 
-__global__ void __launch_bounds__(256) k_chase_exits(PeerTable pt, const u32 *__restrict__ nroots_all, const u32 *__restrict__ exits,
-                                                     const u32 *__restrict__ n_exits, u32 *__restrict__ gid_l) {
-  __shared__ u32 s_groot[DIST_MAX_RANKS];
+// roots on every rank: nroots[r * stride] (a column of the all-gathered count matrix)
+__device__ __forceinline__ void load_groot(u32 *s_groot, const u32 *__restrict__ nroots, u32 stride, int nr) {
   if (threadIdx.x == 0) {
     u32 run = 0;
-    for (int r = 0; r < pt.nr; ++r) {
+    for (int r = 0; r < nr; ++r) {
       s_groot[r] = run;
-      run += nroots_all[r];
+      run += nroots[(u64)r * stride];
     }
   }
   __syncthreads();
-  const u32 n = *n_exits;
+}
+
+// B, short list: every pending fragment walks through the peers' res[]
+__global__ void __launch_bounds__(256) k_chase_walk(PeerTable pt, const u32 *__restrict__ nroots, u32 stride, const u32 *__restrict__ pend_idx,
+                                                    const u32 *__restrict__ pend_key, const u32 *__restrict__ n_pend, u32 *__restrict__ gid_l) {
+  __shared__ u32 s_groot[DIST_MAX_RANKS];
+  load_groot(s_groot, nroots, stride, pt.nr);
+  const u32 n = *n_pend;
   for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const u32 i = exits[t];
     int s = pt.me;
-    u64 w = pt.res[s][i];  // an exit: the global rank of its parent, on a lower GPU
+    u64 w = pend_key[t];  // the global rank to ask about, on a lower GPU
     do {
       const u32 p = (u32)w;
       while (p < pt.roff[s]) --s;  // global rank p lives on the last rank whose offset is <= p
       w = pt.res[s][p - pt.roff[s]];
     } while (!(w & RES_ROOT));
-    gid_l[i] = s_groot[s] + (u32)w;
+    gid_l[pend_idx[t]] = s_groot[s] + (u32)w;
   }
 }
 
+// B, bulk round, owner side: the res[] word of every rank asked about, back to the asking rank block by block
+__global__ void __launch_bounds__(256) k_chase_answer(const uint4 *__restrict__ queries, u32 n, const u64 *__restrict__ res, u32 lo,
+                                                      ScatterTable back) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) scatter_store<unsigned long long>(back, j, (unsigned long long)res[queries[j].x - lo]);
+}
+
+// B, bulk round, asking side: a root ends the walk, anything else is the next rank to ask about
+__global__ void __launch_bounds__(256) k_chase_apply(PeerTable pt, const u32 *__restrict__ nroots, u32 stride, const u32 *__restrict__ pend_idx,
+                                                     const u32 *__restrict__ pend_key, const u32 *__restrict__ apos, const u64 *__restrict__ ans,
+                                                     const u32 *__restrict__ n_pend, u32 *__restrict__ gid_l, u32 *__restrict__ next_idx,
+                                                     u32 *__restrict__ next_key, u32 *__restrict__ n_next) {
+  __shared__ u32 s_groot[DIST_MAX_RANKS];
+  __shared__ PendStage sg;
+  if (threadIdx.x == 0) sg.n = 0;
+  load_groot(s_groot, nroots, stride, pt.nr);
+  const u32 n = *n_pend;
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 t = base + threadIdx.x;
+    bool again = false;
+    u32 idx = 0, key = 0;
+    if (t < n) {
+      idx = pend_idx[t];
+      const u32 p = pend_key[t];
+      const u64 w = ans[apos[t]];
+      if (w & RES_ROOT) {
+        int s = pt.me;
+        while (p < pt.roff[s]) --s;  // the rank that answered: the owner of p
+        gid_l[idx] = s_groot[s] + (u32)w;
+      } else {
+        again = true;
+        key = (u32)w;
+      }
+    }
+    pend_push(sg, again, idx, key, next_idx, next_key, n_next);
+  }
+  pend_flush(sg, next_idx, next_key, n_next);
+}
+
 __global__ void __launch_bounds__(256) k_chase_map(const u64 *__restrict__ res, const u32 *__restrict__ lroot, const u32 *__restrict__ gid_l,
-                                                   const u32 *__restrict__ nroots_all, int me, u32 m, u32 *__restrict__ gid_rank) {
+                                                   const u32 *__restrict__ nroots, u32 stride, int me, u32 m, u32 *__restrict__ gid_rank) {
   __shared__ u32 s_base;
   if (threadIdx.x == 0) {
     u32 run = 0;
-    for (int r = 0; r < me; ++r) run += nroots_all[r];
+    for (int r = 0; r < me; ++r) run += nroots[(u64)r * stride];
     s_base = run;
   }
   __syncthreads();
@@ -604,8 +683,8 @@ int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, 
   k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, row_stride, nr, shift, cuts);
   return 1;
 }
-int dist_cuts_gid(const u32 *nroots_all, int nr, u32 *cuts, u32 *total, cudaStream_t st) {
-  k_cuts_gid<<<1, 32, 0, st>>>(nroots_all, nr, cuts, total);
+int dist_cuts_gid(const u32 *nroots, u32 stride, int nr, u32 *cuts, u32 *total, cudaStream_t st) {
+  k_cuts_gid<<<1, 32, 0, st>>>(nroots, stride, nr, cuts, total);
   return 1;
 }
 int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st) {
@@ -629,25 +708,29 @@ static int split_pack(const RouteArgs &a, u32 *tile_cnt, u32 *counts, const Pay 
 // The two big exchanges (records to the owner of their xStart/10 range; rows to the owner of their group-id range) in two
 // halves: count (per tile and per destination) — the counts of all ranks are then all-gathered on the device — and push:
 // every tile stores its rows straight into the destination ranks' receive buffers at the place the count matrix gives it.
-int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *tile_cnt, u32 *counts, cudaStream_t st) {
+int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *tile_cnt, u32 *counts, cudaStream_t st,
+                     const u32 *n_ptr) {
   cudaMemsetAsync(counts, 0, (nr + 1) * sizeof(u32), st);
   if (n == 0) return 0;
   const u32 tiles = (n + SPLIT_TILE - 1) / SPLIT_TILE;
   KScope ks(KID_DIST_ROWS, st, n);
-  k_route_count<0><<<tiles, 256, 0, st>>>(RouteArgs{keys, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu}, tile_cnt, counts);
+  k_route_count<0><<<tiles, 256, 0, st>>>(RouteArgs{keys, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu, n_ptr}, tile_cnt, counts);
   return 1;
 }
 template <int WPR, class Pay>
-static int push_rows(const RouteArgs &a, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, const Pay &pay, cudaStream_t st) {
+static int push_rows(const RouteArgs &a, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, const Pay &pay, cudaStream_t st,
+                     u32 *apos = nullptr) {
   if (a.n == 0) return 0;
   const u32 tiles = (a.n + SPLIT_TILE - 1) / SPLIT_TILE;
   KScope ks(KID_DIST_ROWS, st, a.n);
   k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, nullptr, counts_all, row_stride, me);
-  k_push_rows<WPR, Pay><<<tiles, 256, sizeof(PushSmem<WPR>), st>>>(a, tile_cnt, pay);
+  k_push_rows<WPR, Pay><<<tiles, 256, sizeof(PushSmem<WPR>), st>>>(a, tile_cnt, pay, apos, counts_all, row_stride);
   return 2;
 }
 cudaError_t dist_init_device() {  // dynamic shared memory opt-in of the push kernels (per device)
   cudaError_t e = cudaFuncSetAttribute(k_push_rows<2, PayRec32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<2>));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_push_rows<1, PayQuery>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<1>));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_push_rows<1, PayGidRow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<1>));
 }
@@ -658,24 +741,24 @@ static RowOuts row_outs(uint4 *const *outs, int nr) {
 }
 int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *const *outs, u32 out_cap,
                       u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows<2>(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
+  return push_rows<2>(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap, nullptr}, tile_cnt, counts_all, row_stride, me,
                       PayRec32{rec, row_outs(outs, nr)}, st);
 }
 int dist_push_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *const *outs, u32 out_cap, u32 *tile_cnt,
                   const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows<1>(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap}, tile_cnt, counts_all, row_stride, me,
+  return push_rows<1>(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap, nullptr}, tile_cnt, counts_all, row_stride, me,
                       PayGidRow{hfi_r, gid_rank, row_outs(outs, nr)}, st);
 }
 // X halo: the fragments whose X super-bucket belongs to another rank; perm[t] = local rank of the t-th row sent
 int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 rank_off, uint4 *out,
                     u32 out_cap, u32 *perm, u32 *tile_cnt, u32 *counts, cudaStream_t st) {
-  return split_pack<1>(RouteArgs{keys2, n, cuts_x, nr, me, 0xFFFFFFFFu, nbx, out_cap}, tile_cnt, counts,
+  return split_pack<1>(RouteArgs{keys2, n, cuts_x, nr, me, 0xFFFFFFFFu, nbx, out_cap, nullptr}, tile_cnt, counts,
                        PayAxisRow{keys2, cl, rank_off, 0xFFFFFFFEu, out}, perm, st);
 }
 // Y pass: every fragment to the owner of its Y super-bucket range
 int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, int nr, u32 rank_off, uint4 *out, u32 *perm,
                     u32 *tile_cnt, u32 *counts, cudaStream_t st) {
-  return split_pack<0>(RouteArgs{keys, n, cuts, nr, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu}, tile_cnt, counts,
+  return split_pack<0>(RouteArgs{keys, n, cuts, nr, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu, nullptr}, tile_cnt, counts,
                        PayAxisRow{keys, cl, rank_off, 0xFFFFFFFFu, out}, perm, st);
 }
 static unsigned hist_grid(u64 n) {  // few CTAs: few histogram flushes
@@ -737,26 +820,55 @@ int dist_root_scan(const u32 *parent, u32 m, u32 *gidscan, u32 *nroots, void *wo
   k_store_total<<<1, 32, 0, st>>>(bsum + nb, nroots);
   return l + 1;
 }
-int dist_chase_local(const u32 *parent, const u32 *gidscan, u32 m, u32 lo, u32 *lroot, u64 *res, u32 *exits, u32 *n_exits, cudaStream_t st) {
-  cudaMemsetAsync(n_exits, 0, sizeof(u32), st);
+int dist_chase_local(const u32 *parent, const u32 *gidscan, u32 m, u32 lo, u32 *lroot, u64 *res, u32 *pend_idx, u32 *pend_key, u32 *n_pend,
+                     cudaStream_t st) {
+  cudaMemsetAsync(n_pend, 0, sizeof(u32), st);
   if (m == 0) return 0;
   KScope ks(KID_CHASE, st, m);
   unsigned grid = blocks_for(m);
   const unsigned cap = (unsigned)sm_count() * 8;
-  k_chase_local<<<grid > cap ? cap : grid, 256, 0, st>>>(parent, gidscan, m, lo, lroot, res, exits, n_exits);
+  k_chase_local<<<grid > cap ? cap : grid, 256, 0, st>>>(parent, gidscan, m, lo, lroot, res, pend_idx, pend_key, n_pend);
   return 1;
 }
-int dist_chase_peers(const PeerTable &pt, const u32 *nroots_all, u32 m, const u64 *res, const u32 *lroot, const u32 *exits,
-                     const u32 *n_exits, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
+// one bulk round, asking side, first half: the ranks asked about go to their owners (cuts = the ranks' first global ranks)
+int dist_chase_ask_count(const u32 *pend_key, u32 bound, const u32 *n_pend, const u32 *roff_dev, int nr, u32 *tile_cnt, u32 *counts,
+                         cudaStream_t st) {
+  return dist_count_plain(pend_key, bound, roff_dev, nr, 0xFFFFFFFFu, tile_cnt, counts, st, n_pend);
+}
+int dist_chase_ask_push(const u32 *pend_key, u32 bound, const u32 *n_pend, const u32 *roff_dev, int nr, uint4 *const *outs, u32 out_cap,
+                        u32 *apos, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
+  return push_rows<1>(RouteArgs{pend_key, bound, roff_dev, nr, me, 0xFFFFFFFFu, 0, out_cap, n_pend}, tile_cnt, counts_all, row_stride, me,
+                      PayQuery{pend_key, row_outs(outs, nr)}, st, apos);
+}
+int dist_chase_answer(const uint4 *queries, u32 n, const u64 *res, u32 lo, const ScatterTable &back, cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_CHASE_EXITS, st, n);
+  k_chase_answer<<<blocks_for(n), 256, 0, st>>>(queries, n, res, lo, back);
+  return 1;
+}
+int dist_chase_apply(const PeerTable &pt, const u32 *nroots, u32 stride, u32 bound, const u32 *pend_idx, const u32 *pend_key, const u32 *apos,
+                     const u64 *ans, const u32 *n_pend, u32 *gid_l, u32 *next_idx, u32 *next_key, u32 *n_next, cudaStream_t st) {
+  cudaMemsetAsync(n_next, 0, sizeof(u32), st);
+  if (bound == 0) return 0;
+  KScope ks(KID_CHASE_EXITS, st, bound);
+  unsigned grid = blocks_for(bound);
+  const unsigned cap = (unsigned)sm_count() * 8;
+  k_chase_apply<<<grid > cap ? cap : grid, 256, 0, st>>>(pt, nroots, stride, pend_idx, pend_key, apos, ans, n_pend, gid_l, next_idx, next_key,
+                                                         n_next);
+  return 1;
+}
+// a short pending list walks through the peers' memory; then every fragment takes the id of its lroot
+int dist_chase_finish(const PeerTable &pt, const u32 *nroots, u32 stride, u32 m, const u64 *res, const u32 *lroot, const u32 *pend_idx,
+                      const u32 *pend_key, const u32 *n_pend, u32 *gid_l, u32 *gid_rank, cudaStream_t st) {
   if (m == 0) return 0;
   unsigned grid = blocks_for(m);
-  const unsigned cap = (unsigned)sm_count() * 8;  // every walk of a typical exit list is in flight at once
+  const unsigned cap = (unsigned)sm_count() * 8;  // every walk of a typical pending list is in flight at once
   {
     KScope ks(KID_CHASE_EXITS, st, m);
-    k_chase_exits<<<grid > cap ? cap : grid, 256, 0, st>>>(pt, nroots_all, exits, n_exits, gid_l);
+    k_chase_walk<<<grid > cap ? cap : grid, 256, 0, st>>>(pt, nroots, stride, pend_idx, pend_key, n_pend, gid_l);
   }
   KScope ks(KID_CHASE, st, m);
-  k_chase_map<<<blocks_for(m), 256, 0, st>>>(res, lroot, gid_l, nroots_all, pt.me, m, gid_rank);
+  k_chase_map<<<blocks_for(m), 256, 0, st>>>(res, lroot, gid_l, nroots, stride, pt.me, m, gid_rank);
   return 2;
 }
 int dist_or_rows(const u32 *all, u64 row_stride, int nr, u64 words, u32 *out, cudaStream_t st) {

@@ -91,6 +91,7 @@ constexpr int W_CNT_B = 17;      // [nr+1] destination counts of the Y exchange
 constexpr int W_ERR = 40;        // device error word of the rank
 constexpr int W_X0 = 41;         // roots on the rank
 constexpr int W_X1 = 42;         // total groups
+constexpr int W_X2 = 43;         // forest: fragments of the rank whose chain is still waiting for an answer from another rank
 constexpr int W_CUTS = 44;       // [nr+1] the cuts of the exchange (identical on every rank; the host sizes the local sort keys from them)
 
 struct Transport {
@@ -473,7 +474,7 @@ struct Dist {
 
   // carved device pointers
   Counters *cnt = nullptr;
-  u32 *d_small = nullptr, *d_small_all = nullptr, *nroots_all = nullptr, *nroots_all2 = nullptr;
+  u32 *d_small = nullptr, *d_small_all = nullptr, *nroots_mat = nullptr;
   u32 *prehist = nullptr;  // 4 x [4][256]: digit counts of the rank / X / Y / gid sort keys, gathered by their producers
   u32 *hist = nullptr, *hist_all = nullptr, *cuts0 = nullptr, *cuts_y = nullptr, *cuts_x = nullptr, *cuts_g = nullptr;
   uint4 *rec4_loc = nullptr, *send_rows = nullptr, *rec4_arr = nullptr, *recv_rows = nullptr;
@@ -491,7 +492,11 @@ struct Dist {
   u8 *xm_send = nullptr, *xm_a = nullptr;
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr, *worklist = nullptr;
   u32 work_cap = 0;
-  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr, *exits = nullptr;
+  u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr;
+  u32 *pend_idx[2] = {nullptr, nullptr}, *pend_key[2] = {nullptr, nullptr}, *n_pend = nullptr;  // forest: pending lists (double buffered)
+  u32 *apos = nullptr, *roff_dev = nullptr;
+  uint4 *queries = nullptr;  // forest bulk rounds: the ranks other GPUs ask this one about (stored by their push kernels)
+  u64 *answers = nullptr;    // ... and the answers to this rank's questions, in the order it sent them (stored by the owners)
   u64 *res = nullptr;  // per fragment: what a walker from another GPU needs (k_chase_local); the peers read it
   void *scan_work = nullptr;
   u32 *gid_a = nullptr, *sgid = nullptr, *srank_g = nullptr;
@@ -513,8 +518,7 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.cnt = (Counters *)take(sizeof(Counters));
   D.d_small = (u32 *)take(SMALL_WORDS * 4);
   D.d_small_all = (u32 *)take((u64)nr * SMALL_WORDS * 4);
-  D.nroots_all = (u32 *)take(DIST_MAX_RANKS * 4);
-  D.nroots_all2 = (u32 *)take(DIST_MAX_RANKS * 4);
+  D.nroots_mat = (u32 *)take((u64)nr * SMALL_WORDS * 4);
   D.prehist = (u32 *)take(4 * 4 * 256 * 4);
   D.hist = (u32 *)take(DIST_BINS * 4);
   D.hist_all = (u32 *)take((u64)nr * DIST_BINS * 4);
@@ -562,7 +566,12 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.gidscan = (u32 *)take(M * 4);
   D.lroot = (u32 *)take(M * 4);
   D.gid_l = (u32 *)take(M * 4);
-  D.exits = (u32 *)take(M * 4 + 16);
+  for (int b = 0; b < 2; ++b) D.pend_idx[b] = (u32 *)take(M * 4), D.pend_key[b] = (u32 *)take(M * 4);
+  D.n_pend = (u32 *)take(16);
+  D.apos = (u32 *)take(M * 4);
+  D.roff_dev = (u32 *)take((DIST_MAX_RANKS + 1) * 4);
+  D.queries = (uint4 *)take(M * 16);
+  D.answers = (u64 *)take(M * 8);
   D.res = (u64 *)take(M * 8);
   D.flag = (u32 *)take(16);
   D.flag_all = (u32 *)take(DIST_MAX_RANKS * 4);
@@ -693,6 +702,15 @@ static int dist_import(rk_ctx *ctx, const u8 *blobs, size_t stride) {
   if (NcclTransport *nt = dynamic_cast<NcclTransport *>(D.tr)) nt->d_flag = D.flag, nt->d_flag_all = D.flag_all;
   D.pt.nr = D.world, D.pt.me = D.rank;
   D.peers_ready = true;
+  return RK_OK;
+}
+
+// the count exchange with the matrix left on the device as well (d_small_all) and on the host (h_small); synchronises
+static int dist_gather_counts_dev(rk_ctx *ctx) {
+  Dist &D = *ctx->dist;
+  CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+  TR(D.tr->gather_small_begin(D.d_small, D.d_small_all, D.h_small, ctx->stream));
+  TR(D.tr->gather_small_end(D.d_small_all, D.h_small, ctx->stream));
   return RK_OK;
 }
 
@@ -858,6 +876,8 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   }
   m_total = off;
   D.pt.roff[nr] = (u32)m_total;
+  for (int d = nr + 1; d <= DIST_MAX_RANKS; ++d) D.pt.roff[d] = 0xFFFFFFFFu;
+  CK(cudaMemcpyAsync(D.roff_dev, D.pt.roff, (nr + 1) * sizeof(u32), cudaMemcpyHostToDevice, st));  // (pageable source: staged at once)
   D.m_total = m_total, D.n_total_loaded = loaded_total;
   const u32 m = (u32)m_of[me];
   D.m_loc = m;
@@ -996,11 +1016,58 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   TR(D.tr->barrier(st));
   launches += dist_merge_y(D.yo_s, D.perm_y, m, D.parent, st);
   CK(cudaEventRecord(ev[2], st));
-  // forest: roots per rank, then every chain is followed to its root through the peers' parent arrays
+  // forest: roots per rank; local chains; the chains that leave the GPU are resolved in bulk rounds while there are many
+  // of them anywhere, the rest by walking through the peers' memory (k7_dist.cu)
   launches += dist_root_scan(D.parent, m, D.gidscan, D.d_small + W_X0, D.scan_work, st);
-  launches += dist_chase_local(D.parent, D.gidscan, m, D.rank_off, D.lroot, D.res, D.exits + 4, D.exits, st);
-  TR(D.tr->all_gather(D.d_small + W_X0, D.nroots_all, 4, st));   // (also: every rank's res[] is final)
-  launches += dist_chase_peers(D.pt, D.nroots_all, m, D.res, D.lroot, D.exits + 4, D.exits, D.gid_l, D.gid_rank, st);
+  launches += dist_chase_local(D.parent, D.gidscan, m, D.rank_off, D.lroot, D.res, D.pend_idx[0], D.pend_key[0], D.n_pend, st);
+  CK(cudaMemcpyAsync(D.d_small + W_X2, D.n_pend, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  {
+    const int rc = dist_gather_counts_dev(ctx);  // host sync: roots and pending chains of every rank (also: every rank's res[] is final)
+    if (rc) return rc;
+  }
+  // the root counts stay on the device as a column of the gathered matrix, in a copy that later gathers do not overwrite
+  CK(cudaMemcpyAsync(D.nroots_mat, D.d_small_all, (size_t)nr * SMALL_WORDS * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  const u32 *nroots = D.nroots_mat + W_X0;
+  // (RK_DIST_BULK_MIN: tuning and tests — 1 resolves every chain in bulk rounds, a huge value only by walking)
+  const u64 bulk_min = getenv("RK_DIST_BULK_MIN") ? strtoull(getenv("RK_DIST_BULK_MIN"), nullptr, 10) : (1ull << 20);
+  int cur = 0;
+  for (int round = 0; round < nr; ++round) {
+    u64 most = 0;
+    for (int r = 0; r < nr; ++r) most = std::max<u64>(most, D.h_small[(size_t)r * SMALL_WORDS + W_X2]);
+    if (most == 0 || most < bulk_min) break;
+    const u32 bound = (u32)std::min<u64>(D.h_small[(size_t)me * SMALL_WORDS + W_X2], m);  // this rank's pending chains
+    // ask: the ranks in question go to their owners
+    uint4 *qouts[DIST_MAX_RANKS];
+    peer_rows(D, D.queries, qouts);
+    launches += dist_chase_ask_count(D.pend_key[cur], bound, D.n_pend, D.roff_dev, nr, D.tile_cnt, D.d_small + W_CNT_A, st);
+    CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    TR(D.tr->gather_small_begin(D.d_small, D.d_small_all, D.h_small, st));
+    launches += dist_chase_ask_push(D.pend_key[cur], bound, D.n_pend, D.roff_dev, nr, qouts, (u32)D.cap, D.apos, D.tile_cnt, D.d_small_all,
+                                    SMALL_WORDS, me, st);
+    TR(D.tr->barrier(st));
+    TR(D.tr->gather_small_end(D.d_small_all, D.h_small, st));
+    Exchange exq;
+    exq.from_matrix(D.h_small, W_CNT_A, nr, me);
+    for (int d = 0; d < nr; ++d) {
+      u64 in = 0;
+      for (int sr = 0; sr < nr; ++sr) in += D.h_small[(size_t)sr * SMALL_WORDS + W_CNT_A + d];
+      if (in > D.cap) return fail(ctx, RK_ERR_NOMEM, "rank %d is asked about %llu chain ends, capacity is %llu rows per rank", d,
+                                  (unsigned long long)in, (unsigned long long)D.cap);
+    }
+    D.tr->bytes_sent += (exq.n_send - exq.scnt[me]) * 16 + (exq.n_recv - exq.rcnt[me]) * 8;
+    // answer: every owner returns its res[] words, block by block, into the asking ranks' answer buffers
+    launches += dist_chase_answer(D.queries, (u32)exq.n_recv, D.res, D.rank_off, scatter_table(D, exq, true, D.answers), st);
+    TR(D.tr->barrier(st));
+    // apply: roots end a chain, anything else is asked about in the next round
+    launches += dist_chase_apply(D.pt, nroots, SMALL_WORDS, bound, D.pend_idx[cur], D.pend_key[cur], D.apos, D.answers, D.n_pend, D.gid_l,
+                                 D.pend_idx[cur ^ 1], D.pend_key[cur ^ 1], D.n_pend + 1, st);
+    CK(cudaMemcpyAsync(D.n_pend, D.n_pend + 1, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    cur ^= 1;
+    CK(cudaMemcpyAsync(D.d_small + W_X2, D.n_pend, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    const int rc = dist_gather_counts_dev(ctx);  // how many chains are still open, everywhere
+    if (rc) return rc;
+  }
+  launches += dist_chase_finish(D.pt, nroots, SMALL_WORDS, m, D.res, D.lroot, D.pend_idx[cur], D.pend_key[cur], D.n_pend, D.gid_l, D.gid_rank, st);
   // (no second barrier: the count exchange of the output stage below completes on a rank only after every rank has
   // entered it, i.e. finished chasing, and parent[] is not written again before the next rk_dist_group)
   CK(cudaEventRecord(ev[3], st));
@@ -1008,7 +1075,7 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   // number of output LINES (groups founded early are larger: equal numbers of groups would give rank 0 far more lines).
   const int bits_gid = ceil_log2(D.m_total) < 1 ? 1 : ceil_log2(D.m_total);  // group ids are < number of fragments
   const int shift_g = bits_gid > 12 ? bits_gid - 12 : 0;
-  launches += dist_cuts_gid(D.nroots_all, nr, D.cuts_g, D.d_small + W_X1, st);  // (the total; the cuts are replaced below)
+  launches += dist_cuts_gid(nroots, SMALL_WORDS, nr, D.cuts_g, D.d_small + W_X1, st);  // (the total; the cuts are replaced below)
   launches += dist_coarse_hist(D.gid_rank, m, shift_g, 0, 0xFFFFFFFFu, D.hist, st);
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
   launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st);

@@ -56,6 +56,21 @@ def test_ranks_as_threads_match_oracle(world, wl):
         _assert_same(m.group(w.len_ratio, w.pos_ratio), g)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("wl", ["dense", "c2", "c3"])
+def test_forest_bulk_rounds_match_oracle(monkeypatch, world, wl):
+    """RK_DIST_BULK_MIN=1: every chain that leaves its GPU is resolved by the ask/answer rounds (what a dense 1e9-fragment
+    comparison uses) instead of by walking through peer memory; chains over several GPUs need several rounds"""
+    monkeypatch.setenv("RK_DIST_BULK_MIN", "1")
+    w = _workload(wl)
+    rec = gen.generate(w)
+    g = O.group(rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
+    with capi.Multi([0] * world) as m:
+        m.load(rec, w.lx + 1, w.ly + 1)
+        _assert_same(m.group(w.len_ratio, w.pos_ratio), g)
+        _assert_same(m.group(0.5, 0.5), O.group(rec, w.lx + 1, w.ly + 1, 0.5, 0.5))
+
+
 def test_ranks_as_threads_unsorted_members():
     w = _workload("dense")
     rec = gen.generate(w)
