@@ -6,18 +6,21 @@
 // file whose records start out spread over the GPUs in file order.  The kernels and the argument for exactness are in
 // k7_dist.cu; this file owns the buffers, the two transports and the order of the launches:
 //
-//   load   K1 on the local slice -> cuts on xStart/10 (all-gathered coarse histogram) -> records to their owner (all-to-all,
-//          32 B each) -> processing order (K2a) -> link maps OR-ed over the GPUs -> keys (K2) -> h (K5a)
-//          -> X halo rows to the higher GPUs, Y rows to the owners of their Y super-bucket range (all-to-all, 16 B each)
-//          -> X and Y bucket sorts (K2b/c)                                                       [2 host syncs: counts]
-//   group  X pass (K3) -> halo owners home (4 B) -> "matched in X" flags to the Y owners (1 B) -> Y pass (K3) -> Y owners
-//          home (4 B) -> root scan, root counts all-gathered, parent chains followed through peer memory (K4) -> rows to the
-//          owner of their group-id range (16 B) -> K5b/c                                          [1 host sync: counts]
+//   load   K1 on the local slice -> [all-gather: xStart/10 histogram + link maps] -> cuts -> exchange 1: the split kernel
+//          stores every 32-byte record into its owner's arena (peer memory) -> processing order (K2a) -> keys (K2) -> h (K5a)
+//          -> X halo rows to the higher GPUs; Y rows (16 B) to the owners of their Y super-bucket range, by copy engines
+//          beside the X bucket sort -> X and Y bucket sorts (K2b/c)                              [2 host syncs: counts]
+//   group  X pass (K3) -> halo owners stored at their home rank (4 B) -> "matched in X" bytes stored at the Y owners
+//          -> Y pass (K3) -> the Y owners stored at the home ranks -> root scan; local chains; chains that leave the GPU in
+//          bulk ask/answer rounds (many) or by walking the peers' res[] (few) (K4) -> output rows (16 B) stored at the
+//          owner of their group-id range -> K5b/c                                                [2 host syncs: counts]
 //
-// Transports: NCCL (dlopen'ed: the process may already hold torch's libnccl.so.2; grouped ncclSend/ncclRecv with counts
-// the host knows, ncclAllGather for the small tables), or — ranks that are threads of one process, possibly on the same
-// device (tests on a one-GPU box) — plain device copies between host barriers.  Peer memory for the forest: cudaIpc
-// handles between processes, raw pointers (+ cudaDeviceEnablePeerAccess) inside one.
+// Every rank's partition arena is carved identically and mapped into every peer (cudaIpc handles between processes, raw
+// pointers + cudaDeviceEnablePeerAccess inside one), so a local buffer address translates to the same buffer on any rank;
+// kernels store rows straight into it (k7_dist.cu: k_push_rows, scatter_store), copy engines push the Y rows.
+// NCCL (dlopen'ed: the process may already hold torch's libnccl.so.2) carries the small tables (ncclAllGather of counts,
+// histograms, link maps) and is the barrier behind every push.  Ranks that are threads of one process, possibly on the same
+// device (tests on a one-GPU box), exchange the small tables through host memory between host barriers instead.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <unistd.h>
@@ -486,10 +489,10 @@ struct Dist {
   float *identity_r = nullptr;
   uint4 *hfi_r = nullptr;
   uint4 *halo_send = nullptr, *halo_recv = nullptr;
-  u32 *halo_grank = nullptr, *halo_res = nullptr, *away_res = nullptr;
+  u32 *halo_grank = nullptr, *away_res = nullptr;
   u32 *skx = nullptr, *rx = nullptr, *ky_a = nullptr, *grank_a = nullptr, *sky_a = nullptr, *ry_a = nullptr;
-  u32 *parent_x = nullptr, *xm_bits = nullptr, *parent = nullptr, *gidscan = nullptr, *parent_y = nullptr, *yo_a = nullptr, *yo_s = nullptr;
-  u8 *xm_send = nullptr, *xm_a = nullptr;
+  u32 *parent_x = nullptr, *xm_bits = nullptr, *parent = nullptr, *gidscan = nullptr, *parent_y = nullptr, *yo_s = nullptr;
+  u8 *xm_a = nullptr;
   u32 *ent_rank = nullptr, *ent_c = nullptr, *ent_len = nullptr, *worklist = nullptr;
   u32 work_cap = 0;
   u32 *gid_rank = nullptr, *flag = nullptr, *flag_all = nullptr, *lroot = nullptr, *gid_l = nullptr;
@@ -552,7 +555,6 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.halo_send = (uint4 *)take(H * 16);
   D.halo_recv = (uint4 *)take(H * 16);
   D.halo_grank = (u32 *)take(H * 4);
-  D.halo_res = (u32 *)take(H * 4);
   D.away_res = (u32 *)take(H * 4);
   D.skx = (u32 *)take(MC * 4);
   D.rx = (u32 *)take(MC * 4);
@@ -576,9 +578,7 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.flag = (u32 *)take(16);
   D.flag_all = (u32 *)take(DIST_MAX_RANKS * 4);
   D.parent_y = (u32 *)take(M * 4);
-  D.yo_a = (u32 *)take(M * 4);
   D.yo_s = (u32 *)take(M * 4);
-  D.xm_send = take(M);
   D.xm_a = take(M);
   D.ent_rank = (u32 *)take(MC * 4);
   D.ent_c = (u32 *)take(MC * 4);
