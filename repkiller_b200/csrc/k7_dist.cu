@@ -37,8 +37,12 @@ __global__ void __launch_bounds__(256) k_coarse_hist(const u32 *__restrict__ key
 
 // one CTA of 1024 threads: the ranks' histograms (row r at hist_all + r * row_stride words) summed, cuts[r] = first bin boundary (as a key value)
 // at which the cumulative count reaches total*r/nr; cuts[0] = 0, cuts[nr] = 0xFFFFFFFF.  Identical on every rank.
+// gid_total (output exchange only): the bins are blocks of 2^shift group ids and *gid_total is the number of groups; a bin
+// then weighs 3 per line + 8 per line beyond one per group — sort_groups costs per member of a group with several members,
+// and the groups founded early (low ids) are the large ones: with equal LINE counts rank 0 needed 0.63 ms for its range
+// where the last rank needed 0.37 ms (8 GPUs, 10M lines each).
 __global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__ hist_all, u64 row_stride, int nr, int shift,
-                                                         u32 *__restrict__ cuts) {
+                                                         u32 *__restrict__ cuts, const u32 *__restrict__ gid_total) {
   __shared__ unsigned long long s_cum[DIST_BINS + 1];
   __shared__ unsigned long long s_part[1024];
   constexpr int PER = DIST_BINS / 1024;
@@ -47,6 +51,11 @@ __global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__
     const u32 b = threadIdx.x * PER + j;
     unsigned long long c = 0;
     for (int r = 0; r < nr; ++r) c += hist_all[(u64)r * row_stride + b];
+    if (gid_total) {
+      const unsigned long long first = (unsigned long long)b << shift, total_g = *gid_total;
+      const unsigned long long groups = first >= total_g ? 0 : (total_g - first < (1ull << shift) ? total_g - first : (1ull << shift));
+      c = 3 * c + 8 * (c > groups ? c - groups : 0);
+    }
     v[j] = c;
     sum += c;
   }
@@ -401,8 +410,35 @@ __global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ r
   hist_flush(s_h, ho);
 }
 
+// X bucket keys of a rank, made local before the X sort: key2 = 2 * (global super-bucket key) + own bit becomes
+// 2 * (strand * (R + 1) + min(key - first key of the rank's range in that strand, R)) + own bit — log2(4 (R + 1)) bits
+// instead of log2(4 nbx): one radix pass fewer from 4 GPUs on.  Keys past the range (fragments that were sent away as halo:
+// their local result is overwritten anyway) share the one extra slot R.
+struct XRemap {
+  u32 nbx, base[2], range[2], R;
+};
+__device__ __forceinline__ u32 x_local_key(u32 key2, const XRemap &x) {
+  const u32 k = key2 >> 1, s = k >= x.nbx ? 1u : 0u;
+  const u32 loc = k - x.base[s];
+  return 2u * (s * (x.R + 1u) + (loc < x.range[s] ? loc : x.R)) + (key2 & 1u);
+}
+__global__ void __launch_bounds__(256) k_x_remap(u32 *__restrict__ keys2, u32 n, XRemap x, HistOut ho) {
+  __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
+  hist_zero(s_h);
+  __syncthreads();
+  for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
+    const u64 i = base + threadIdx.x;
+    u32 k = 0;
+    if (i < n) keys2[i] = k = x_local_key(keys2[i], x);
+    hist_add(s_h, k, i < n, ho);
+  }
+  __syncthreads();
+  hist_flush(s_h, ho);
+}
+
 // arrival of the rows of one axis pass: keys[j], cl[j], grank[j] of row j
-__global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restrict__ rows, u32 n, u32 key_base, u32 *__restrict__ keys,
+template <bool XLOCAL>
+__global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restrict__ rows, u32 n, u32 key_base, XRemap x, u32 *__restrict__ keys,
                                                           uint2 *__restrict__ cl, u32 *__restrict__ grank, HistOut ho) {
   __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
   hist_zero(s_h);
@@ -412,7 +448,7 @@ __global__ void __launch_bounds__(256) k_unpack_axis_rows(const uint4 *__restric
     u32 k = 0;
     if (j < n) {
       const uint4 r = rows[j];
-      keys[j] = k = r.x - key_base;
+      keys[j] = k = XLOCAL ? x_local_key(r.x, x) : r.x - key_base;
       cl[j] = make_uint2(r.y, r.z);
       grank[j] = r.w;
     }
@@ -679,8 +715,8 @@ int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_
   k_coarse_hist<<<b > cap ? cap : b, 256, 0, st>>>(keys, n, shift, pre_shift, drop_key, hist);
   return 1;
 }
-int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st) {
-  k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, row_stride, nr, shift, cuts);
+int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st, const u32 *gid_total) {
+  k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, row_stride, nr, shift, cuts, gid_total);
   return 1;
 }
 int dist_cuts_gid(const u32 *nroots, u32 stride, int nr, u32 *cuts, u32 *total, cudaStream_t st) {
@@ -773,7 +809,28 @@ int dist_key0_of_rec(const uint4 *rec, u32 n, u32 key_base, u32 *key0, HistOut h
 int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 key_base, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
   KScope ks(KID_DIST_ROWS, st, n);
-  k_unpack_axis_rows<<<hist_grid(n), 256, 0, st>>>(rows, n, key_base, keys, cl, grank, ho);
+  k_unpack_axis_rows<false><<<hist_grid(n), 256, 0, st>>>(rows, n, key_base, XRemap{}, keys, cl, grank, ho);
+  return 1;
+}
+// the X side: the rank's own keys in place, the arrived halo rows while they are unpacked
+static XRemap make_xremap(u32 nbx, const u32 *base, const u32 *range) {
+  XRemap x{};
+  x.nbx = nbx;
+  x.base[0] = base[0], x.base[1] = base[1], x.range[0] = range[0], x.range[1] = range[1];
+  x.R = range[0] > range[1] ? range[0] : range[1];
+  return x;
+}
+int dist_x_local_keys(u32 *keys2, u32 n, u32 nbx, const u32 *base, const u32 *range, HistOut ho, cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_x_remap<<<hist_grid(n), 256, 0, st>>>(keys2, n, make_xremap(nbx, base, range), ho);
+  return 1;
+}
+int dist_unpack_halo_rows(const uint4 *rows, u32 n, u32 nbx, const u32 *base, const u32 *range, u32 *keys, uint2 *cl, u32 *grank, HistOut ho,
+                          cudaStream_t st) {
+  if (n == 0) return 0;
+  KScope ks(KID_DIST_ROWS, st, n);
+  k_unpack_axis_rows<true><<<hist_grid(n), 256, 0, st>>>(rows, n, 0, make_xremap(nbx, base, range), keys, cl, grank, ho);
   return 1;
 }
 int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho, cudaStream_t st) {

@@ -88,13 +88,14 @@ static NcclApi &nccl_api() {
 // ---------------------------------------------------------------------------------------------------------------------
 // transports
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SMALL_WORDS = 64;  // per-rank row of the count exchanges
+constexpr int SMALL_WORDS = 96;  // per-rank row of the count exchanges
 constexpr int W_CNT_A = 0;       // [nr+1] destination counts (exchange 1 / X halo / output exchange)
 constexpr int W_CNT_B = 17;      // [nr+1] destination counts of the Y exchange
 constexpr int W_ERR = 40;        // device error word of the rank
 constexpr int W_X0 = 41;         // roots on the rank
 constexpr int W_X1 = 42;         // total groups
 constexpr int W_X2 = 43;         // forest: fragments of the rank whose chain is still waiting for an answer from another rank
+constexpr int W_CUTSX = 64;      // [2][nr] the first X super-bucket key every rank owns, per strand class
 constexpr int W_CUTS = 44;       // [nr+1] the cuts of the exchange (identical on every rank; the host sizes the local sort keys from them)
 
 struct Transport {
@@ -894,7 +895,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
                                 m ? D.prehist : nullptr);
   CK(cudaEventRecord(ev[3], st));
   launches += launch_keys(D.aidx_r, m, g, D.rec4_arr, linkx, linky, D.xl, D.yl_r, D.ys_r, D.kx2, D.ky, D.identity_r, st,
-                          hist_of(1, D.bits_x + 1), HistOut{nullptr, 0, 0}, D.gfidx_r, 1u);
+                          HistOut{nullptr, 0, 0}, HistOut{nullptr, 0, 0}, D.gfidx_r, 1u);
   launches += launch_hkey(D.k0_r, D.ys_r, m, nullptr, st, D.gfidx_r, D.identity_r, D.hfi_r);
   CK(cudaEventRecord(ev[4], st));
   // X halo: fragments whose X super-bucket belongs to a higher rank
@@ -908,6 +909,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_y, D.cuts_y, st);
   launches += dist_split_axis(D.ky, D.yl_r, m, D.cuts_y, nr, D.rank_off, D.send_rows, D.perm_y, D.tile_cnt, D.d_small + W_CNT_B, st);
   CK(cudaMemcpyAsync(D.d_small + W_CUTS, D.cuts_y, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(D.d_small + W_CUTSX, D.cuts_x, 2 * nr * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   {
     const int rc = dist_gather_counts(ctx);  // host sync 2
     if (rc) return rc;
@@ -939,9 +941,20 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   TR(D.tr->all_to_all(D.halo_send, D.exh.soff, D.exh.scnt, D.halo_recv, D.exh.roff, D.exh.rcnt, D.exh.poff, 16, st));
   // the Y rows travel (copy engines, NVLink) while this GPU unpacks its halo and sorts its X buckets
   TR(D.tr->a2a_begin(D.send_rows, D.exy.soff, D.exy.scnt, D.recv_rows, D.exy.roff, D.exy.rcnt, D.exy.poff, 16, st, D.side));
-  launches += dist_unpack_axis_rows(D.halo_recv, D.n_halo, 0, D.kx2 + m, D.xl + m, D.halo_grank, hist_of(1, D.bits_x + 1), st);
+  // X sort keys relative to the first super-bucket of the rank's range (per strand class)
+  const u32 *cutsx_h = D.h_small + (size_t)me * SMALL_WORDS + W_CUTSX;
+  u32 x_base[2], x_range[2];
+  for (int sc = 0; sc < 2; ++sc) {
+    x_base[sc] = cutsx_h[sc * nr + me];
+    const u32 end = me + 1 < nr ? cutsx_h[sc * nr + me + 1] : (u32)(sc + 1) * g.nbx;
+    x_range[sc] = end > x_base[sc] ? end - x_base[sc] : 1u;
+  }
+  const u32 x_R = std::max(x_range[0], x_range[1]);
+  const int bits_x_l = ceil_log2(4ull * ((u64)x_R + 1));
+  launches += dist_x_local_keys(D.kx2, m, g.nbx, x_base, x_range, hist_of(1, bits_x_l), st);
+  launches += dist_unpack_halo_rows(D.halo_recv, D.n_halo, g.nbx, x_base, x_range, D.kx2 + m, D.xl + m, D.halo_grank, hist_of(1, bits_x_l), st);
   CK(cudaEventRecord(ev[5], st));
-  launches += launch_sort_pairs(D.kx2, nullptr, D.skx, D.rx, D.tmp_k, D.tmp_v, (u64)m + D.n_halo, D.bits_x + 1, D.sort_work, st, &D.cnt->err,
+  launches += launch_sort_pairs(D.kx2, nullptr, D.skx, D.rx, D.tmp_k, D.tmp_v, (u64)m + D.n_halo, bits_x_l, D.sort_work, st, &D.cnt->err,
                                 (m + D.n_halo) ? D.prehist + 1024 : nullptr);
   CK(cudaEventRecord(ev[6], st));
   TR(D.tr->a2a_end(st));
@@ -1071,14 +1084,15 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   // (no second barrier: the count exchange of the output stage below completes on a rank only after every rank has
   // entered it, i.e. finished chasing, and parent[] is not written again before the next rk_dist_group)
   CK(cudaEventRecord(ev[3], st));
-  // output exchange: to the owner of the group-id range.  The ranges are cut so that every rank gets about the same
-  // number of output LINES (groups founded early are larger: equal numbers of groups would give rank 0 far more lines).
+  // output exchange: to the owner of the group-id range.  The ranges are cut for about equal sort_groups WORK: lines, with
+  // the lines of groups with several members weighted up (groups founded early are the large ones: equal numbers of
+  // groups gave rank 0 far more lines, equal numbers of lines still far more work — see k_cuts_from_hist).
   const int bits_gid = ceil_log2(D.m_total) < 1 ? 1 : ceil_log2(D.m_total);  // group ids are < number of fragments
   const int shift_g = bits_gid > 12 ? bits_gid - 12 : 0;
   launches += dist_cuts_gid(nroots, SMALL_WORDS, nr, D.cuts_g, D.d_small + W_X1, st);  // (the total; the cuts are replaced below)
   launches += dist_coarse_hist(D.gid_rank, m, shift_g, 0, 0xFFFFFFFFu, D.hist, st);
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
-  launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st);
+  launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st, D.d_small + W_X1);
   CK(cudaMemcpyAsync(D.d_small + W_CNT_B, D.cuts_g, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   uint4 *outs[DIST_MAX_RANKS];
   peer_rows(D, D.recv_rows, outs);
@@ -1403,7 +1417,7 @@ int rk_multi_load_aos(rk_multi *mg, const void *frags, uint64_t n, uint64_t seqx
   }
   u64 biggest = 0;
   for (int r = 0; r < mg->n; ++r) biggest = std::max(biggest, lo[r + 1] - lo[r]);
-  const u64 want = biggest + biggest / 3 + (1u << 16);
+  const u64 want = biggest + biggest / 2 + (1u << 16);
   if (want > mg->cap) {
     const int rc = multi_set_capacity(mg, want);
     if (rc) return rc;

@@ -277,7 +277,8 @@ struct ScatterTable {                 // positions 0..n of a kernel's output in 
   int nr;
 };
 int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_key, u32 *hist, cudaStream_t st);
-int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st);
+int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st,
+                        const u32 *gid_total = nullptr);
 int dist_cuts_gid(const u32 *nroots, u32 stride, int nr, u32 *cuts, u32 *total, cudaStream_t st);
 int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st);
 u64 dist_split_work_bytes(u64 n);
@@ -293,6 +294,9 @@ int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, in
                     u32 *tile_cnt, u32 *counts, cudaStream_t st);
 int dist_key0_of_rec(const uint4 *rec, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st);
 int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 key_base, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st);
+int dist_x_local_keys(u32 *keys2, u32 n, u32 nbx, const u32 *base, const u32 *range, HistOut ho, cudaStream_t st);
+int dist_unpack_halo_rows(const uint4 *rows, u32 n, u32 nbx, const u32 *base, const u32 *range, u32 *keys, uint2 *cl, u32 *grank, HistOut ho,
+                          cudaStream_t st);
 int dist_gid_keys(const uint4 *rows, u32 n, u32 gid_base, u32 *keys, HistOut ho, cudaStream_t st);
 int dist_x_owners(const u32 *parent_x, u32 m, u32 nh, u32 rank_off, const u32 *halo_grank, u32 *parent, const ScatterTable &home,
                   cudaStream_t st);

@@ -23,8 +23,9 @@ def slice_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def default_capacity(n_per_rank: int) -> int:
-    """workspace rows per rank: room for an uneven partition (the cuts balance fragments to within a histogram bin)"""
-    return int(n_per_rank * 1.3) + (1 << 16)
+    """workspace rows per rank: room for an uneven partition (the cuts of the output exchange balance sort_groups work, not
+    lines: a rank whose groups are small gets more lines)"""
+    return int(n_per_rank * 1.5) + (1 << 16)
 
 
 def bootstrap(ctx: capi.Context, cap_per_rank: int, group=None) -> None:
