@@ -475,7 +475,7 @@ def ours(args):
             "checksum_match": (checksum == checksum_1gpu) if checksum_1gpu is not None else None,
             "e2e": {"value": e2e_value if do_e2e else None, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * 109) if partitioned else int(n * 33), "d2h_bytes_per_step": int(lines * 13 + 40),
-                    "ms_per_step": ms_e2e / args.steps,
+                    "ms_per_step": ms_e2e / args.steps if do_e2e else None,
                     "ingest": "rk_dist_load_aos: 109-byte records" if partitioned else
                               "rk_load_packed: 33 B per fragment (what the drop-in CLI's parser hands over)",
                     "record_ingest": None if ms_e2e_aos is None else {

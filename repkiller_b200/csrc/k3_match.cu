@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256)
     k_keys(const u32 *__restrict__ fidx_r, u32 m, Geometry g, const uint4 *__restrict__ rec4, const u32 *__restrict__ link_x,
            const u32 *__restrict__ link_y, uint2 *__restrict__ xl_r, uint2 *__restrict__ yl_r, u32 *__restrict__ ys_r,
            u32 *__restrict__ kx, u32 *__restrict__ ky, float *__restrict__ identity_r, HistOut hx, HistOut hy,
-           u32 *__restrict__ gfidx_r, u32 own_bit) {
+           u32 *__restrict__ gfidx_r, u32 own_bit, const uint2 *__restrict__ rec6) {
   // the digit counts of the two sort keys are gathered here (the keys would otherwise be read again by each sort)
   __shared__ u32 s_hx[HIST_PASSES][HIST_RADIX], s_hy[HIST_PASSES][HIST_RADIX];
   const bool do_hist = hx.ghist != nullptr;
@@ -47,9 +47,18 @@ __global__ void __launch_bounds__(256)
     const bool valid = i < m;
     u32 kxv = 0, kyv = 0;
     if (valid) {
-      // one 32-byte gather (one sector): {xStart, yStart, length, flags} {identity bits, 0, 0, 0}
-      const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
-      const uint4 rec = ldg_gather_u4(src), rec1 = ldg_gather_u4(src + 1);
+      // one 32-byte gather (one sector): {xStart, yStart, length, flags} {identity bits, file index, 0, 0} — or, multi-GPU,
+      // the 24-byte row that arrived in exchange 1 (three 8-byte words, one or two sectors)
+      uint4 rec, rec1;
+      if (rec6) {
+        const uint2 *src = rec6 + 3 * (u64)fidx_r[i];
+        const uint2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        rec = make_uint4(a.x, a.y, b.x, b.y);
+        rec1 = make_uint4(c.x, c.y, 0u, 0u);
+      } else {
+        const uint4 *src = rec4 + 2 * (u64)fidx_r[i];
+        rec = ldg_gather_u4(src), rec1 = ldg_gather_u4(src + 1);
+      }
       identity_r[i] = __uint_as_float(rec1.x);
       if (gfidx_r) gfidx_r[i] = rec1.y;
       const u32 x = rec.x, y = rec.y, l = rec.z;
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(256)
 
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
                 uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x, HistOut hist_y,
-                u32 *gfidx_r, u32 own_bit) {
+                u32 *gfidx_r, u32 own_bit, const uint2 *rec6) {
   if (m == 0) return 0;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -86,7 +95,7 @@ int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u
   u32 blocks = (m + 255) / 256;
   if (hist_x.ghist && blocks > (u32)sms * 8) blocks = (u32)sms * 8;  // few CTAs: few histogram flushes
   KScope ks(KID_KEYS, st, m);
-  k_keys<<<blocks, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r, hist_x, hist_y, gfidx_r, own_bit);
+  k_keys<<<blocks, 256, 0, st>>>(fidx_r, m, g, rec4, link_x, link_y, xl_r, yl_r, ys_r, kx, ky, identity_r, hist_x, hist_y, gfidx_r, own_bit, rec6);
   return 1;
 }
 

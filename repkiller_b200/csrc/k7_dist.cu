@@ -41,16 +41,40 @@ __global__ void __launch_bounds__(256) k_coarse_hist(const u32 *__restrict__ key
 // then weighs 3 per line + 8 per line beyond one per group — sort_groups costs per member of a group with several members,
 // and the groups founded early (low ids) are the large ones: with equal LINE counts rank 0 needed 0.63 ms for its range
 // where the last rank needed 0.37 ms (8 GPUs, 10M lines each).
+struct CutsSmem {
+  unsigned long long cum[DIST_BINS + 1];  // exclusive prefix of the (weighted) bin counts
+  u32 lin[DIST_BINS + 1];                 // exclusive prefix of the plain bin counts (lines)
+  unsigned long long wtot[32];
+  u32 ltot[32], lmax[32];
+};
+// first c in [0, n] with a[c] >= x (a ascending; n + 1 entries)
+template <class T>
+__device__ __forceinline__ u32 first_ge(const T *a, u32 n, T x) {
+  u32 lo = 0, hi = n;
+  while (lo < hi) {
+    const u32 mid = (lo + hi) >> 1;
+    if (a[mid] >= x) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+// line_cap (weighted cuts only): no rank's range may hold more than line_cap lines — the weighted cut is moved to the nearest
+// bin boundary that leaves every rank, this one and the ones after it, within its rows (possible whenever the lines fit at all)
 __global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__ hist_all, u64 row_stride, int nr, int shift,
-                                                         u32 *__restrict__ cuts, const u32 *__restrict__ gid_total) {
-  __shared__ unsigned long long s_cum[DIST_BINS + 1];
-  __shared__ unsigned long long s_part[1024];
+                                                         u32 *__restrict__ cuts, const u32 *__restrict__ gid_total, u64 line_cap) {
+  extern __shared__ __align__(16) unsigned char cuts_smem_raw[];
+  CutsSmem &sm = *reinterpret_cast<CutsSmem *>(cuts_smem_raw);
   constexpr int PER = DIST_BINS / 1024;
+  const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned long long v[PER], sum = 0;
+  u32 l[PER], lsum = 0, lbig = 0;
   for (int j = 0; j < PER; ++j) {
     const u32 b = threadIdx.x * PER + j;
     unsigned long long c = 0;
     for (int r = 0; r < nr; ++r) c += hist_all[(u64)r * row_stride + b];
+    l[j] = (u32)c;
+    lsum += (u32)c;
+    lbig = max(lbig, (u32)c);
     if (gid_total) {
       const unsigned long long first = (unsigned long long)b << shift, total_g = *gid_total;
       const unsigned long long groups = first >= total_g ? 0 : (total_g - first < (1ull << shift) ? total_g - first : (1ull << shift));
@@ -59,36 +83,67 @@ __global__ void __launch_bounds__(1024) k_cuts_from_hist(const u32 *__restrict__
     v[j] = c;
     sum += c;
   }
-  s_part[threadIdx.x] = sum;
+  // block-wide exclusive scan of (sum, lsum): warp scan, then the 32 warp totals by warp 0
+  unsigned long long inc = sum;
+  u32 linc = lsum;
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    const u32 lt = __shfl_up_sync(0xFFFFFFFFu, linc, d);
+    if (lane >= (u32)d) inc += t, linc += lt;
+  }
+  lbig = __reduce_max_sync(0xFFFFFFFFu, lbig);
+  if (lane == 31) sm.wtot[w] = inc, sm.ltot[w] = linc, sm.lmax[w] = lbig;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long t = sm.wtot[lane];
+    u32 lt = sm.ltot[lane];
+    const unsigned long long own = t;
+    const u32 lown = lt;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, t, d);
+      const u32 lu = __shfl_up_sync(0xFFFFFFFFu, lt, d);
+      if (lane >= (u32)d) t += u, lt += lu;
+    }
+    const u32 big = __reduce_max_sync(0xFFFFFFFFu, sm.lmax[lane]);
+    sm.wtot[lane] = t - own, sm.ltot[lane] = lt - lown;
+    if (lane == 31) sm.cum[DIST_BINS] = t, sm.lin[DIST_BINS] = lt, sm.lmax[0] = big;
+  }
+  __syncthreads();
+  unsigned long long run = sm.wtot[w] + inc - sum;
+  u32 lrun = sm.ltot[w] + linc - lsum;
+  for (int j = 0; j < PER; ++j) {
+    sm.cum[threadIdx.x * PER + j] = run, sm.lin[threadIdx.x * PER + j] = lrun;  // exclusive
+    run += v[j], lrun += l[j];
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int t = 0; t < 1024; ++t) {
-      const unsigned long long c = s_part[t];
-      s_part[t] = run;
-      run += c;
-    }
-    s_cum[DIST_BINS] = run;
-  }
-  __syncthreads();
-  unsigned long long run = s_part[threadIdx.x];
-  for (int j = 0; j < PER; ++j) {
-    s_cum[threadIdx.x * PER + j] = run;  // exclusive
-    run += v[j];
-  }
-  if (threadIdx.x <= (u32)nr) cuts[threadIdx.x] = threadIdx.x == (u32)nr ? 0xFFFFFFFFu : 0u;
-  __syncthreads();
-  const unsigned long long total = s_cum[DIST_BINS];
-  for (int j = 0; j < PER; ++j) {
-    const u32 b = threadIdx.x * PER + j;
-    const unsigned long long lo = s_cum[b], hi = s_cum[b + 1];
+    const unsigned long long total = sm.cum[DIST_BINS];
+    const unsigned long long lines = sm.lin[DIST_BINS];
+    u32 prev = 0;
+    cuts[0] = 0;
     for (int r = 1; r < nr; ++r) {
-      const unsigned long long target = total * (unsigned long long)r / (unsigned long long)nr;
-      if (lo < target && target <= hi) {
-        const unsigned long long key = ((unsigned long long)b + 1) << shift;
-        cuts[r] = key > 0xFFFFFFFEull ? 0xFFFFFFFEu : (u32)key;
+      u32 c = first_ge(sm.cum, (u32)DIST_BINS, total * (unsigned long long)r / (unsigned long long)nr);
+      if (line_cap) {
+        // what the ranks r.. can hold — each counted one bin short, so that a boundary between this bound and the bound of
+        // rank r-1's own rows below always exists (cuts fall on bin boundaries)
+        const unsigned long long big = sm.lmax[0];
+        const unsigned long long rest = (unsigned long long)(nr - r) * (line_cap > big ? line_cap - big : 0);
+        if (lines > rest) {
+          const u32 lo = first_ge(sm.lin, (u32)DIST_BINS, (u32)(lines - rest));
+          c = c < lo ? lo : c;
+        }
+        const unsigned long long room = (unsigned long long)sm.lin[prev] + line_cap;  // what rank r-1 can hold
+        if (room < lines) {
+          const u32 over = first_ge(sm.lin, (u32)DIST_BINS, (u32)(room + 1));  // first boundary that is too far
+          c = c >= over ? (over > 0 ? over - 1 : 0) : c;
+        }
       }
+      c = c < prev ? prev : c;
+      prev = c;
+      const unsigned long long key = (unsigned long long)c << shift;
+      cuts[r] = key > 0xFFFFFFFEull ? 0xFFFFFFFEu : (u32)key;
     }
+    cuts[nr] = 0xFFFFFFFFu;
   }
 }
 
@@ -216,13 +271,22 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(u32 *__restrict__ tile_cn
 
 // `out` of a payload: one pointer per destination — the local send buffer for all of them, or every rank's receive buffer
 // (mapped peer memory: the rows then cross NVLink as the stores of this kernel, no send buffer and no copy in between)
-struct RowOuts {
-  uint4 *p[DIST_MAX_RANKS];
+template <class W>
+struct RowOutsT {
+  W *p[DIST_MAX_RANKS];
 };
-struct PayRec32 {  // exchange 1: the whole 32-byte record
+typedef RowOutsT<uint4> RowOuts;
+// exchange 1: the six words of a record that the owner needs — {xStart, yStart} {length, flags} {identity, file index} —
+// 24 bytes on the wire instead of the 32-byte rec4 form K1 writes (25 % of the largest exchange)
+struct PayRec24 {
+  typedef uint2 Word;
+  static constexpr int WPR = 3;
   const uint4 *rec;
-  RowOuts out;
-  __device__ __forceinline__ void load(u32 i, uint4 *v) const { v[0] = rec[2 * (u64)i], v[1] = rec[2 * (u64)i + 1]; }
+  RowOutsT<uint2> out;
+  __device__ __forceinline__ void load(u32 i, uint2 *v) const {
+    const uint4 a = rec[2 * (u64)i], b = rec[2 * (u64)i + 1];
+    v[0] = make_uint2(a.x, a.y), v[1] = make_uint2(a.z, a.w), v[2] = make_uint2(b.x, b.y);
+  }
 };
 struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
   const u32 *keys;
@@ -235,6 +299,8 @@ struct PayAxisRow {  // one axis pass: {key, center, length, global rank}
   }
 };
 struct PayGidRow {  // output exchange: {h, file index, identity bits, gid}
+  typedef uint4 Word;
+  static constexpr int WPR = 1;
   const uint4 *hfi_r;
   const u32 *gid_rank;
   RowOuts out;
@@ -245,6 +311,8 @@ struct PayGidRow {  // output exchange: {h, file index, identity bits, gid}
 };
 
 struct PayQuery {  // forest: "what is behind global rank keys[i]?" asked of the rank that owns it
+  typedef uint4 Word;
+  static constexpr int WPR = 1;
   const u32 *keys;
   RowOuts out;
   __device__ __forceinline__ void load(u32 i, uint4 *v) const { v[0] = make_uint4(keys[i], 0u, 0u, 0u); }
@@ -295,18 +363,20 @@ __global__ void __launch_bounds__(256) k_split_pack(RouteArgs a, const u32 *__re
 // stored to the destination ranks' receive buffers as contiguous runs (consecutive threads -> consecutive 16-byte words).
 // Row-by-row stores from the routing loop reach a peer as scattered 32-byte writes, which NVLink moves at a fraction of
 // its rate (measured at 8 GPUs: 1.7 ms per step in these kernels against 1.05 ms for the same rows through the copy engines).
-template <int WPR>
+template <class W, int WPR>
 struct PushSmem {
-  uint4 rows[SPLIT_TILE * WPR];
+  W rows[SPLIT_TILE * WPR];
   unsigned char dest[SPLIT_TILE];
 };
 // apos (optional): for every element, the position of its row in this rank's SEND order (blocks by destination) — where
 // a value that the destination returns block by block will land; needs the count matrix to undo the receiver offsets.
-template <int WPR, class Pay>
+template <class Pay>
 __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__restrict__ tile_off, Pay pay, u32 *__restrict__ apos,
                                                    const u32 *__restrict__ counts_all, u32 row_stride) {
+  typedef typename Pay::Word W;
+  constexpr int WPR = Pay::WPR;
   extern __shared__ __align__(16) unsigned char push_smem_raw[];
-  PushSmem<WPR> &sm = *reinterpret_cast<PushSmem<WPR> *>(push_smem_raw);
+  PushSmem<W, WPR> &sm = *reinterpret_cast<PushSmem<W, WPR> *>(push_smem_raw);
   __shared__ u32 s_cuts[DIST_MAX_RANKS + 2];
   __shared__ u32 s_run[NRP], s_start[NRP], s_goff[NRP];
   __shared__ u32 s_w[8][NRP];
@@ -371,7 +441,7 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
     const int d = dsts[j];
     if (d >= 0 && d < a.nr) {
       const u32 slot = s_start[d] + ranks[j];
-      uint4 v[WPR];
+      W v[WPR];
       pay.load((u32)(base + (u64)j * 256 + tid), v);
       if (apos) apos[base + (u64)j * 256 + tid] = s_goff[d] + ranks[j] + s_back[d];
 #pragma unroll
@@ -380,7 +450,7 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
     }
   }
   __syncthreads();
-  // copy-out: consecutive threads store consecutive 16-byte words of a destination's run
+  // copy-out: consecutive threads store consecutive words of a destination's run
   const u32 total = s_start[a.nr];
   for (u32 x = tid; x < total * WPR; x += 256) {
     const u32 slot = x / WPR, q = x % WPR;
@@ -395,15 +465,15 @@ __global__ void __launch_bounds__(256) k_push_rows(RouteArgs a, const u32 *__res
 // The three kernels below produce the keys of a sort; like K1/K2 on one GPU they count the digits of those keys on the way
 // (HistOut), so that the sort needs no histogram pass of its own.  Warp-uniform loops: every lane votes in hist_add.
 
-// key0 = xStart / 10 of the arrived records (the sort key of the processing order)
-__global__ void __launch_bounds__(256) k_key0_of_rec(const uint4 *__restrict__ rec, u32 n, u32 key_base, u32 *__restrict__ key0, HistOut ho) {
+// key0 = xStart / 10 of the arrived records (24-byte rows; the sort key of the processing order)
+__global__ void __launch_bounds__(256) k_key0_of_rec(const uint2 *__restrict__ rec6, u32 n, u32 key_base, u32 *__restrict__ key0, HistOut ho) {
   __shared__ u32 s_h[HIST_PASSES][HIST_RADIX];
   hist_zero(s_h);
   __syncthreads();
   for (u64 base = (u64)blockIdx.x * blockDim.x; base < n; base += (u64)gridDim.x * blockDim.x) {
     const u64 i = base + threadIdx.x;
     u32 k = 0;
-    if (i < n) key0[i] = k = rec[2 * i].x / XBUCKET - key_base;  // relative to the rank's first key: fewer sort passes
+    if (i < n) key0[i] = k = rec6[3 * i].x / XBUCKET - key_base;  // relative to the rank's first key: fewer sort passes
     hist_add(s_h, k, i < n, ho);
   }
   __syncthreads();
@@ -715,8 +785,9 @@ int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_
   k_coarse_hist<<<b > cap ? cap : b, 256, 0, st>>>(keys, n, shift, pre_shift, drop_key, hist);
   return 1;
 }
-int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st, const u32 *gid_total) {
-  k_cuts_from_hist<<<1, 1024, 0, st>>>(hist_all, row_stride, nr, shift, cuts, gid_total);
+int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st, const u32 *gid_total,
+                        u64 line_cap) {
+  k_cuts_from_hist<<<1, 1024, sizeof(CutsSmem), st>>>(hist_all, row_stride, nr, shift, cuts, gid_total, gid_total ? line_cap : 0);
   return 1;
 }
 int dist_cuts_gid(const u32 *nroots, u32 stride, int nr, u32 *cuts, u32 *total, cudaStream_t st) {
@@ -753,37 +824,40 @@ int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_k
   k_route_count<0><<<tiles, 256, 0, st>>>(RouteArgs{keys, n, cuts, nr, 0, drop_key, 0, 0xFFFFFFFFu, n_ptr}, tile_cnt, counts);
   return 1;
 }
-template <int WPR, class Pay>
+template <class Pay>
 static int push_rows(const RouteArgs &a, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, const Pay &pay, cudaStream_t st,
                      u32 *apos = nullptr) {
   if (a.n == 0) return 0;
   const u32 tiles = (a.n + SPLIT_TILE - 1) / SPLIT_TILE;
   KScope ks(KID_DIST_ROWS, st, a.n);
   k_tile_offsets<<<a.nr, 1024, 0, st>>>(tile_cnt, tiles, nullptr, counts_all, row_stride, me);
-  k_push_rows<WPR, Pay><<<tiles, 256, sizeof(PushSmem<WPR>), st>>>(a, tile_cnt, pay, apos, counts_all, row_stride);
+  k_push_rows<Pay><<<tiles, 256, sizeof(PushSmem<typename Pay::Word, Pay::WPR>), st>>>(a, tile_cnt, pay, apos, counts_all, row_stride);
   return 2;
 }
 cudaError_t dist_init_device() {  // dynamic shared memory opt-in of the push kernels (per device)
-  cudaError_t e = cudaFuncSetAttribute(k_push_rows<2, PayRec32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<2>));
+  cudaError_t e = cudaFuncSetAttribute(k_cuts_from_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CutsSmem));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_push_rows<1, PayQuery>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<1>));
+  e = cudaFuncSetAttribute(k_push_rows<PayRec24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<uint2, 3>));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_push_rows<1, PayGidRow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<1>));
+  e = cudaFuncSetAttribute(k_push_rows<PayQuery>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<uint4, 1>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_push_rows<PayGidRow>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<uint4, 1>));
 }
-static RowOuts row_outs(uint4 *const *outs, int nr) {
-  RowOuts o{};
+template <class W>
+static RowOutsT<W> row_outs(W *const *outs, int nr) {
+  RowOutsT<W> o{};
   for (int d = 0; d < nr; ++d) o.p[d] = outs[d];
   return o;
 }
-int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *const *outs, u32 out_cap,
+int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint2 *const *outs, u32 out_cap,
                       u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows<2>(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap, nullptr}, tile_cnt, counts_all, row_stride, me,
-                      PayRec32{rec, row_outs(outs, nr)}, st);
+  return push_rows(RouteArgs{key0, n, cuts, nr, 0, drop_key, 0, out_cap, nullptr}, tile_cnt, counts_all, row_stride, me,
+                   PayRec24{rec, row_outs<uint2>(outs, nr)}, st);
 }
 int dist_push_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *const *outs, u32 out_cap, u32 *tile_cnt,
                   const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows<1>(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap, nullptr}, tile_cnt, counts_all, row_stride, me,
-                      PayGidRow{hfi_r, gid_rank, row_outs(outs, nr)}, st);
+  return push_rows(RouteArgs{gid_rank, n, cuts, nr, 0, 0xFFFFFFFFu, 0, out_cap, nullptr}, tile_cnt, counts_all, row_stride, me,
+                   PayGidRow{hfi_r, gid_rank, row_outs<uint4>(outs, nr)}, st);
 }
 // X halo: the fragments whose X super-bucket belongs to another rank; perm[t] = local rank of the t-th row sent
 int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x, int nr, u32 nbx, int me, u32 rank_off, uint4 *out,
@@ -801,9 +875,9 @@ static unsigned hist_grid(u64 n) {  // few CTAs: few histogram flushes
   const unsigned b = blocks_for(n), cap = (unsigned)sm_count() * 8;
   return b > cap ? cap : b;
 }
-int dist_key0_of_rec(const uint4 *rec, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st) {
+int dist_key0_of_rec(const uint2 *rec6, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st) {
   if (n == 0) return 0;
-  k_key0_of_rec<<<hist_grid(n), 256, 0, st>>>(rec, n, key_base, key0, ho);
+  k_key0_of_rec<<<hist_grid(n), 256, 0, st>>>(rec6, n, key_base, key0, ho);
   return 1;
 }
 int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 key_base, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st) {
@@ -894,8 +968,8 @@ int dist_chase_ask_count(const u32 *pend_key, u32 bound, const u32 *n_pend, cons
 }
 int dist_chase_ask_push(const u32 *pend_key, u32 bound, const u32 *n_pend, const u32 *roff_dev, int nr, uint4 *const *outs, u32 out_cap,
                         u32 *apos, u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st) {
-  return push_rows<1>(RouteArgs{pend_key, bound, roff_dev, nr, me, 0xFFFFFFFFu, 0, out_cap, n_pend}, tile_cnt, counts_all, row_stride, me,
-                      PayQuery{pend_key, row_outs(outs, nr)}, st, apos);
+  return push_rows(RouteArgs{pend_key, bound, roff_dev, nr, me, 0xFFFFFFFFu, 0, out_cap, n_pend}, tile_cnt, counts_all, row_stride, me,
+                   PayQuery{pend_key, row_outs<uint4>(outs, nr)}, st, apos);
 }
 int dist_chase_answer(const uint4 *queries, u32 n, const u64 *res, u32 lo, const ScatterTable &back, cudaStream_t st) {
   if (n == 0) return 0;

@@ -481,7 +481,8 @@ struct Dist {
   u32 *d_small = nullptr, *d_small_all = nullptr, *nroots_mat = nullptr;
   u32 *prehist = nullptr;  // 4 x [4][256]: digit counts of the rank / X / Y / gid sort keys, gathered by their producers
   u32 *hist = nullptr, *hist_all = nullptr, *cuts0 = nullptr, *cuts_y = nullptr, *cuts_x = nullptr, *cuts_g = nullptr;
-  uint4 *rec4_loc = nullptr, *send_rows = nullptr, *rec4_arr = nullptr, *recv_rows = nullptr;
+  uint4 *rec4_loc = nullptr, *send_rows = nullptr, *recv_rows = nullptr;
+  uint2 *rec6_arr = nullptr;  // the records this rank owns, in arrival order: 24-byte rows stored by the peers' push kernels
   u32 *key0_loc = nullptr, *tile_cnt = nullptr, *perm_x = nullptr, *perm_y = nullptr;
   u32 *key0a = nullptr, *k0_r = nullptr, *aidx_r = nullptr, *tmp_k = nullptr, *tmp_v = nullptr;
   void *sort_work = nullptr;
@@ -531,8 +532,8 @@ static u64 dist_carve(Dist &D, u8 *base) {
   D.cuts_x = (u32 *)take(2 * DIST_MAX_RANKS * 4);
   D.cuts_g = (u32 *)take((DIST_MAX_RANKS + 1) * 4);
   D.rec4_loc = (uint4 *)take(M * 32);
-  D.send_rows = (uint4 *)take(M * 32);
-  D.rec4_arr = (uint4 *)take(M * 32);
+  D.send_rows = (uint4 *)take(M * 16);
+  D.rec6_arr = (uint2 *)take(M * 24);
   D.recv_rows = (uint4 *)take(M * 16);
   D.key0_loc = (u32 *)take(M * 4);
   D.tile_cnt = (u32 *)take(dist_split_work_bytes(M));
@@ -842,8 +843,8 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   launches += dist_or_rows(pub_all + DIST_BINS + lxw, pub_words, nr, lyw, linky, st);
   // count per destination -> all ranks' counts on the device -> every tile stores its records straight into the owners'
   // receive buffers (peer memory over NVLink) -> barrier; the host reads the count matrix while the rows travel
-  uint4 *outs[DIST_MAX_RANKS];
-  peer_rows(D, D.rec4_arr, outs);
+  uint2 *outs[DIST_MAX_RANKS];
+  for (int d = 0; d < nr; ++d) outs[d] = d == me ? D.rec6_arr : D.tr->on_peer(d, D.rec6_arr);
   launches += dist_count_plain(D.key0_loc, (u32)n_use, D.cuts0, nr, g.vsize - 1, D.tile_cnt, D.d_small + W_CNT_A, st);
   CK(cudaMemcpyAsync(D.d_small + W_ERR, &D.cnt->err, sizeof(u32), cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(D.d_small + W_CUTS, D.cuts0, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
@@ -860,7 +861,7 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
     return dist_check_small(ctx, true);
   }
   D.ex1.from_matrix(D.h_small, W_CNT_A, nr, me);
-  D.tr->bytes_sent += (D.ex1.n_send - D.ex1.scnt[me]) * 32;  // (the rows this rank's kernels stored into peer memory)
+  D.tr->bytes_sent += (D.ex1.n_send - D.ex1.scnt[me]) * 24;  // (the rows this rank's kernels stored into peer memory)
   u64 m_total = 0, loaded_total = 0;
   u64 m_of[DIST_MAX_RANKS] = {0};
   for (int s = 0; s < nr; ++s) {
@@ -890,12 +891,12 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   const u32 key0_base = cuts0_h[me];
   const u64 key0_end = (me + 1 < nr && cuts0_h[me + 1] < g.vsize) ? cuts0_h[me + 1] : g.vsize;
   const int bits_rank_l = ceil_log2(key0_end > key0_base ? key0_end - key0_base : 1) < 1 ? 1 : ceil_log2(key0_end - key0_base);
-  launches += dist_key0_of_rec(D.rec4_arr, m, key0_base, D.key0a, hist_of(0, bits_rank_l), st);
+  launches += dist_key0_of_rec(D.rec6_arr, m, key0_base, D.key0a, hist_of(0, bits_rank_l), st);
   launches += launch_sort_pairs(D.key0a, nullptr, D.k0_r, D.aidx_r, D.tmp_k, D.tmp_v, m, bits_rank_l, D.sort_work, st, &D.cnt->err,
                                 m ? D.prehist : nullptr);
   CK(cudaEventRecord(ev[3], st));
-  launches += launch_keys(D.aidx_r, m, g, D.rec4_arr, linkx, linky, D.xl, D.yl_r, D.ys_r, D.kx2, D.ky, D.identity_r, st,
-                          HistOut{nullptr, 0, 0}, HistOut{nullptr, 0, 0}, D.gfidx_r, 1u);
+  launches += launch_keys(D.aidx_r, m, g, nullptr, linkx, linky, D.xl, D.yl_r, D.ys_r, D.kx2, D.ky, D.identity_r, st,
+                          HistOut{nullptr, 0, 0}, HistOut{nullptr, 0, 0}, D.gfidx_r, 1u, D.rec6_arr);
   launches += launch_hkey(D.k0_r, D.ys_r, m, nullptr, st, D.gfidx_r, D.identity_r, D.hfi_r);
   CK(cudaEventRecord(ev[4], st));
   // X halo: fragments whose X super-bucket belongs to a higher rank
@@ -1092,7 +1093,9 @@ static int dist_group(rk_ctx *ctx, double len_ratio, double pos_ratio, unsigned 
   launches += dist_cuts_gid(nroots, SMALL_WORDS, nr, D.cuts_g, D.d_small + W_X1, st);  // (the total; the cuts are replaced below)
   launches += dist_coarse_hist(D.gid_rank, m, shift_g, 0, 0xFFFFFFFFu, D.hist, st);
   TR(D.tr->all_gather(D.hist, D.hist_all, DIST_BINS * 4, st));
-  launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st, D.d_small + W_X1);
+  // no range may hold more lines than a rank has rows (RK_DIST_LINE_CAP: tests — a tighter bound than the capacity)
+  const u64 line_cap = getenv("RK_DIST_LINE_CAP") ? std::min<u64>(D.cap, strtoull(getenv("RK_DIST_LINE_CAP"), nullptr, 10)) : D.cap;
+  launches += dist_cuts_from_hist(D.hist_all, DIST_BINS, nr, shift_g, D.cuts_g, st, D.d_small + W_X1, line_cap);
   CK(cudaMemcpyAsync(D.d_small + W_CNT_B, D.cuts_g, (nr + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
   uint4 *outs[DIST_MAX_RANKS];
   peer_rows(D, D.recv_rows, outs);

@@ -175,10 +175,11 @@ int launch_sort_pairs(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32
 // rec4: file order, two 16-byte words per record {xStart, yStart, length, flags} {identity bits, 0, 0, 0} (one 32-byte
 // sector per gather); xl_r/yl_r: rank-order {center, length} per axis (one 8-byte gather per fragment in the match
 // kernels); identity_r: rank order.  Multi-GPU: gfidx_r = the record's global file index (second word of rec4), and with
-// own_bit the X key is written as 2*key+1 so that halo entries (2*key) of the same super-bucket sort before the rank's own
+// own_bit the X key is written as 2*key+1 so that halo entries (2*key) of the same super-bucket sort before the rank's own;
+// rec6 (instead of rec4): the 24-byte rows of exchange 1, {xStart, yStart} {length, flags} {identity, file index}
 int launch_keys(const u32 *fidx_r, u32 m, Geometry g, const uint4 *rec4, const u32 *link_x, const u32 *link_y, uint2 *xl_r,
                 uint2 *yl_r, u32 *ys_r, u32 *kx, u32 *ky, float *identity_r, cudaStream_t st, HistOut hist_x = HistOut{nullptr, 0, 0},
-                HistOut hist_y = HistOut{nullptr, 0, 0}, u32 *gfidx_r = nullptr, u32 own_bit = 0);
+                HistOut hist_y = HistOut{nullptr, 0, 0}, u32 *gfidx_r = nullptr, u32 own_bit = 0, const uint2 *rec6 = nullptr);
 
 // K3: one axis pass of generate_fragment_groups.  is_y: fragments with parent != NONE insert unconditionally.
 struct MatchArgs {
@@ -278,13 +279,13 @@ struct ScatterTable {                 // positions 0..n of a kernel's output in 
 };
 int dist_coarse_hist(const u32 *keys, u32 n, int shift, int pre_shift, u32 drop_key, u32 *hist, cudaStream_t st);
 int dist_cuts_from_hist(const u32 *hist_all, u64 row_stride, int nr, int shift, u32 *cuts, cudaStream_t st,
-                        const u32 *gid_total = nullptr);
+                        const u32 *gid_total = nullptr, u64 line_cap = 0);
 int dist_cuts_gid(const u32 *nroots, u32 stride, int nr, u32 *cuts, u32 *total, cudaStream_t st);
 int dist_cuts_x(const u32 *cuts0, int nr, Geometry g, const u32 *link_x, u32 *cuts_x, cudaStream_t st);
 u64 dist_split_work_bytes(u64 n);
 int dist_count_plain(const u32 *keys, u32 n, const u32 *cuts, int nr, u32 drop_key, u32 *tile_cnt, u32 *counts, cudaStream_t st,
                      const u32 *n_ptr = nullptr);
-int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint4 *const *outs, u32 out_cap,
+int dist_push_records(const u32 *key0, u32 n, const u32 *cuts, int nr, u32 drop_key, const uint4 *rec, uint2 *const *outs, u32 out_cap,
                       u32 *tile_cnt, const u32 *counts_all, u32 row_stride, int me, cudaStream_t st);
 int dist_push_gid(const u32 *gid_rank, const uint4 *hfi_r, u32 n, const u32 *cuts, int nr, uint4 *const *outs, u32 out_cap, u32 *tile_cnt,
                   const u32 *counts_all, u32 row_stride, int me, cudaStream_t st);
@@ -292,7 +293,7 @@ int dist_split_halo(const u32 *keys2, const uint2 *cl, u32 n, const u32 *cuts_x,
                     u32 out_cap, u32 *perm, u32 *tile_cnt, u32 *counts, cudaStream_t st);
 int dist_split_axis(const u32 *keys, const uint2 *cl, u32 n, const u32 *cuts, int nr, u32 rank_off, uint4 *out, u32 *perm,
                     u32 *tile_cnt, u32 *counts, cudaStream_t st);
-int dist_key0_of_rec(const uint4 *rec, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st);
+int dist_key0_of_rec(const uint2 *rec6, u32 n, u32 key_base, u32 *key0, HistOut ho, cudaStream_t st);
 int dist_unpack_axis_rows(const uint4 *rows, u32 n, u32 key_base, u32 *keys, uint2 *cl, u32 *grank, HistOut ho, cudaStream_t st);
 int dist_x_local_keys(u32 *keys2, u32 n, u32 nbx, const u32 *base, const u32 *range, HistOut ho, cudaStream_t st);
 int dist_unpack_halo_rows(const uint4 *rows, u32 n, u32 nbx, const u32 *base, const u32 *range, u32 *keys, uint2 *cl, u32 *grank, HistOut ho,

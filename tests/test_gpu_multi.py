@@ -71,6 +71,28 @@ def test_forest_bulk_rounds_match_oracle(monkeypatch, world, wl):
         _assert_same(m.group(0.5, 0.5), O.group(rec, w.lx + 1, w.ly + 1, 0.5, 0.5))
 
 
+@pytest.mark.parametrize("world,wl", [(8, "c2"), (3, "dense"), (5, "c2"), (2, "tiny")])
+def test_output_ranges_respect_the_row_capacity(monkeypatch, world, wl):
+    """the output ranges are cut by estimated sort_groups work, which gives the ranks with small groups more lines; no rank
+    may get more lines than it has rows for (RK_DIST_LINE_CAP stands in for a tight capacity)"""
+    w = _workload(wl)
+    rec = gen.generate(w)
+    g = O.group(rec, w.lx + 1, w.ly + 1, w.len_ratio, w.pos_ratio)
+    with capi.Multi([0] * world) as m:
+        m.load(rec, w.lx + 1, w.ly + 1)
+        m.group(w.len_ratio, w.pos_ratio)
+        free = max(m.info(r)["n_lines"] for r in range(world))
+    cap = -(-g.n_kept // world)
+    cap += cap // 8 + 64             # 12 % over an even split (the cuts fall on boundaries of 1/4096 of the group ids)
+    monkeypatch.setenv("RK_DIST_LINE_CAP", str(cap))
+    with capi.Multi([0] * world) as m:
+        m.load(rec, w.lx + 1, w.ly + 1)
+        _assert_same(m.group(w.len_ratio, w.pos_ratio), g)
+        lines = [m.info(r)["n_lines"] for r in range(world)]
+    assert sum(lines) == g.n_kept and max(lines) <= cap, (lines, cap)
+    print(f"largest range without the bound: {free} lines; bound {cap}; with it: {max(lines)}")
+
+
 def test_ranks_as_threads_unsorted_members():
     w = _workload("dense")
     rec = gen.generate(w)
