@@ -1,5 +1,8 @@
 #include "FragmentsDatabase.h"
 
+#include "GeckoFrags.h"
+
+#include <algorithm>
 #include <atomic>
 
 #include <cerrno>
@@ -190,7 +193,99 @@ std::vector<std::vector<FragFile>> parse_rows_parallel(const char *data, size_t 
   return out;
 }
 
-FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, const std::vector<int> &devices) {
+FragsHead read_frags_head(const char *data, size_t size, FragsInput input) {
+  FragsHead h;
+  h.binary = input == FragsInput::gecko_binary;
+  if (h.binary) {  // GeckoFrags.h: 16-byte header, 109-byte big-endian records
+    if (!gecko_frags_layout_ok(size))
+      throw std::runtime_error("repkiller-b200: not a GECKO binary fragments file (16-byte header + 109-byte records)");
+    uint64_t nx = 0, ny = 0;
+    gecko_frags_lengths((const unsigned char *)data, &nx, &ny);
+    h.total_frags = gecko_frags_count(size);
+    // the header the output file starts with: the 16 lines GECKO's CSV rendering of this file would carry
+    h.header = "All by-Identity Ungapped Fragments (Hits based approach)\n"
+               "[Abr.2015 -- < bitlab - Departamento de Arquitectura de Computadores >\n"
+               "SeqX filename : (binary fragments file)\nSeqY filename : (binary fragments file)\n"
+               "SeqX name : X\nSeqY name : Y\n"
+               "SeqX length : " + std::to_string(nx) + "\nSeqY length : " + std::to_string(ny) + "\n"
+               "Min.fragment.length : 0\nMin.Identity : 0.00\nTot Hits (seeds) : 0\nTot Hits (seeds) used: 0\n"
+               "Total fragments : " + std::to_string(h.total_frags) + "\n"
+               "========================================================\n"
+               "Type,xStart,yStart,xEnd,yEnd,strand(f/r),block,length,score,ident,similarity,%ident,SeqX,SeqY\n"
+               "========================================================\n";
+    h.seqx_len = nx + 1, h.seqy_len = ny + 1;  // like the CSV route: header value + 1 (:62,65)
+    h.body_pos = GECKO_FRAGS_HEADER_BYTES;
+    return h;
+  }
+  size_t pos = 0;
+  auto next_line = [&](std::string &out) {
+    const size_t s = pos;
+    while (pos < size && data[pos] != '\n') ++pos;
+    out.assign(data + s, pos - s);
+    if (pos < size) ++pos;
+  };
+  std::string line;
+  for (int ln = 1; ln <= 16; ++ln) {  // reference: :57-77
+    next_line(line);
+    h.header.append(line).append("\n");
+    if (ln == 7) h.seqx_len = (uint64_t)(value_after_colon(line) + 1);
+    if (ln == 8) h.seqy_len = (uint64_t)(value_after_colon(line) + 1);
+    if (ln == 13) h.total_frags = (uint64_t)value_after_colon(line);
+  }
+  h.body_pos = pos;
+  return h;
+}
+
+std::vector<std::vector<FragFile>> read_frags_records(const char *data, size_t size, const FragsHead &head, unsigned nthreads) {
+  // by all host cores (RK_PARSE_THREADS overrides the count)
+  if (nthreads == 0) {
+    nthreads = std::thread::hardware_concurrency();
+    if (nthreads < 1 || size - head.body_pos < (1u << 20)) nthreads = 1;
+    if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
+  }
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  if (!head.binary) return parse_rows_parallel(data, size, head.body_pos, nthreads);
+  // consecutive record ranges, byte-swapped
+  std::vector<std::vector<FragFile>> chunks(nthreads);
+  std::vector<std::thread> pool;
+  const uint64_t n = head.total_frags;
+  for (unsigned t = 0; t < nthreads; ++t) {
+    const uint64_t lo = n / nthreads * t + std::min<uint64_t>(t, n % nthreads), hi = n / nthreads * (t + 1) + std::min<uint64_t>(t + 1, n % nthreads);
+    if (hi > lo)
+      pool.emplace_back([&chunks, t, lo, hi, data] {
+        chunks[t].resize(hi - lo);
+        gecko_frags_decode((const unsigned char *)data, lo, hi - lo, chunks[t].data());
+      });
+  }
+  for (auto &th : pool) th.join();
+  return chunks;
+}
+
+FragsInput detect_frags_input(const std::string &path, std::ifstream &stream) {
+  if (const char *e = getenv("RK_INPUT_FORMAT")) {
+    if (!strcmp(e, "frags")) return FragsInput::gecko_binary;
+    if (!strcmp(e, "csv")) return FragsInput::csv;
+  }
+  static const char suffix[] = ".frags";
+  const size_t sl = sizeof suffix - 1;
+  if (path.size() < sl || path.compare(path.size() - sl, sl, suffix) != 0) return FragsInput::csv;
+  const std::streampos here = stream.tellg();
+  stream.seekg(0, std::ios::end);
+  const std::streampos fin = stream.tellg();
+  if (here == std::streampos(-1) || fin == std::streampos(-1) || fin < here) {
+    stream.clear();
+    return FragsInput::csv;
+  }
+  stream.seekg(here);
+  const int first = stream.peek();
+  stream.clear();
+  stream.seekg(here);
+  return (gecko_frags_layout_ok((size_t)(fin - here)) && first == 0) ? FragsInput::gecko_binary : FragsInput::csv;
+}
+
+FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager &seq_manager, const std::vector<int> &devices,
+                                     FragsInput input) {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   // CUDA start-up (a few hundred ms) runs beside the file read and the parse
@@ -226,43 +321,27 @@ FragmentsDatabase::FragmentsDatabase(std::ifstream &frags_file, sequence_manager
     }
   }
   const auto t1 = clk::now();
-  size_t pos = 0;
-  auto next_line = [&](std::string &out) {
-    const size_t s = pos;
-    while (pos < size && data[pos] != '\n') ++pos;
-    out.assign(data + s, pos - s);
-    if (pos < size) ++pos;
-  };
-  std::string line;
-  uint64_t total_frags = 0;
-  for (int ln = 1; ln <= 16; ++ln) {  // reference: :57-77
-    next_line(line);
-    header.append(line).append("\n");
-    if (ln == 7) seq_manager.sequences.emplace_back(0, (uint64_t)(value_after_colon(line) + 1));
-    if (ln == 8) seq_manager.sequences.emplace_back(1, (uint64_t)(value_after_colon(line) + 1));
-    if (ln == 13) total_frags = (uint64_t)value_after_colon(line);
-  }
+  const FragsHead head = read_frags_head(data, size, input);
+  header = head.header;
+  seq_manager.sequences.emplace_back(0, head.seqx_len);
+  seq_manager.sequences.emplace_back(1, head.seqy_len);
+  const uint64_t total_frags = head.total_frags;
   seq_manager.read_header(header);
   vsize = 1 + seq_manager.get_sequence_by_label(0).len / 10;  // :84
 
-  // the rows are parsed by all host cores (RK_PARSE_THREADS overrides the count)
-  unsigned nthreads = std::thread::hardware_concurrency();
-  const size_t body = size - pos;
-  if (nthreads < 1 || body < (1u << 20)) nthreads = 1;
-  if (const char *e = getenv("RK_PARSE_THREADS")) nthreads = (unsigned)atoi(e);
   // The device gets the compact form (rk_load_packed: 33 B per fragment over PCIe instead of the 109-byte record): pinned
   // memory for it is allocated beside the parse, for min(T, bytes / 28) records — a full GECKO row has 14 non-empty
   // fields and 13 commas, i.e. at least 30 bytes with its line end.  This is only a guess: readFragment's short-row
   // padding also accepts rows like "Frag,5" (7 bytes), so the count is checked after the parse and the buffers are
-  // re-allocated for exactly `accepted` records when the guess was too small.
-  const uint64_t rows_upper = body / 28 + 1;
+  // re-allocated for exactly `accepted` records when the guess was too small.  (A binary file states its count.)
+  const uint64_t rows_upper = head.binary ? total_frags : (size - head.body_pos) / 28 + 1;
   cap_ = (rows_upper < total_frags ? rows_upper : total_frags) + 2;
   create_thread.join();
   if (!ctx_ && !multi_) throw std::runtime_error(std::string("repkiller-b200: ") + rk_create_error());
   auto packed_bytes = [](uint64_t cap) { return cap * 33 + 64; };
   std::thread alloc_thread([this, &packed_bytes] { packed_ = (unsigned char *)rk_host_alloc(packed_bytes(cap_)); });
   Joiner alloc_joiner{alloc_thread};
-  std::vector<std::vector<FragFile>> chunks = parse_rows_parallel(data, size, pos, nthreads);
+  std::vector<std::vector<FragFile>> chunks = read_frags_records(data, size, head, 0);
   uint64_t accepted = 0;
   for (const auto &c : chunks) accepted += c.size();
   alloc_thread.join();

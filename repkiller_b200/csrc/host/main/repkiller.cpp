@@ -84,7 +84,8 @@ int main(int argc, char *argv[]) {
   const bool legacy_writer = legacy_env || devices.size() > 1;
 
   sequence_manager seq_manager;
-  FragmentsDatabase frag_db(frags_file, seq_manager, devices);
+  // (beside the reference's CSV: GECKO's binary .frags container, see FragmentsDatabase.h)
+  FragmentsDatabase frag_db(frags_file, seq_manager, devices, detect_frags_input(multifrags_path, frags_file));
   frags_file.close();
   if (timing) {
     const rk_load_stats &ls = frag_db.load_stats();

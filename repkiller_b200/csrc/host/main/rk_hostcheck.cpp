@@ -16,6 +16,15 @@
 //                                             sort_groups with an arbitrary diag_func table against std::sort with the
 //                                             reference's comparator (commonFunctions.cpp:148-159) on the same lists (GPU)
 //   rk_hostcheck buckets <in.csv> <out.bin>   the records visited by begin()..end(), in visiting order (GPU)
+//   rk_hostcheck tofrags <in.csv> <out.frags> the accepted records of a CSV as a GECKO binary file (GeckoFrags.h; no GPU)
+//   rk_hostcheck fragsbin <in.frags> <out.bin>
+//                                             the records a binary file loads as, 109 B each; prints "<seqX length>
+//                                             <seqY length> <records>" (no GPU)
+//   rk_hostcheck ingest <in> <out.bin> <out.header> [threads]
+//                                             the input stage of the FragmentsDatabase constructor (detect_frags_input,
+//                                             read_frags_head, read_frags_records) on a CSV or a .frags file: records,
+//                                             header text; prints "<seqX len> <seqY len> <stated records> <binary>" (no GPU)
+// Every mode that builds a FragmentsDatabase takes a CSV or a .frags file (detect_frags_input).
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -27,6 +36,7 @@
 #include <vector>
 
 #include "../FragmentsDatabase.h"
+#include "../GeckoFrags.h"
 #include "../SaverQueue.h"
 #include "../commonFunctions.h"
 
@@ -77,6 +87,63 @@ int main(int argc, char **argv) {
     fclose(f);
     return 0;
   }
+  if (mode == "tofrags") {
+    std::string header;
+    std::vector<FragFile> recs = parse_rows(argv[2], &header);
+    uint64_t len[2] = {0, 0};
+    size_t pos = 0;
+    for (int ln = 1; ln <= 8; ++ln) {  // lines 7 and 8: "SeqX length : N", "SeqY length : N"
+      const size_t e = header.find('\n', pos);
+      const std::string line = header.substr(pos, e - pos);
+      if (ln >= 7) len[ln - 7] = (uint64_t)atoll(line.c_str() + line.find(':') + 1);
+      pos = e + 1;
+    }
+    std::vector<unsigned char> file(GECKO_FRAGS_HEADER_BYTES + recs.size() * sizeof(FragFile));
+    gecko_frags_encode(len[0], len[1], recs.data(), recs.size(), file.data());
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 3;
+    fwrite(file.data(), 1, file.size(), f);
+    fclose(f);
+    return 0;
+  }
+  if (mode == "fragsbin") {
+    std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+    std::vector<unsigned char> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    if (!gecko_frags_layout_ok(file.size())) return 4;
+    uint64_t nx, ny;
+    gecko_frags_lengths(file.data(), &nx, &ny);
+    const uint64_t n = gecko_frags_count(file.size());
+    std::vector<FragFile> recs(n);
+    gecko_frags_decode(file.data(), 0, n, recs.data());
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 3;
+    if (n) fwrite(recs.data(), sizeof(FragFile), n, f);
+    fclose(f);
+    printf("%llu %llu %llu\n", (unsigned long long)nx, (unsigned long long)ny, (unsigned long long)n);
+    return 0;
+  }
+  if (mode == "ingest" && argc >= 5) {
+    std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
+    if (!in) return 3;
+    const FragsInput input = detect_frags_input(argv[2], in);
+    std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    try {
+      const FragsHead head = read_frags_head(data.data(), data.size(), input);
+      const auto chunks = read_frags_records(data.data(), data.size(), head, argc >= 6 ? (unsigned)atoi(argv[5]) : 0);
+      FILE *f = fopen(argv[3], "wb");
+      if (!f) return 3;
+      for (const auto &c : chunks)
+        if (!c.empty()) fwrite(c.data(), sizeof(FragFile), c.size(), f);
+      fclose(f);
+      std::ofstream(argv[4], std::ofstream::binary) << head.header;
+      printf("%llu %llu %llu %d\n", (unsigned long long)head.seqx_len, (unsigned long long)head.seqy_len,
+             (unsigned long long)head.total_frags, (int)head.binary);
+    } catch (const std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 4;
+    }
+    return 0;
+  }
   if (mode == "floatcheck") {
     uint64_t rng = 88172645463325252ull ^ (uint64_t)atoll(argv[3]);
     auto nx = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
@@ -121,7 +188,7 @@ int main(int argc, char **argv) {
   if (mode == "steps" && argc >= 6) {
     std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
     sequence_manager sm;
-    FragmentsDatabase db(in, sm);
+    FragmentsDatabase db(in, sm, 0, detect_frags_input(argv[2], in));
     FGList groups;
     generate_fragment_groups(db, groups, sm, std::stod(argv[4]), std::stod(argv[5]));
     std::vector<size_t> diag(db.getA());
@@ -133,7 +200,7 @@ int main(int argc, char **argv) {
   if (mode == "steps_pure" && argc >= 8) {
     std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
     sequence_manager sm;
-    FragmentsDatabase db(in, sm);
+    FragmentsDatabase db(in, sm, 0, detect_frags_input(argv[2], in));
     FGList groups, other;
     generate_fragment_groups(db, groups, sm, std::stod(argv[4]), std::stod(argv[5]));
     generate_fragment_groups(db, other, sm, std::stod(argv[6]), std::stod(argv[7]));  // leaves ITS state on the device
@@ -147,7 +214,7 @@ int main(int argc, char **argv) {
   if (mode == "sort_any" && argc >= 5) {
     std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
     sequence_manager sm;
-    FragmentsDatabase db(in, sm);
+    FragmentsDatabase db(in, sm, 0, detect_frags_input(argv[2], in));
     FGList groups;
     generate_fragment_groups(db, groups, sm, std::stod(argv[3]), std::stod(argv[4]));
     std::vector<size_t> diag(db.getA());
@@ -176,7 +243,7 @@ int main(int argc, char **argv) {
   if (mode == "buckets" && argc >= 4) {
     std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
     sequence_manager sm;
-    FragmentsDatabase db(in, sm);
+    FragmentsDatabase db(in, sm, 0, detect_frags_input(argv[2], in));
     FILE *f = fopen(argv[3], "wb");
     if (!f) return 3;
     for (const auto &fl : db)

@@ -6,6 +6,10 @@ diag i64@0, xStart u64@8, yStart u64@16, xEnd u64@24, yEnd u64@32, length u64@40
 score u64@56, similarity f32@64, seqX u64@68, seqY u64@76, block i64@84, strand char@92,
 evalue long double@93 (16 opaque bytes).
 
+GECKO's binary container (``.frags``; csrc/host/GeckoFrags.h, SURVEY.md §8f N4 — not read by the reference, restated from
+GECKO's published writer): two big-endian uint64 sequence lengths, then the same 109-byte records with every field stored
+most significant byte first.
+
 The CSV container is what the reference's ``FragmentsDatabase`` constructor reads
 (/root/reference/src/FragmentsDatabase.cpp:54-101): 16 header lines (line 7 ``SeqX length``, line 8
 ``SeqY length``, line 13 ``Total fragments``), then one ``Frag,...`` row per fragment.
@@ -78,3 +82,48 @@ def write_csv(path: str, rec: np.ndarray, lx_header: int, ly_header: int, total_
     with open(path, "w", encoding="latin1", newline="") as f:
         f.write(make_header(lx_header, ly_header, rec.shape[0] if total_frags is None else total_frags))
         f.write(records_to_csv_rows(rec))
+
+
+# ---- GECKO's binary container (.frags) ----------------------------------------------------------------------------------
+FRAG_DTYPE_BE = np.dtype(
+    {
+        "names": FRAG_DTYPE.names,
+        "formats": [">i8", ">u8", ">u8", ">u8", ">u8", ">u8", ">u8", ">u8", ">f4", ">u8", ">u8", ">i8", "S1", "V16"],
+        "offsets": [0, 8, 16, 24, 32, 40, 48, 56, 64, 68, 76, 84, 92, 93],
+        "itemsize": FRAG_BYTES,
+    }
+)
+GECKO_HEADER_BYTES = 16
+
+
+def records_to_gecko_binary(rec: np.ndarray, seqx_len: int, seqy_len: int) -> bytes:
+    """header (two big-endian uint64) + every record with its fields byte-reversed (``evalue`` included)"""
+    be = np.zeros(rec.shape[0], dtype=FRAG_DTYPE_BE)
+    for name in FRAG_DTYPE.names:
+        if name != "evalue":
+            be[name] = rec[name]
+    ev = np.ascontiguousarray(rec["evalue"]).view(np.uint8).reshape(-1, 16)[:, ::-1]
+    be["evalue"] = np.ascontiguousarray(ev).view("V16").reshape(-1)
+    return int(seqx_len).to_bytes(8, "big") + int(seqy_len).to_bytes(8, "big") + be.tobytes()
+
+
+def write_gecko_binary(path: str, rec: np.ndarray, seqx_len: int, seqy_len: int) -> None:
+    with open(path, "wb") as f:
+        f.write(records_to_gecko_binary(rec, seqx_len, seqy_len))
+
+
+def gecko_binary_as_loaded(data: bytes) -> tuple[np.ndarray, int, int]:
+    """What a .frags file loads as (GeckoFrags.h): the record ``readFragment`` builds from a CSV row printing the stored values
+    (/root/reference/src/FragmentsDatabase.cpp:30-43) — ident := trunc(similarity), diag := xStart - yStart, seqX 0, seqY 1,
+    evalue 0 — and the two sequence lengths of the header."""
+    if len(data) < GECKO_HEADER_BYTES or (len(data) - GECKO_HEADER_BYTES) % FRAG_BYTES:
+        raise ValueError("not a GECKO binary fragments file")
+    lx, ly = int.from_bytes(data[:8], "big"), int.from_bytes(data[8:16], "big")
+    be = np.frombuffer(data, dtype=FRAG_DTYPE_BE, offset=GECKO_HEADER_BYTES)
+    rec = empty_records(be.shape[0])
+    for name in ("xStart", "yStart", "xEnd", "yEnd", "length", "score", "similarity", "block", "strand"):
+        rec[name] = be[name]
+    rec["diag"] = (rec["xStart"].astype(np.int64) - rec["yStart"].astype(np.int64))
+    rec["ident"] = rec["similarity"].astype(np.uint64)   # (finite, non-negative similarities: what GECKO stores)
+    rec["seqX"], rec["seqY"] = 0, 1
+    return rec, lx, ly

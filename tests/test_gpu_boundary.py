@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from repkiller_b200 import gen
+from repkiller_b200 import frags, gen
 from repkiller_b200.frags import FRAG_DTYPE, make_header
 
 pytestmark = pytest.mark.gpu
@@ -139,3 +139,28 @@ def test_cli_over_several_ranks(tmp_path, medium_cases):
     p = subprocess.run([CLI, str(inp), str(outp), "0.05", "0.05"], capture_output=True, env=dict(os.environ, RK_DEVICES="0,0,0"))
     assert p.returncode == 0, p.stderr
     assert hashlib.md5(outp.read_bytes()).hexdigest() == c["ref_md5"]
+
+
+def test_cli_reads_geckos_binary_container(tmp_path, medium_cases):
+    """SURVEY §8f N4 (parity unpinned: the reference reads CSV only).  A .frags file — 16-byte header, 109-byte big-endian
+    records (csrc/host/GeckoFrags.h) — loads as its CSV rendering does, so the CLI writes the lines the reference wrote for
+    that CSV (md5 of the golden set, header excluded: a binary file carries no header text), on one GPU and over three ranks."""
+    c = medium_cases["c1"]
+    w = gen.Workload(**c["workload"])
+    rec = gen.generate(w)
+    csv_in, bin_in = tmp_path / "c1.csv", tmp_path / "c1.frags"
+    O.write_input_csv(str(csv_in), rec, w.lx, w.ly)
+    frags.write_gecko_binary(str(bin_in), rec, w.lx, w.ly)
+    out_csv = tmp_path / "from_csv.out"
+    p = subprocess.run([CLI, str(csv_in), str(out_csv), "0.05", "0.05"], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    assert hashlib.md5(out_csv.read_bytes()).hexdigest() == c["ref_md5"]
+    body = out_csv.read_bytes().split(b"\n", 16)[16]
+    for env in ({}, {"RK_DEVICES": "0,0,0"}):
+        out_bin = tmp_path / "from_bin.out"
+        p = subprocess.run([CLI, str(bin_in), str(out_bin), "0.05", "0.05"], capture_output=True, env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr
+        lines = out_bin.read_bytes().split(b"\n", 16)
+        assert lines[16] == body, env
+        assert lines[6] == b"SeqX length : %d" % w.lx and lines[7] == b"SeqY length : %d" % w.ly
+        assert lines[12] == b"Total fragments : %d" % w.n
