@@ -469,12 +469,10 @@ struct Dist {
   // state of the last load
   bool loaded = false;
   Geometry g{};
-  int bits_rank = 1, bits_x = 1, bits_y = 1;
-  u64 n_loc = 0, file_off = 0;
+  int bits_rank = 1, bits_y = 1;
   u32 m_loc = 0, rank_off = 0, n_halo = 0, n_away = 0, m_y = 0;
   u64 m_total = 0, n_total_loaded = 0;
   Exchange ex1, exh, exy;
-  const u8 *aos_dev = nullptr;
 
   // carved device pointers
   Counters *cnt = nullptr;
@@ -777,7 +775,6 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
   const Geometry g = make_geometry(seqx_len, seqy_len);
   D.g = g;
   D.bits_rank = ceil_log2(g.vsize) < 1 ? 1 : ceil_log2(g.vsize);
-  D.bits_x = ceil_log2(2ull * g.nbx);
   D.bits_y = ceil_log2(2ull * g.nby);
   const u64 lxw = (2ull * g.nbx + 31) / 32 + 1, lyw = (2ull * g.nby + 31) / 32 + 1, lmax = lxw > lyw ? lxw : lyw;
   const u64 pub_words = DIST_BINS + lxw + lyw;  // what a rank publishes after K1: its xStart/10 histogram and its link maps
@@ -815,8 +812,6 @@ static int dist_load(rk_ctx *ctx, const void *frags, u64 n_loc, u64 file_off, u6
     CK(cudaMemcpyAsync(D.aos_buf, frags, n_use * RK_FRAG_BYTES, cudaMemcpyHostToDevice, st));
     aos = D.aos_buf;
   }
-  D.aos_dev = aos;
-  D.n_loc = n_use, D.file_off = file_off;
   CK(cudaEventRecord(ev[1], st));
   u64 launches = 0;
 
