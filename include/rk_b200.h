@@ -227,7 +227,11 @@ typedef struct {
   uint64_t bytes_sent;    /* payload this rank sent to other ranks during the call */
 } rk_dist_info;
 int rk_dist_unique_id(void *id128);
-/* cap_per_rank: rows of workspace per GPU (the same on every rank; about 1.3 x the fragments per GPU) */
+/* cap_per_rank: rows of workspace per GPU, the same on every rank; 1.5 x the fragments per GPU + 65536 is what
+ * rk_create_multi and bench.py use.  It bounds what ONE rank may own at any stage: the records of its xStart/10 range, the
+ * rows of its Y range, and the output lines of its group-id range (a group is never split: a comparison whose largest
+ * group alone exceeds the capacity needs a larger one).  A stage that would exceed it fails on every rank with
+ * RK_ERR_NOMEM and a message naming the rank and the count; nothing is truncated. */
 int rk_dist_init(rk_ctx *ctx, int rank, int nranks, const void *id128, uint64_t cap_per_rank);
 int rk_dist_export(rk_ctx *ctx, void *blob);
 int rk_dist_import(rk_ctx *ctx, const void *blobs /* nranks x RK_DIST_BLOB_BYTES, in rank order */);
