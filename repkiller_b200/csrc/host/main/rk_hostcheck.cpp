@@ -25,6 +25,7 @@
 //                                             read_frags_head, read_frags_records) on a CSV or a .frags file: records,
 //                                             header text; prints "<seqX len> <seqY len> <stated records> <binary>" (no GPU)
 // Every mode that builds a FragmentsDatabase takes a CSV or a .frags file (detect_frags_input).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -126,10 +127,16 @@ int main(int argc, char **argv) {
     std::ifstream in(argv[2], std::ifstream::in | std::ifstream::binary);
     if (!in) return 3;
     const FragsInput input = detect_frags_input(argv[2], in);
-    std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    in.seekg(0, std::ios::end);
+    std::string data((size_t)in.tellg(), '\0');
+    in.seekg(0);
+    in.read(&data[0], (std::streamsize)data.size());
     try {
+      const auto t0 = std::chrono::steady_clock::now();
       const FragsHead head = read_frags_head(data.data(), data.size(), input);
       const auto chunks = read_frags_records(data.data(), data.size(), head, argc >= 6 ? (unsigned)atoi(argv[5]) : 0);
+      if (getenv("RK_TIMING"))
+        fprintf(stderr, "[rk] records_ms=%.1f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
       FILE *f = fopen(argv[3], "wb");
       if (!f) return 3;
       for (const auto &c : chunks)
